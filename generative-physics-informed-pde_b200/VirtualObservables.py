@@ -1,0 +1,661 @@
+"""Virtual observables for the B200 physics layer (API surface of bottleneck/VirtualObservables.py).
+
+Design (not the reference's): the reference keeps one Python object per data point, each holding a
+dense Gamma = V^T K assembled on the CPU from a FEniCS/scipy CSR matrix, and loops over them
+(VirtualObservables.py:61-69, 642-669, 891-898, 971-998).  Here
+
+  * the fine operator is never assembled: r = V^T (K_fom(a) u~ - f) and q = K_ff(a) (V s) are launches
+    of the matrix-free kernels in csrc/vo.cu (``VoPlan.residual`` / ``VoPlan.residual_T``);
+  * Gamma and alpha, where the reference API exposes them, are produced on the device by those same
+    kernels: Gamma^T = K_ff V is ``residual_T`` applied to the identity, alpha = -r(y = 0);
+  * an ensemble conditions all its data points in one batched pass (``condition_gaussian``) and
+    evaluates all residuals in one launch; the per-data-point classes are thin views kept for
+    callers that index into the ensemble (generative.py:198-207, training.py:320-339).
+
+The names the reference's callers use are kept: QuerryPoint(.x/.bc/.K/.f/.construct_querry_weak_galerkin),
+QuerryPointEnsemble, the samplers, LinearQuerry(.Gamma/.GammaTransposed/.alpha/.m/.resample),
+QuerryEnsemble.FromQuerryPointEnsemble, VirtualObservable(.update/.mean/.vars/.vo_variances),
+VirtualObservablesEnsemble(.update/.mean/.vars/.logsigma/.resample/.N/.m/.dim_out) and the temperature
+schedules.  Flux test functions (bottleneck/flux.py) need UFL facet integrals and stay out of scope.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import fem
+
+_F64 = torch.float64
+
+
+def _as_f64(value, device):
+    return torch.as_tensor(value, dtype=_F64, device=device)
+
+
+# ======================================================================================= device plan
+class VoPlan(object):
+    """One gpde_vo_plan: fine-mesh element data and the Dirichlet map, resident on a device."""
+
+    def __init__(self, physics, device, cell_to_input=None, n_inputs=None, load=None):
+        self._lib = _lib.load()
+        self.device = _lib.require_cuda(device, "virtual observables")
+        mesh = physics.mesh
+        if cell_to_input is None:
+            cell_to_input, n_inputs = np.arange(mesh.num_cells), mesh.num_cells
+        host = dict(
+            cells=np.ascontiguousarray(mesh.cells, dtype=np.int32),
+            Ke=np.ascontiguousarray(mesh.element_stiffness(), dtype=np.float64),
+            c2i=np.ascontiguousarray(cell_to_input, dtype=np.int32),
+            free=np.ascontiguousarray(physics.free_dofs, dtype=np.int64),
+            bc=np.ascontiguousarray(physics.constrained_dofs, dtype=np.int64),
+        )
+        if load is not None:
+            host["load"] = np.ascontiguousarray(load, dtype=np.float64)
+        p = {k: v.ctypes.data_as(ctypes.c_void_p) for k, v in host.items()}
+        self.handle = ctypes.c_void_p()
+        rc = self._lib.gpde_vo_plan_create(ctypes.byref(self.handle), mesh.num_nodes, mesh.num_cells, p["cells"],
+                                           p["Ke"], p["c2i"], int(n_inputs), p["free"], host["free"].size, p["bc"],
+                                           host["bc"].size, p.get("load"), self.device.index)
+        _lib.check(rc, "gpde_vo_plan_create")
+        info = (ctypes.c_int64 * 8)()
+        _lib.check(self._lib.gpde_vo_plan_info(self.handle, info), "gpde_vo_plan_info")
+        self.n_nodes, self.n_cells, self.n_inputs, self.d, self.n_bc, self.slots_per_row = (int(v) for v in info[:6])
+        self._scratch = None
+
+    def __del__(self):
+        handle, self.handle = getattr(self, "handle", None), None
+        if handle:
+            try:
+                self._lib.gpde_vo_plan_destroy(handle)
+            except Exception:
+                pass
+
+    @classmethod
+    def cached(cls, physics, device, pixel_input=False):
+        """Plans are immutable; one per (physics, device, input layout) is kept on the physics object."""
+        device = _lib.require_cuda(device, "virtual observables")
+        store = physics.__dict__.setdefault("_gpde_vo_plans", {})
+        key = (device.index, bool(pixel_input))
+        if key not in store:
+            if pixel_input:
+                store[key] = cls(physics, device, physics.mesh.pixel_of_cell(), physics.mesh.nx * physics.mesh.ny)
+            else:
+                store[key] = cls(physics, device)
+        return store[key]
+
+    def _workspace(self, B, m):
+        need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, B, m)))
+        if self._scratch is None or self._scratch.numel() < need:
+            self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._scratch
+
+    def residual(self, a, y, g, V, *, a_is_log=True, want_rho=False, ignore_load=False):
+        """r[B,m] = V^T (K(a_b) u~_b - f)_free with u~ = (y on free dofs, g on Dirichlet dofs).
+
+        a [B,n_inputs] or [n_inputs] (shared); y [B,d] or None (zeros); g [B,n_bc], [n_bc] or None;
+        V [d,m] or None (then only rho[B,d], the fine residual itself, is produced).
+        Returns r, or (r, rho) when want_rho / V is None."""
+        dt = a.dtype
+        sfx = _lib.suffix(dt)
+        B = y.shape[0] if y is not None else (a.shape[0] if a.dim() == 2 else 1)
+        a = a.contiguous()
+        y = None if y is None else y.to(dt).contiguous()
+        g = None if g is None else g.to(dt).contiguous()
+        m = 0 if V is None else int(V.shape[1])
+        Vc = None if V is None else V.to(dt).contiguous()
+        r = a.new_empty((B, m)) if m else None
+        rho = a.new_empty((B, self.d)) if (want_rho or not m) else None
+        fn = getattr(self._lib, "gpde_vo_residual_" + sfx)
+        rc = fn(self.handle, _lib.ptr(a), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(y),
+                _lib.ptr(g), (self.n_bc if g.dim() == 2 else 0) if g is not None else 0, _lib.ptr(Vc), m,
+                _lib.ptr(r), _lib.ptr(rho), _lib.ptr(self._workspace(B, m)) if m else None,
+                1 if ignore_load else 0, B, _lib.stream_of(a.device))
+        _lib.check(rc, "gpde_vo_residual_" + sfx)
+        return (r, rho) if rho is not None else r
+
+    def residual_T(self, a, V, s, *, a_is_log=True):
+        """q[B,d] = K_ff(a_b) (V s_b)  (= Gamma_b^T s_b)."""
+        dt = a.dtype
+        sfx = _lib.suffix(dt)
+        a, s, Vc = a.contiguous(), s.to(dt).contiguous(), V.to(dt).contiguous()
+        B, m = s.shape
+        q = a.new_empty((B, self.d))
+        fn = getattr(self._lib, "gpde_vo_residual_T_" + sfx)
+        rc = fn(self.handle, _lib.ptr(a), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(Vc), m,
+                _lib.ptr(s), _lib.ptr(q), _lib.ptr(self._workspace(B, m)), B, _lib.stream_of(a.device))
+        _lib.check(rc, "gpde_vo_residual_T_" + sfx)
+        return q
+
+
+class VoResidualFn(torch.autograd.Function):
+    """r = V^T (K(a) u~ - f), differentiable in y: dL/dy = K_ff(a) V gbar_r (one residual_T launch)."""
+
+    @staticmethod
+    def forward(ctx, y, a, g, V, plan, a_is_log):
+        ctx.plan, ctx.a_is_log = plan, a_is_log
+        ctx.save_for_backward(a, V)
+        return plan.residual(a, y, g, V, a_is_log=a_is_log)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gbar_r):
+        a, V = ctx.saved_tensors
+        return ctx.plan.residual_T(a, V, gbar_r.contiguous(), a_is_log=ctx.a_is_log), None, None, None, None, None
+
+
+def condition_gaussian(Gamma, alpha, noise_var, g, prec):
+    """Posterior of y ~ N(g, diag(1/prec)) given Gamma y = alpha + eps, eps ~ N(0, diag(noise_var)).
+
+    Batched over the leading axis: Gamma [N,m,d], alpha [N,m], noise_var [m], g/prec [N,d].
+    Same algebra as VirtualObservable.update (VirtualObservables.py:656-669):
+        Lambda = Gamma C Gamma^T + Sigma,  mean = g - C Gamma^T Lambda^-1 (Gamma g - alpha),
+        vars = diag(C) - diag(C Gamma^T Lambda^-1 Gamma C)."""
+    C = 1.0 / prec
+    GC = Gamma * C.unsqueeze(-2)                                   # [N,m,d]
+    Lam = GC @ Gamma.transpose(-1, -2) + torch.diag(noise_var)
+    chol = torch.linalg.cholesky(Lam)
+    resid = (Gamma @ g.unsqueeze(-1)).squeeze(-1) - alpha          # [N,m]
+    sol = torch.cholesky_solve(resid.unsqueeze(-1), chol)          # Lambda^-1 resid
+    mean = g - (GC.transpose(-1, -2) @ sol).squeeze(-1)
+    Z = torch.cholesky_solve(GC, chol)                             # Lambda^-1 Gamma C
+    return mean, C - (GC * Z).sum(dim=-2)
+
+
+# ======================================================================================= query points
+class QuerryPoint(object):
+    """One data point of the virtual-observable set: fine log-conductivity ``x`` (one value per DG0
+    cell) and its boundary condition ``bc``   (VirtualObservables.py:8-69)."""
+
+    def __init__(self, physics, x, bc, device=None):
+        assert isinstance(x, np.ndarray) and x.ndim == 1
+        assert not isinstance(physics, dict)
+        assert physics.dim_in == x.size
+        self._physics, self._x, self._bc, self._device = physics, x, bc, device
+        self._host_system = None
+
+    physics = property(lambda self: self._physics)
+    bc = property(lambda self: self._bc)
+    x = property(lambda self: self._x, doc="log-conductivity (the reference's naming)")
+    dim_in = property(lambda self: self._x.size)
+    dim_out = property(lambda self: self._physics.dim_out)
+
+    def _assemble_system(self):
+        # host scipy CSR, API parity only (VirtualObservables.py:57-59); the device path never forms K
+        if self._host_system is None:
+            self._host_system = self._physics.assemble_system(np.exp(self._x), bc=self._bc, only_free_dofs=True)
+        return self._host_system
+
+    K = property(lambda self: self._assemble_system()[0])
+    f = property(lambda self: self._assemble_system()[1])
+
+    def dirichlet_values(self):
+        return self._bc.constrained_dofs_values(self._physics.identifier)
+
+    def weak_galerkin_on_device(self, V, device=None):
+        """(Gamma [m,d], alpha [m]) as float64 device tensors via the matrix-free kernels."""
+        device = device if device is not None else self._device
+        if device is None and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = _lib.require_cuda(device if device is not None else "cpu", "QuerryPoint")
+        plan = VoPlan.cached(self._physics, device)
+        Vd = _as_f64(V, device)
+        assert Vd.shape[0] == self.dim_out
+        a = _as_f64(self._x, device)
+        Gamma = plan.residual_T(a, Vd, torch.eye(Vd.shape[1], dtype=_F64, device=device))
+        alpha = -plan.residual(a, None, _as_f64(self.dirichlet_values(), device), Vd)
+        load = self._bc.assemble_vanilla_force_vector(self._physics.identifier)
+        if np.any(load != 0):   # the cached plan carries no load vector: add V^T f_free
+            alpha = alpha + Vd.t() @ _as_f64(load[self._physics.free_dofs], device)
+        return Gamma, alpha.reshape(-1)
+
+    def construct_querry_weak_galerkin(self, V):
+        """numpy (Gamma, alpha) like VirtualObservables.py:61-69."""
+        Gamma, alpha = self.weak_galerkin_on_device(V)
+        return Gamma.cpu().numpy(), alpha.cpu().numpy()
+
+
+class QuerryPointEnsemble(object):
+    """VirtualObservables.py:72-116."""
+
+    def __init__(self, QPs):
+        self._QPs = list(QPs)
+
+    def __iter__(self):
+        return iter(self._QPs)
+
+    def __getitem__(self, item):
+        return self._QPs[item]
+
+    def __len__(self):
+        return len(self._QPs)
+
+    N = property(lambda self: len(self._QPs))
+    dim_out = property(lambda self: self._QPs[0].dim_out)
+
+    def X(self, dtype, device):
+        return torch.tensor(np.stack([qp.x for qp in self._QPs]), dtype=dtype, device=device)
+
+    def dirichlet_values(self, dtype, device):
+        return torch.tensor(np.stack([qp.dirichlet_values() for qp in self._QPs]), dtype=dtype, device=device)
+
+    @classmethod
+    def FromArrays(cls, X_DG, BCE, physics, device=None):
+        X_DG = X_DG.detach().cpu().numpy() if isinstance(X_DG, torch.Tensor) else np.asarray(X_DG)
+        assert X_DG.dtype == np.float64
+        return cls(QuerryPoint(physics, X_DG[n].ravel(), BCE[n], device=device) for n in range(X_DG.shape[0]))
+
+    @classmethod
+    def FromDataSet(cls, dataset, physics):
+        X_DG = dataset.get('X_DG')
+        assert X_DG.dtype == torch.double
+        return cls.FromArrays(X_DG, dataset.get('BCE'), physics)
+
+
+# ======================================================================================= samplers
+class BaseSampler(object):
+    """Produces the weighting matrix V [d,m] of one data point and its (Gamma, alpha).
+    precision_mask: -1 = infinite precision, +1 = learnable (VirtualObservables.py:120-168)."""
+
+    is_constant = False
+
+    def __init__(self, qp):
+        self._qp = qp
+
+    qp = property(lambda self: self._qp)
+    dim = property(lambda self: self.qp.dim_out)
+    fixed_precision = property(lambda self: bool(np.all(self.precision_mask < 0)))
+    precision_mask = property(lambda self: -np.ones(self.m))
+
+    def sample_V(self):
+        return self._sample()
+
+    def sample(self):
+        return self.qp.weak_galerkin_on_device(self._sample())
+
+    def __call__(self):
+        return self.sample()
+
+
+class ConstLengthScaleGenerator(object):
+    def __init__(self, l):
+        self._l = l
+
+    def __call__(self):
+        return self._l
+
+
+class RadialBasisFunctionSampler(BaseSampler):
+    """exp(-|x-r0|^2/l^2) with r0 ~ U[0,1]^2 at the fine free nodes (VirtualObservables.py:172-228,
+    fawkes/Expressions.py:26-31): nodal interpolation of a P1 function is evaluation at the nodes."""
+
+    def __init__(self, qp, l, N_aux):
+        super().__init__(qp)
+        assert l is not None
+        self._rows, self._l, self.m = qp.bc.free_dofs('fom'), l, N_aux
+
+    def _sample(self):
+        centres = np.array([[np.random.uniform(), np.random.uniform()] for _ in range(self.m)])
+        return fem.rbf_weighting(self.qp.physics.mesh, self._rows, centres, self._l)
+
+
+class GaussianSketchingSampler(BaseSampler):
+    """i.i.d. N(0,1) weighting vectors (VirtualObservables.py:230-258)."""
+
+    def __init__(self, qp, N_aux):
+        super().__init__(qp)
+        self.m = N_aux
+
+    def _sample(self):
+        return np.stack([np.random.normal(0, 1, self.qp.dim_out) for _ in range(self.m)], axis=1)
+
+
+class CoarseGrainedResidualSampler(BaseSampler):
+    """V = W, constant (VirtualObservables.py:297-321)."""
+
+    is_constant = True
+
+    def __init__(self, qp, W):
+        super().__init__(qp)
+        self._W = W
+        self._cached = qp.weak_galerkin_on_device(W)
+        self.m = int(self._cached[1].numel())
+
+    def _sample(self):
+        return self._W
+
+    def sample(self):
+        return self._cached
+
+
+class ConcatenatedSamplers(BaseSampler):
+    """Columns of several samplers side by side (VirtualObservables.py:260-294); one device pass."""
+
+    def __init__(self, samplers):
+        super().__init__(None)
+        self._samplers = list(samplers)
+
+    qp = property(lambda self: self._samplers[0].qp)
+    m = property(lambda self: sum(s.m for s in self._samplers))
+    is_constant = property(lambda self: all(s.is_constant for s in self._samplers))
+    precision_mask = property(lambda self: np.concatenate([s.precision_mask for s in self._samplers]))
+
+    def _sample(self):
+        return np.hstack([s.sample_V() for s in self._samplers])
+
+
+class FluxConstrainSampler(BaseSampler):
+    def __init__(self, qp, FluxConstrain):
+        raise NotImplementedError('flux test functions need FEniCS facet integrals (bottleneck/flux.py)')
+
+
+# ======================================================================================= linear query
+class LinearQuerry(object):
+    """Holds Gamma [m,d], Gamma^T and alpha [m] of one data point as float64 device tensors
+    (VirtualObservables.py:353-447)."""
+
+    def __init__(self, querry_point, sampler, dtype, device):
+        self._querry_point, self._sampler = querry_point, sampler
+        self.dtype, self.device = dtype, device
+        self._store = {}
+        self.resample(ForceResample=True)
+
+    def _f64_slot(name):
+        def get(self):
+            return self._store.get(name)
+
+        def put(self, value):
+            assert value.dtype == torch.double
+            self._store[name] = value
+        return property(get, put)
+
+    Gamma = _f64_slot("Gamma")
+    GammaTransposed = _f64_slot("GammaTransposed")
+    alpha = _f64_slot("alpha")
+    del _f64_slot
+
+    m = property(lambda self: self.Gamma.shape[0], doc="number of virtual observables")
+    dim_out = property(lambda self: self.Gamma.shape[1])
+    precision_mask = property(lambda self: self._sampler.precision_mask)
+
+    def _set(self, Gamma, alpha):
+        self.Gamma = _as_f64(Gamma, self.device)
+        self.alpha = _as_f64(alpha, self.device)
+        self.GammaTransposed = self.Gamma.t()
+
+    def resample(self, ForceResample=False):
+        if ForceResample or not self._sampler.is_constant:
+            self._set(*self._sampler())
+
+    def temporary_set_galerkin_manually(self, V):
+        self._set(*self._querry_point.weak_galerkin_on_device(V, device=self.device))
+        self.precision = -torch.ones(self.m, dtype=torch.double, device=self.device)
+
+
+class QuerryEnsemble(object):
+    """VirtualObservables.py:450-543."""
+
+    def __init__(self, querries, dtype, device):
+        self._querries, self.dtype, self.device = list(querries), dtype, device
+
+    def __len__(self):
+        return len(self._querries)
+
+    def __getitem__(self, item):
+        return self._querries[item]
+
+    def __iter__(self):
+        return iter(self._querries)
+
+    N = property(lambda self: len(self._querries))
+    m = property(lambda self: sum(q.m for q in self._querries), doc="total number of pieces of information")
+    precision_mask = property(lambda self: self._querries[0].precision_mask)
+    dim_out = property(lambda self: self._querries[0].dim_out)
+
+    def resample(self, ForceResample=False):
+        for q in self._querries:
+            q.resample(ForceResample=ForceResample)
+
+    @classmethod
+    def FromQuerryPointEnsemble(cls, QuerryPointEnsemble, physics, CGR, flux, N_gaussian, N_rbf, l_rbf=None, *,
+                                dtype=None, device=None):
+        assert isinstance(physics, dict) and dtype is not None and device is not None
+        W = physics['W']
+        if W is None:
+            raise NotImplementedError('need to provide W (as numpy array)')
+        assert isinstance(W, np.ndarray) and W.shape[0] > W.shape[1]
+        if flux:
+            raise NotImplementedError('flux constraints need FEniCS (bottleneck/flux.py)')
+        if N_rbf > 0:
+            assert l_rbf is not None
+        querries = []
+        for qp in QuerryPointEnsemble:
+            qp._device = device
+            parts = []
+            if CGR:
+                parts.append(CoarseGrainedResidualSampler(qp, W))
+            if N_gaussian > 0:
+                parts.append(GaussianSketchingSampler(qp, N_gaussian))
+            if N_rbf > 0:
+                parts.append(RadialBasisFunctionSampler(qp, l_rbf, N_rbf))
+            sampler = parts[0] if len(parts) == 1 else ConcatenatedSamplers(parts)
+            querries.append(LinearQuerry(qp, sampler, dtype=dtype, device=device))
+        return cls(querries, dtype=dtype, device=device)
+
+
+# ======================================================================================= virtual observables
+class BaseVirtualObservable(object):
+    def __init__(self, querry_point, dtype, device):
+        assert isinstance(querry_point, QuerryPoint)
+        self._querry_point, self.dtype, self.device = querry_point, dtype, device
+
+    querry_point = property(lambda self: self._querry_point)
+    d_y = property(lambda self: self._querry_point.dim_out)
+
+
+class VirtualObservable(BaseVirtualObservable):
+    """Posterior N(mean, diag(vars)) of one data point's fine solution given its virtual observables
+    (VirtualObservables.py:596-669)."""
+
+    def __init__(self, querry, querry_point, dtype, device):
+        super().__init__(querry_point, dtype, device)
+        assert isinstance(querry, LinearQuerry)
+        self._querry = querry
+        self._mean = self._vars = self._noise = None
+
+    querry = property(lambda self: self._querry)
+    mean = property(lambda self: self._mean)
+    vars = property(lambda self: self._vars)
+    m = property(lambda self: self._querry.m)
+
+    @property
+    def vo_variances(self):
+        return self._noise
+
+    @vo_variances.setter
+    def vo_variances(self, value):
+        assert value.dtype == torch.double and value.device == self.device
+        self._noise = value
+
+    def resample(self, ForceResample=False):
+        self._querry.resample(ForceResample=ForceResample)
+
+    def _set_posterior(self, mean, vars_):
+        self._mean, self._vars = mean, vars_
+
+    @torch.no_grad()
+    def update(self, g, prec, iteration, *, ForceUpdate=False):
+        if not ForceUpdate:
+            raise RuntimeError
+        q = self._querry
+        mean, vars_ = condition_gaussian(q.Gamma.unsqueeze(0), q.alpha.unsqueeze(0), self._noise,
+                                         g.to(_F64).unsqueeze(0), prec.to(_F64).unsqueeze(0))
+        self._set_posterior(mean[0], vars_[0])
+
+
+class BaseVirtualObservablesEnsemble(object):
+    """VirtualObservables.py:796-905."""
+
+    def __init__(self, QuerryPointEnsemble, virtual_observables, dtype, device):
+        self._QuerryPointEnsemble = QuerryPointEnsemble
+        self._virtual_observables = list(virtual_observables)
+        self.dtype, self.device = dtype, device
+        assert all(vo.m == self._virtual_observables[0].m for vo in self._virtual_observables)
+        self._cache = {}
+
+    def __getitem__(self, item):
+        return self._virtual_observables[item]
+
+    def __iter__(self):
+        return iter(self._virtual_observables)
+
+    def __len__(self):
+        return len(self._virtual_observables)
+
+    X = property(lambda self: self._QuerryPointEnsemble.X)
+    N = property(lambda self: len(self._virtual_observables))
+    m = property(lambda self: self._virtual_observables[0].m)
+    M = property(lambda self: sum(vo.m for vo in self._virtual_observables))
+    dim_out = property(lambda self: self._virtual_observables[0].d_y)
+
+    def flush_cache(self):
+        self._cache.clear()
+
+    def _stacked(self, what):
+        if what not in self._cache:
+            rows = [getattr(vo, what) for vo in self._virtual_observables]
+            assert all(r.dtype == torch.double for r in rows)
+            self._cache[what] = torch.stack(rows).to(device=self.device, dtype=self.dtype)
+        return self._cache[what].detach()
+
+    mean = property(lambda self: self._stacked("mean"))
+    vars = property(lambda self: self._stacked("vars"))
+    logsigma = property(lambda self: 0.5 * torch.log(self.vars))
+
+    def update(self, G, PREC, iteration, writer=None):
+        self.update_vo_precision(iteration, writer)
+        for n, vo in enumerate(self._virtual_observables):
+            vo.update(G[n, :], PREC[n, :], iteration, ForceUpdate=True)
+        self.flush_cache()
+
+    def update_vo_precision(self, iteration, writer=None):
+        raise NotImplementedError
+
+    def resample(self, ForceResample=False):
+        for vo in self._virtual_observables:
+            vo.resample(ForceResample=ForceResample)
+
+
+class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
+    """VirtualObservables.py:908-998, batched: ``update`` conditions all N data points together and
+    ``residuals`` evaluates all N residual vectors in one kernel launch."""
+
+    # per-chunk budget for the stacked Gamma [n,m,d] used by the batched conditioning
+    max_stack_bytes = 1 << 30
+
+    def __init__(self, QuerryPointEnsemble, QuerryEnsemble, dtype, device):
+        vos = [VirtualObservable(q, qp, dtype=dtype, device=device) for q, qp in zip(QuerryEnsemble, QuerryPointEnsemble)]
+        super().__init__(QuerryPointEnsemble, vos, dtype=dtype, device=device)
+        self._QuerryEnsemble = QuerryEnsemble
+        self._alpha_0 = self._beta_0 = 1e-6
+        self._prec_alpha = 0.5 * self.N + self._alpha_0
+        self._prec_beta = torch.ones(self.m, dtype=torch.double, device=self.device)
+        self._infinite_precision_mask = torch.tensor(QuerryEnsemble[0].precision_mask < 0, dtype=torch.bool,
+                                                     device=self.device)
+        self._mean_vo_variances = self._get_mean_vo_variances()
+        self._set_member_variance_values(self._mean_vo_variances)
+        self._precision_initialized = False
+        self._resident = None
+
+    infinite_precision_mask = property(lambda self: self._infinite_precision_mask)
+    fixed_precision = property(lambda self: bool(self._infinite_precision_mask.all().item()))
+
+    def _get_mean_vo_variances(self):
+        mv = self._prec_beta / (self._prec_alpha + 1)   # VirtualObservables.py:962-966
+        mv[self._infinite_precision_mask] = 0
+        return mv
+
+    def _set_member_variance_values(self, mean_vo_vars):
+        for vo in self._virtual_observables:
+            vo.vo_variances = mean_vo_vars
+
+    # -- device-resident inputs of the whole ensemble -------------------------------------------
+    def _inputs(self):
+        if self._resident is None:
+            qpe = self._QuerryPointEnsemble
+            plan = VoPlan.cached(qpe[0].physics, self.device)
+            self._resident = (plan, qpe.X(_F64, self.device), qpe.dirichlet_values(_F64, self.device))
+        return self._resident
+
+    def residuals(self, Y, V):
+        """r[N,m] = V^T (K_fom(x_n) y~_n - f) for all data points in ONE launch; V [d,m] is a weighting
+        matrix shared by the ensemble (e.g. V = W of the coarse-grained-residual sampler)."""
+        plan, X, G = self._inputs()
+        return plan.residual(X, Y.to(_F64), G, _as_f64(V, self.device))
+
+    def residual_gradients(self, S, V):
+        """q[N,d] = K_ff(x_n) V s_n for all data points in one launch (S [N,m])."""
+        plan, X, _ = self._inputs()
+        return plan.residual_T(X, _as_f64(V, self.device), S.to(_F64))
+
+    @torch.no_grad()
+    def update(self, G, PREC, iteration, writer=None):
+        self.update_vo_precision(iteration, writer)
+        vos = self._virtual_observables
+        per = 8 * self.m * self.dim_out
+        step = max(1, int(self.max_stack_bytes // max(per, 1)))
+        for lo in range(0, self.N, step):
+            chunk = vos[lo:lo + step]
+            Gam = torch.stack([vo.querry.Gamma for vo in chunk])
+            alp = torch.stack([vo.querry.alpha for vo in chunk])
+            mean, vars_ = condition_gaussian(Gam, alp, self._mean_vo_variances, G[lo:lo + step].to(_F64),
+                                             PREC[lo:lo + step].to(_F64))
+            for k, vo in enumerate(chunk):
+                vo._set_posterior(mean[k], vars_[k])
+        self.flush_cache()
+
+    @torch.no_grad()
+    def update_vo_precision(self, iteration, writer=None):
+        if not self._precision_initialized:
+            self._precision_initialized = True
+            return
+        if self[0].mean is None or self[0].vars is None:
+            raise RuntimeError
+        if self.fixed_precision:
+            return
+        beta = torch.zeros(self.m, dtype=torch.double, device=self.device)
+        for vo in self._virtual_observables:   # VirtualObservables.py:985-990
+            Gam = vo.querry.Gamma
+            beta += (Gam @ vo.mean - vo.querry.alpha) ** 2 + (Gam ** 2) @ vo.vars
+        self._prec_beta = 0.5 * beta + self._beta_0
+        self._mean_vo_variances = self._get_mean_vo_variances()
+        self._set_member_variance_values(self._mean_vo_variances)
+        if writer is not None:
+            writer.add_scalar('Monitor/Mean_VO_variances', torch.mean(self._mean_vo_variances), global_step=iteration)
+
+
+# ======================================================================================= schedules
+class TemperatureSchedule(object):
+    """T(iteration) between T_init and T_final over num_steps (VirtualObservables.py:1040-1091)."""
+
+    def __init__(self, T_init, T_final, num_steps):
+        assert num_steps > 1 and T_final < T_init
+        self._T_init, self._T_final, self._num_steps = T_init, T_final, num_steps
+
+    def _progress(self, iteration):
+        if iteration > self._num_steps:
+            raise RuntimeError
+        return iteration / (self._num_steps - 1)
+
+    def get_temperature(self, iteration):
+        raise NotImplementedError
+
+
+class LinearTemperatureSchedule(TemperatureSchedule):
+    def get_temperature(self, iteration):
+        return self._T_init + self._progress(iteration) * (self._T_final - self._T_init)
+
+
+class ExponentialTemperatureSchedule(TemperatureSchedule):
+    def get_temperature(self, iteration):
+        return self._T_init * np.exp(np.log(self._T_final / self._T_init) * self._progress(iteration))

@@ -1,0 +1,354 @@
+// Virtual-observable residuals on sm_100a, matrix-free.
+//   r_b = V^T (K_fom(a_b) u~_b - f)_free          (= Gamma_b y_b - alpha_b,  VirtualObservables.py:61-69, 662)
+//   q_b = K_ff(a_b) (V s_b)                        (= Gamma_b^T s_b,          VirtualObservables.py:663)
+// The reference materialises K_fom as scipy CSR per data point with FEniCS and forms the dense
+// Gamma = V^T K on the CPU; here K_fom(a) = sum_c a_c K_c is never formed: each free row i gathers its
+// incident cells ("row-cell ELL", slot-major so that consecutive rows read consecutive words):
+//   rho_i = sum_slots a[in] * (c0 * u_i + c1 * u~[j1] + c2 * u~[j2]) - f_i
+//
+// Version 1 (round 1, first measured path): a matvec kernel (one CTA owns S samples, conductivities
+// staged in shared memory with exp() applied once) + a tiled FP64 contraction kernel.
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace gpde {
+
+struct VoDev {
+    int n_nodes, n_cells, n_inputs, d, n_bc, nslots;
+    const int *ell_in;    // [nslots*d] conductivity input index of the slot's cell
+    const int *ell_j1;    // [nslots*d] source of the 2nd vertex: >=0 -> y index, <0 -> -(g index)-1
+    const int *ell_j2;    // [nslots*d]
+    const double *ell_c0, *ell_c1, *ell_c2;   // [nslots*d]
+    const double *f_free;  // [d]
+};
+
+}  // namespace gpde
+
+struct gpde_vo_plan {
+    gpde::VoDev dev;
+    int device;
+    std::vector<void *> allocs;
+};
+
+namespace gpde {
+
+__device__ __forceinline__ double ldd(const double *p) { return *p; }
+__device__ __forceinline__ double ldd(const float *p) { return (double)*p; }
+
+constexpr int kVoThreads = 256;
+
+// rho[b,i] for S samples per CTA.  ea (shared) = conductivities of the S samples, exp() applied.
+template <typename Ta, typename Ty, typename To, int S>
+__global__ void __launch_bounds__(kVoThreads)
+vo_matvec_kernel(VoDev P, const Ta *__restrict__ a, long long a_stride, int a_is_log,
+                 const Ty *__restrict__ y, const Ta *__restrict__ g, long long g_stride, int sub_f,
+                 double *__restrict__ rho_ws, To *__restrict__ rho_out, long long B, int stage_a) {
+    extern __shared__ double ea[];   // [S][n_inputs] when stage_a
+    const int d = P.d;
+    for (long long b0 = (long long)blockIdx.x * S; b0 < B; b0 += (long long)gridDim.x * S) {
+        if (stage_a) {
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const long long b = min(b0 + s, B - 1);
+                for (int p = threadIdx.x; p < P.n_inputs; p += kVoThreads) {
+                    double v = ldd(a + b * a_stride + p);
+                    ea[s * P.n_inputs + p] = a_is_log ? exp(v) : v;
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < d; i += kVoThreads) {
+            double acc[S], yi[S];
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const long long b = min(b0 + s, B - 1);
+                yi[s] = y ? ldd(y + b * d + i) : 0.0;
+                acc[s] = sub_f ? -P.f_free[i] : 0.0;
+            }
+            for (int t = 0; t < P.nslots; ++t) {
+                const int k = t * d + i;
+                const int in = P.ell_in[k], j1 = P.ell_j1[k], j2 = P.ell_j2[k];
+                const double c0 = P.ell_c0[k], c1 = P.ell_c1[k], c2 = P.ell_c2[k];
+#pragma unroll
+                for (int s = 0; s < S; ++s) {
+                    const long long b = min(b0 + s, B - 1);
+                    double av;
+                    if (stage_a) av = ea[s * P.n_inputs + in];
+                    else {
+                        av = ldd(a + b * a_stride + in);
+                        if (a_is_log) av = exp(av);
+                    }
+                    double u1, u2;
+                    if (j1 >= 0) u1 = y ? ldd(y + b * d + j1) : 0.0;
+                    else u1 = g ? ldd(g + b * g_stride + (-j1 - 1)) : 0.0;
+                    if (j2 >= 0) u2 = y ? ldd(y + b * d + j2) : 0.0;
+                    else u2 = g ? ldd(g + b * g_stride + (-j2 - 1)) : 0.0;
+                    acc[s] = fma(av, fma(c0, yi[s], fma(c1, u1, c2 * u2)), acc[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const long long b = b0 + s;
+                if (b < B) {
+                    if (rho_ws) rho_ws[b * d + i] = acc[s];
+                    if (rho_out) rho_out[b * d + i] = (To)acc[s];
+                }
+            }
+        }
+    }
+}
+
+// R[B,m] = rho[B,d] V[d,m]   (FP64 accumulate).  CTA tile 32 samples x 32 columns, k chunks of 32.
+template <typename Tv, typename To>
+__global__ void __launch_bounds__(256)
+vo_contract_kernel(const double *__restrict__ rho, const Tv *__restrict__ V, To *__restrict__ R,
+                   long long B, int d, int m) {
+    __shared__ double rs[32][33];
+    __shared__ double vs[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty in 0..7
+    const long long b0 = (long long)blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < d; k0 += 32) {
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = ty * 4 + r;
+            const long long b = b0 + row;
+            const int k = k0 + tx;
+            rs[row][tx] = (b < B && k < d) ? rho[b * d + k] : 0.0;
+            const int kk = k0 + row, nn = n0 + tx;
+            vs[row][tx] = (kk < d && nn < m) ? ldd(V + (long long)kk * m + nn) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) {
+            const double v = vs[k][tx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[r] = fma(rs[ty * 4 + r][k], v, acc[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const long long b = b0 + ty * 4 + r;
+        if (b < B && n0 + tx < m) R[b * m + n0 + tx] = (To)acc[r];
+    }
+}
+
+// w[B,d] = s[B,m] V^T
+template <typename Tv>
+__global__ void vo_expand_kernel(const Tv *__restrict__ s, const Tv *__restrict__ V, double *__restrict__ w,
+                                 long long B, int d, int m) {
+    const long long total = B * (long long)d;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / d;
+        const int i = (int)(idx - b * d);
+        double acc = 0.0;
+        for (int q = 0; q < m; ++q) acc = fma(ldd(s + b * m + q), ldd(V + (long long)i * m + q), acc);
+        w[idx] = acc;
+    }
+}
+
+template <typename T>
+static cudaError_t track_vo(gpde_vo_plan *pl, const T **dst, const std::vector<T> &src) {
+    T *p = nullptr;
+    cudaError_t e = upload(&p, src);
+    if (p) pl->allocs.push_back((void *)p);
+    *dst = p;
+    return e;
+}
+
+template <typename Ta, typename Ty, typename To>
+static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride, int a_is_log, const Ty *y,
+                         const Ta *g, long long g_stride, int sub_f, double *rho_ws, To *rho_out, long long B,
+                         cudaStream_t st) {
+    const VoDev &P = pl->dev;
+    const size_t per = sizeof(double) * (size_t)P.n_inputs;
+    const size_t cap = 200 * 1024;
+    const int nsm = sm_count(pl->device);
+    int S = 1;
+    if (B >= 4LL * nsm * 2 && 4 * per <= cap) S = 4;
+    else if (B >= 2LL * nsm * 2 && 2 * per <= cap) S = 2;
+    const int stage = (S * per <= cap) ? 1 : 0;
+    const size_t smem = stage ? S * per : 0;
+    const long long ctas = (B + S - 1) / S;
+    const unsigned grid = (unsigned)std::min<long long>(ctas, (long long)nsm * 8);
+#define GPDE_LAUNCH_MV(SS)                                                                               \
+    {                                                                                                    \
+        auto kern = vo_matvec_kernel<Ta, Ty, To, SS>;                                                    \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        kern<<<grid, kVoThreads, smem, st>>>(P, a, a_stride, a_is_log, y, g, g_stride, sub_f, rho_ws,    \
+                                             rho_out, B, stage);                                          \
+    }
+    if (S == 4) GPDE_LAUNCH_MV(4)
+    else if (S == 2) GPDE_LAUNCH_MV(2)
+    else GPDE_LAUNCH_MV(1)
+#undef GPDE_LAUNCH_MV
+    GPDE_CUDA_OK(cudaGetLastError());
+    return GPDE_OK;
+}
+
+template <typename T>
+static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int a_is_log, const T *y, const T *g,
+                       int64_t g_stride, const T *V, int m, T *r, T *rho, void *workspace, int flags, int64_t B,
+                       gpde_stream_t stream) {
+    if (!pl || !a || B < 0 || m < 0) return fail(GPDE_ERR_ARG, "vo_residual: bad argument");
+    if (m > 0 && (!V || !r)) return fail(GPDE_ERR_ARG, "vo_residual: V and r are required when m > 0");
+    if (m > 0 && !workspace) return fail(GPDE_ERR_ARG, "vo_residual: workspace required");
+    if (m == 0 && !rho) return fail(GPDE_ERR_ARG, "vo_residual: nothing to compute");
+    if (B == 0) return GPDE_OK;
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *ws = m > 0 ? (double *)workspace : nullptr;
+    int rc = launch_matvec<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, (flags & 1) ? 0 : 1, ws, rho, B, st);
+    if (rc != GPDE_OK) return rc;
+    if (m > 0) {
+        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((m + 31) / 32));
+        vo_contract_kernel<T, T><<<grid, 256, 0, st>>>(ws, V, r, B, pl->dev.d, m);
+        GPDE_CUDA_OK(cudaGetLastError());
+    }
+    return GPDE_OK;
+}
+
+template <typename T>
+static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int a_is_log, const T *V, int m,
+                         const T *s, T *q, void *workspace, int64_t B, gpde_stream_t stream) {
+    if (!pl || !a || !V || !s || !q || !workspace || m <= 0 || B < 0)
+        return fail(GPDE_ERR_ARG, "vo_residual_T: bad argument");
+    if (B == 0) return GPDE_OK;
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *w = (double *)workspace;
+    const long long total = B * (long long)pl->dev.d;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 16);
+    vo_expand_kernel<T><<<grid, 256, 0, st>>>(s, V, w, B, pl->dev.d, m);
+    GPDE_CUDA_OK(cudaGetLastError());
+    return launch_matvec<T, double, T>(pl, a, a_stride, a_is_log, w, (const T *)nullptr, 0, 0, (double *)nullptr,
+                                       q, B, st);
+}
+
+}  // namespace gpde
+
+using namespace gpde;
+
+extern "C" {
+
+int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int32_t *cell_dofs, const double *Ke,
+                        const int32_t *cell_to_input, int n_inputs, const int64_t *free_dofs, int d,
+                        const int64_t *bc_dofs, int n_bc, const double *f_full, int device) {
+    if (!plan || !cell_dofs || !Ke || !cell_to_input || !free_dofs || n_nodes <= 0 || n_cells <= 0 ||
+        n_inputs <= 0 || d <= 0 || n_bc < 0 || (n_bc > 0 && !bc_dofs))
+        return fail(GPDE_ERR_ARG, "vo_plan_create: bad argument");
+    std::vector<int> src(n_nodes, INT32_MIN);   // node -> encoded source
+    for (int i = 0; i < d; ++i) {
+        if (free_dofs[i] < 0 || free_dofs[i] >= n_nodes) return fail(GPDE_ERR_ARG, "vo_plan_create: free dof range");
+        src[free_dofs[i]] = i;
+    }
+    for (int c = 0; c < n_bc; ++c) {
+        if (bc_dofs[c] < 0 || bc_dofs[c] >= n_nodes) return fail(GPDE_ERR_ARG, "vo_plan_create: bc dof range");
+        if (src[bc_dofs[c]] != INT32_MIN) return fail(GPDE_ERR_ARG, "vo_plan_create: dof both free and constrained");
+        src[bc_dofs[c]] = -c - 1;
+    }
+    for (int v = 0; v < n_nodes; ++v)
+        if (src[v] == INT32_MIN) return fail(GPDE_ERR_ARG, "vo_plan_create: node %d neither free nor constrained", v);
+    // incident cells per free row
+    std::vector<int> count(d, 0);
+    for (int c = 0; c < n_cells; ++c) {
+        if (cell_to_input[c] < 0 || cell_to_input[c] >= n_inputs)
+            return fail(GPDE_ERR_ARG, "vo_plan_create: cell_to_input out of range");
+        for (int l = 0; l < 3; ++l) {
+            const int v = cell_dofs[3 * c + l];
+            if (v < 0 || v >= n_nodes) return fail(GPDE_ERR_ARG, "vo_plan_create: cell dof out of range");
+            if (src[v] >= 0) count[src[v]]++;
+        }
+    }
+    int nslots = 0;
+    for (int i = 0; i < d; ++i) nslots = std::max(nslots, count[i]);
+    const size_t tot = (size_t)nslots * d;
+    std::vector<int> ell_in(tot, 0), ell_j1(tot), ell_j2(tot);
+    std::vector<double> c0(tot, 0.0), c1(tot, 0.0), c2(tot, 0.0);
+    for (size_t k = 0; k < tot; ++k) ell_j1[k] = ell_j2[k] = (int)(k % d);   // padding: self, zero coefficients
+    std::fill(count.begin(), count.end(), 0);
+    for (int c = 0; c < n_cells; ++c)
+        for (int l = 0; l < 3; ++l) {
+            const int v = cell_dofs[3 * c + l];
+            if (src[v] < 0) continue;
+            const int i = src[v], t = count[i]++;
+            const int l1 = (l + 1) % 3, l2 = (l + 2) % 3;
+            const size_t k = (size_t)t * d + i;
+            ell_in[k] = cell_to_input[c];
+            ell_j1[k] = src[cell_dofs[3 * c + l1]];
+            ell_j2[k] = src[cell_dofs[3 * c + l2]];
+            c0[k] = Ke[9 * c + 3 * l + l];
+            c1[k] = Ke[9 * c + 3 * l + l1];
+            c2[k] = Ke[9 * c + 3 * l + l2];
+        }
+    std::vector<double> f_free(d, 0.0);
+    if (f_full)
+        for (int i = 0; i < d; ++i) f_free[i] = f_full[free_dofs[i]];
+
+    gpde_vo_plan *pl = new gpde_vo_plan();
+    pl->device = device;
+    DeviceGuard guard(device);
+    VoDev &D = pl->dev;
+    D.n_nodes = n_nodes; D.n_cells = n_cells; D.n_inputs = n_inputs; D.d = d; D.n_bc = n_bc; D.nslots = nslots;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_in, ell_in);
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_j1, ell_j1);
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_j2, ell_j2);
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_c0, c0);
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_c1, c1);
+    if (e == cudaSuccess) e = track_vo(pl, &D.ell_c2, c2);
+    if (e == cudaSuccess) e = track_vo(pl, &D.f_free, f_free);
+    if (e != cudaSuccess) {
+        gpde_vo_plan_destroy(pl);
+        return fail(GPDE_ERR_CUDA, "vo_plan_create: upload failed: %s", cudaGetErrorString(e));
+    }
+    *plan = pl;
+    return GPDE_OK;
+}
+
+int gpde_vo_plan_destroy(gpde_vo_plan *pl) {
+    if (!pl) return GPDE_OK;
+    DeviceGuard guard(pl->device);
+    for (void *p : pl->allocs) cudaFree(p);
+    delete pl;
+    return GPDE_OK;
+}
+
+int gpde_vo_plan_info(const gpde_vo_plan *pl, int64_t out[8]) {
+    if (!pl || !out) return fail(GPDE_ERR_ARG, "vo_plan_info: null");
+    out[0] = pl->dev.n_nodes; out[1] = pl->dev.n_cells; out[2] = pl->dev.n_inputs; out[3] = pl->dev.d;
+    out[4] = pl->dev.n_bc; out[5] = pl->dev.nslots; out[6] = pl->device; out[7] = 0;
+    return GPDE_OK;
+}
+
+size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
+    (void)m;
+    if (!pl || B < 0) return 0;
+    return sizeof(double) * (size_t)pl->dev.d * (size_t)B;
+}
+
+int gpde_vo_residual_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, int a_is_log, const double *y,
+                         const double *g, int64_t g_stride, const double *V, int m, double *r, double *rho,
+                         void *workspace, int flags, int64_t B, gpde_stream_t stream) {
+    return vo_residual<double>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, rho, workspace, flags, B, stream);
+}
+int gpde_vo_residual_f32(const gpde_vo_plan *pl, const float *a, int64_t a_stride, int a_is_log, const float *y,
+                         const float *g, int64_t g_stride, const float *V, int m, float *r, float *rho,
+                         void *workspace, int flags, int64_t B, gpde_stream_t stream) {
+    return vo_residual<float>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, rho, workspace, flags, B, stream);
+}
+int gpde_vo_residual_T_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, int a_is_log, const double *V,
+                           int m, const double *s, double *q, void *workspace, int64_t B, gpde_stream_t stream) {
+    return vo_residual_T<double>(pl, a, a_stride, a_is_log, V, m, s, q, workspace, B, stream);
+}
+int gpde_vo_residual_T_f32(const gpde_vo_plan *pl, const float *a, int64_t a_stride, int a_is_log, const float *V,
+                           int m, const float *s, float *q, void *workspace, int64_t B, gpde_stream_t stream) {
+    return vo_residual_T<float>(pl, a, a_stride, a_is_log, V, m, s, q, workspace, B, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,161 @@
+/*
+ * gpde_b200.h -- C ABI of the B200-native physics layer (libgpde_b200.so).
+ *
+ * Drop-in boundary for the ONE hot path of pkmtum/generative-physics-informed-pde:
+ *   - the coarse-grained model (assemble K(x)=sum_e x_e K_e, solve, adjoint):
+ *       reference bottleneck/ROM.py:59-100  (+ autograd of it)
+ *       reference bottleneck/components.py:296-311 (exp(X)+1e-8, prolongation y = W u)
+ *   - the virtual-observable residuals  r = V^T (K_fom(a) u~ - f)_free  and the transposed
+ *     application  q = K_ff(a) (V s):
+ *       reference bottleneck/VirtualObservables.py:57-69, 642-669, 971-998
+ *
+ * Conventions
+ *   - plain C: pointers + sizes only, no torch / C++ types cross this boundary;
+ *   - "host" pointers are read during the call and never retained;
+ *   - "device" pointers must live on the plan's device; the library never allocates or frees
+ *     user data -- scratch comes from the caller (query *_workspace_bytes first);
+ *   - every launch goes to the caller's stream (a cudaStream_t passed as void*); no entry point
+ *     synchronises the device except plan_create (uploads constants) and plan_destroy;
+ *   - plans are immutable after creation => re-entrant across streams; one plan per device;
+ *   - return value: 0 = ok, <0 = error (gpde_last_error() gives the text for this thread);
+ *     numerical failures are reported LAPACK-style through a device info word, never by a trap;
+ *   - matrices are row-major; batch is the leading axis (X[B,E], F[B,n], u[B,n], y[B,d] ...),
+ *     exactly the torch layouts the reference passes around.
+ *   - *_f64: double I/O.  *_f32: float I/O, double arithmetic inside (meets the 1e-5 tier).
+ */
+#ifndef GPDE_B200_H
+#define GPDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GPDE_OK 0
+#define GPDE_ERR_ARG (-1)      /* bad argument */
+#define GPDE_ERR_CUDA (-2)     /* CUDA runtime error (allocation, launch) */
+#define GPDE_ERR_SIZE (-3)     /* problem too large for this build's kernels */
+
+/* info word bits written by the ROM kernels (atomicOr into *info, device int32) */
+#define GPDE_INFO_NONPOSITIVE_X 1      /* some conductivity <= 1e-12   (ROM.py:74-76 -> ValueError) */
+#define GPDE_INFO_NOT_SPD 2            /* non-positive pivot in the factorisation              */
+
+typedef struct gpde_rom_plan gpde_rom_plan;
+typedef struct gpde_vo_plan gpde_vo_plan;
+typedef void *gpde_stream_t; /* cudaStream_t */
+
+int gpde_version(void);
+const char *gpde_last_error(void);
+
+/* ------------------------------------------------------------------ coarse-grained model */
+
+/* Replaces ROM.__init__ (bottleneck/ROM.py:8-15): keeps the element tensor and Dirichlet map on
+ * the device, in the sparse/banded form the kernels use.
+ *   M_host   [n,n,E] row-major, M[:,:,e] = unit-conductivity stiffness of coarse cell e (ROM.py:46-53)
+ *   bc_dofs  [n_bc]  constrained dofs (physics.constrained_dofs, ROM.py:14)
+ * Free dofs are the remaining ones, ascending (optionally reordered to shrink the band). */
+int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M_host,
+                         const int64_t *bc_dofs, int n_bc, int device);
+int gpde_rom_plan_destroy(gpde_rom_plan *plan);
+
+/* out[0]=n, [1]=E, [2]=n_free, [3]=half bandwidth, [4]=factor doubles per sample,
+ * [5]=assembly contributions, [6]=lanes per sample, [7]=device */
+int gpde_rom_plan_info(const gpde_rom_plan *plan, int64_t out[8]);
+
+/* bytes of factor stash needed for a batch of B samples (always doubles) */
+size_t gpde_rom_factor_bytes(const gpde_rom_plan *plan, int64_t B);
+
+/* Replaces ROM.__call__ (bottleneck/ROM.py:65-88)  [x_is_log = 0: X are conductivities]
+ * and ReducedOrderModelOperator's exp(X)+1e-8 -> rom (components.py:298) [x_is_log = 1].
+ *   X [B,E], F [B,n] (Dirichlet values already written at bc_dofs, BoundaryConditions.py:132-147)
+ *   u [B,n]  solution incl. Dirichlet dofs
+ *   factor   [gpde_rom_factor_bytes] banded LDL^T factor kept for the adjoint (may be NULL)
+ *   info     device int32, OR-ed with GPDE_INFO_* (may be NULL)                              */
+int gpde_rom_forward_f64(const gpde_rom_plan *plan, const double *X, int x_is_log, const double *F,
+                         double *u, double *factor, int *info, int64_t B, gpde_stream_t stream);
+int gpde_rom_forward_f32(const gpde_rom_plan *plan, const float *X, int x_is_log, const float *F,
+                         float *u, double *factor, int *info, int64_t B, gpde_stream_t stream);
+
+/* Replaces autograd through matmul/index_put/solve: with lambda = A^-T gbar_u,
+ *   gradX[b,e] = - sum_{i free} sum_j lambda_i K_e[i,j] u_j   (times exp(X) when x_is_log)
+ *   gradF[b,:] = lambda                                            (may be NULL)
+ * factor == NULL => the factorisation is recomputed from X.                                  */
+int gpde_rom_adjoint_f64(const gpde_rom_plan *plan, const double *X, int x_is_log, const double *u,
+                         const double *factor, const double *gbar_u, double *gradX, double *gradF,
+                         int64_t B, gpde_stream_t stream);
+int gpde_rom_adjoint_f32(const gpde_rom_plan *plan, const float *X, int x_is_log, const float *u,
+                         const double *factor, const float *gbar_u, float *gradX, float *gradF,
+                         int64_t B, gpde_stream_t stream);
+
+/* GetStiffness (bottleneck/ROM.py:91-100): K[n,n,B] (batch LAST, as the reference returns it),
+ * Dirichlet rows replaced by identity rows when dirichlet != 0.  X are conductivities.       */
+int gpde_rom_stiffness_f64(const gpde_rom_plan *plan, const double *X, double *K, int dirichlet,
+                           int64_t B, gpde_stream_t stream);
+
+/* Prolongation y = W u and its transpose gbar_u = W^T gbar_y (components.py:298 einsum 'sk,nk->ns')
+ * with W[d,n] held as CSR on the device (rows have <= 3 non-zeros for P1).                    */
+typedef struct gpde_prolong_plan gpde_prolong_plan;
+int gpde_prolong_plan_create(gpde_prolong_plan **plan, int d, int n, const double *W_host, int device);
+int gpde_prolong_plan_destroy(gpde_prolong_plan *plan);
+int gpde_prolong_apply_f64(const gpde_prolong_plan *plan, const double *u, double *y, int64_t B,
+                           gpde_stream_t stream);                 /* y[B,d]  = u[B,n] W^T */
+int gpde_prolong_apply_T_f64(const gpde_prolong_plan *plan, const double *gy, double *gu, int64_t B,
+                             gpde_stream_t stream);               /* gu[B,n] = gy[B,d] W   */
+int gpde_prolong_apply_f32(const gpde_prolong_plan *plan, const float *u, float *y, int64_t B,
+                           gpde_stream_t stream);
+int gpde_prolong_apply_T_f32(const gpde_prolong_plan *plan, const float *gy, float *gu, int64_t B,
+                             gpde_stream_t stream);
+
+/* ------------------------------------------------------------------ virtual observables */
+
+/* Replaces QuerryPoint._assemble_system / LinearEllipticPhysics.assemble_system
+ * (VirtualObservables.py:57-59, physics/LinearElliptic.py:137-159): the fine operator is kept
+ * matrix-free as element data; K_fom(a) = sum_c a[cell_to_input[c]] * Ke[c].
+ *   cell_dofs     [n_cells,3]   P1 connectivity
+ *   Ke            [n_cells,3,3] unit-conductivity element stiffness
+ *   cell_to_input [n_cells]     index of the per-sample conductivity entry used by cell c
+ *                               (identity for DG0 input; pixel id for image input)
+ *   free_dofs [d], bc_dofs [n_bc]; f_full [n_nodes] load vector or NULL (zero)               */
+int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int32_t *cell_dofs,
+                        const double *Ke, const int32_t *cell_to_input, int n_inputs,
+                        const int64_t *free_dofs, int d, const int64_t *bc_dofs, int n_bc,
+                        const double *f_full, int device);
+int gpde_vo_plan_destroy(gpde_vo_plan *plan);
+/* out[0]=n_nodes, [1]=n_cells, [2]=n_inputs, [3]=d, [4]=n_bc, [5]=slots per row, [6]=device */
+int gpde_vo_plan_info(const gpde_vo_plan *plan, int64_t out[8]);
+
+/* scratch bytes for residual / residual_T on B samples with m weighting functions */
+size_t gpde_vo_workspace_bytes(const gpde_vo_plan *plan, int64_t B, int m);
+
+/* r[B,m] = V^T (K_fom(a_b) u~_b - f)_free ,  u~ = y on free dofs, g on constrained dofs
+ *        = Gamma_b y_b - alpha_b   (VirtualObservables.py:61-69, 662, 990).
+ *   a   [B or 1, n_inputs]  (a_stride = n_inputs, or 0 to share one field across the batch)
+ *   a_is_log != 0: a holds log-conductivities (QuerryPoint.x), exp() applied inside
+ *   y   [B,d]   (NULL = zeros);  g [B or 1, n_bc] with g_stride = n_bc or 0 (NULL = zeros)
+ *   V   [d,m] row-major weighting matrix (NULL with m=0: only rho is produced)
+ *   rho [B,d] optional output of the fine residual itself (may be NULL)
+ *   flags: bit0 = ignore the load vector f                                                  */
+int gpde_vo_residual_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,
+                         const double *y, const double *g, int64_t g_stride, const double *V, int m,
+                         double *r, double *rho, void *workspace, int flags, int64_t B,
+                         gpde_stream_t stream);
+int gpde_vo_residual_f32(const gpde_vo_plan *plan, const float *a, int64_t a_stride, int a_is_log,
+                         const float *y, const float *g, int64_t g_stride, const float *V, int m,
+                         float *r, float *rho, void *workspace, int flags, int64_t B,
+                         gpde_stream_t stream);
+
+/* q[B,d] = K_ff(a_b) (V s_b) = Gamma_b^T s_b  (VirtualObservables.py:663; with s = P r it is the
+ * gradient of 1/2 r^T P r w.r.t. y).  With B = m, s = I and a_stride = 0 it yields Gamma itself. */
+int gpde_vo_residual_T_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,
+                           const double *V, int m, const double *s, double *q, void *workspace,
+                           int64_t B, gpde_stream_t stream);
+int gpde_vo_residual_T_f32(const gpde_vo_plan *plan, const float *a, int64_t a_stride, int a_is_log,
+                           const float *V, int m, const float *s, float *q, void *workspace,
+                           int64_t B, gpde_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPDE_B200_H */

@@ -1,0 +1,95 @@
+"""ORACLE (test infrastructure, not product code): CPU restatement of the reference's
+virtual-observable arithmetic (bottleneck/VirtualObservables.py).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
+import this module.
+
+Pinned against the reference itself through tests/golden/ (make_golden.py runs the
+reference's QuerryPoint / LinearQuerry / VirtualObservable / VirtualObservablesEnsemble
+classes under stub ``dolfin``).  The fine system (K, f) fed to it comes from
+oracle/fem_p1.py ("parity unpinned" at the FEniCS boundary).
+"""
+import numpy as np
+import torch
+
+
+def construct_querry_weak_galerkin(K, f, V):
+    """Gamma = V^T K (dense m x d), alpha = V^T f   (VirtualObservables.py:61-69)."""
+    assert V.shape[0] == K.shape[0]
+    assert V.shape[0] == f.shape[0]
+    Gamma = V.T @ K
+    alpha = V.T @ f
+    return np.asarray(Gamma), np.asarray(alpha)
+
+
+def vo_residual(K, f, V, y):
+    """r = Gamma y - alpha = V^T (K_ff y - f_eff)   (VirtualObservables.py:662, 990)."""
+    Gamma, alpha = construct_querry_weak_galerkin(K, f, V)
+    return Gamma @ y - alpha
+
+
+def vo_residual_batch(Ks, fs, V, Y):
+    """Reference route, one data point at a time (Python loop as VirtualObservables.py:895, 985)."""
+    return np.stack([vo_residual(K, f, V, y) for K, f, y in zip(Ks, fs, Y)])
+
+
+def vo_residual_transposed(K, V, s):
+    """q = Gamma^T s = K_ff (V s)   (the transposed application at VirtualObservables.py:663)."""
+    return K.T @ (V @ s)
+
+
+def virtual_observable_update(Gamma, alpha, vo_variances, g, prec):
+    """Gaussian conditioning of N(g, diag(1/prec)) on Gamma y = alpha (+ noise vo_variances)
+    -- VirtualObservable.update, VirtualObservables.py:642-669, same torch ops.
+    Gamma [m,d], alpha [m], vo_variances [m], g [d], prec [d]  ->  mean [d], vars [d]."""
+    Gamma = torch.as_tensor(Gamma, dtype=torch.double)
+    alpha = torch.as_tensor(alpha, dtype=torch.double)
+    g = torch.as_tensor(g, dtype=torch.double)
+    prec = torch.as_tensor(prec, dtype=torch.double)
+    vo_variances = torch.as_tensor(vo_variances, dtype=torch.double)
+    GT = Gamma  # the reference's "_GammaTransposed" is Gamma.t().t() == Gamma  (:653-654)
+    cov = 1 / prec
+    Lambda = torch.einsum('im, m, sm -> is', [GT, cov, GT])
+    Lambda = Lambda + torch.diag(vo_variances)
+    L = torch.linalg.cholesky(Lambda)
+    LambdaInv = torch.cholesky_inverse(L)
+    solvec = LambdaInv @ (GT @ g - alpha)
+    mean = g - torch.einsum('i, mi, m -> i', [cov, GT, solvec])
+    A = GT * cov
+    sub = torch.einsum('si, sm, mi -> i', [A, LambdaInv, A])
+    return mean, cov - sub
+
+
+def mean_vo_variances(prec_beta, prec_alpha, infinite_precision_mask):
+    """beta/(alpha+1), zero where the precision is infinite (VirtualObservables.py:962-966)."""
+    mv = prec_beta / (prec_alpha + 1)
+    mv = mv.clone()
+    mv[infinite_precision_mask] = 0
+    return mv
+
+
+def update_vo_precision_beta(Gammas, alphas, means, varss, beta_0=1e-6):
+    """prec_beta = 0.5 * sum_n [(Gamma_n mean_n - alpha_n)^2 + Gamma_n^2 vars_n] + beta_0
+    (VirtualObservables.py:981-992)."""
+    m = Gammas[0].shape[0]
+    beta = torch.zeros(m, dtype=torch.double)
+    for Gamma, alpha, mean, vars_ in zip(Gammas, alphas, means, varss):
+        Gamma = torch.as_tensor(Gamma, dtype=torch.double)
+        beta = beta + (Gamma @ torch.as_tensor(mean) - torch.as_tensor(alpha)) ** 2 \
+            + (Gamma ** 2 @ torch.as_tensor(vars_))
+    return 0.5 * beta + beta_0
+
+
+def energy_vo_update(K, f, prec, g, mean0, Vs, temperature=1.0):
+    """EnergyVirtualObservable.update (VirtualObservables.py:769-788): subspace Newton steps on
+    A = diag(prec) + K/T, b = f/T + prec*g with the supplied weighting matrices Vs (one per
+    iteration).  Returns (mean, vars)."""
+    invT = 1.0 / temperature
+    vars_ = 1 / (prec + invT * K.diagonal())
+    A = np.diag(prec) + invT * K
+    b = invT * f + prec * g
+    mean = mean0.copy()
+    for V in Vs:
+        Mm = np.array(V.T @ A @ V)
+        mean = mean - V @ np.linalg.solve(Mm, V.T @ np.array(A @ mean - b).flatten())
+    return mean, vars_

@@ -1,0 +1,160 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference classes (bottleneck/ROM.py,
+bottleneck/components.py, bottleneck/VirtualObservables.py from /root/reference) under the stub-dolfin
+shim (oracle/ref_shim.py), fed with the constants of the restated P1 assembler (oracle/fem_p1.py).
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The fixtures pin (a) the oracle restatements in oracle/rom_ref.py / oracle/vo_ref.py and (b) through
+them the CUDA path.  They do NOT pin the FEniCS boundary (mesh/dof numbering, assembled constants):
+FEniCS is not installable here -- "parity unpinned" for that part, see DESIGN.md.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import fem_p1, ref_shim  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def synthetic_inputs(P, B, kind, seed, ell):
+    rng = np.random.RandomState(seed)
+    nx_f, ny_f = P['nx_fom'], P['ny_fom']
+    img = fem_p1.sample_log_field(ny_f, nx_f, 0.4, 0.8, ell, B, rng)          # fine log-conductivity images
+    X_DG = fem_p1.image_to_function(img, P['pixel_of_cell_fom'])               # [B, E_f]
+    # coarse log-conductivity: mean of the fine log field over each coarse cell
+    E = len(P['cells_rom'])
+    mid = P['coords_fom'][P['cells_fom']].mean(axis=1)
+    nx, ny = P['nx_rom'], P['ny_rom']
+    sx = np.minimum((mid[:, 0] * nx).astype(int), nx - 1)
+    sy = np.minimum((mid[:, 1] * ny).astype(int), ny - 1)
+    upper = (mid[:, 1] * ny - sy) > (mid[:, 0] * nx - sx)
+    owner = 2 * (sy * nx + sx) + upper.astype(int)
+    logX = np.stack([X_DG[:, owner == e].mean(axis=1) for e in range(E)], axis=1)
+    coef = rng.uniform(-0.5, 0.5, size=(B, 4))
+    g_rom = np.stack([fem_p1.dirichlet_left_right(P['coords_rom'], kind, coef[b])[1] for b in range(B)])
+    g_fom = np.stack([fem_p1.dirichlet_left_right(P['coords_fom'], kind, coef[b])[1] for b in range(B)])
+    F = fem_p1.full_F_with_applied_bc(len(P['coords_rom']), P['bc_dofs_rom'], g_rom)
+    gbar = rng.normal(size=(B, len(P['coords_rom'])))
+    return dict(img=img, X_DG=X_DG, logX=logX, bc_coef=coef, g_rom=g_rom, g_fom=g_fom, F=F, gbar_u=gbar)
+
+
+def rom_case(ref, name, nx, refines, B, kind, seed, ell):
+    P = fem_p1.build_problem(nx, nx, refines)
+    inp = synthetic_inputs(P, B, kind, seed, ell)
+    ROM = ref['ROM'].ROM
+    Operator = ref['components'].ReducedOrderModelOperator
+    phys = ref_shim.PhysicsLike(P['bc_dofs_rom'], P['free_dofs_rom'], len(P['cells_rom']))
+    M = torch.tensor(P['M'], dtype=torch.double)
+    rom = ROM(phys, M, torch.double, torch.device('cpu'))
+    W = torch.tensor(P['W'], dtype=torch.double)
+    op = Operator(rom, W, dtype=torch.double, device=torch.device('cpu'))
+
+    logX = torch.tensor(inp['logX'], requires_grad=True)
+    F = torch.tensor(inp['F'], requires_grad=True)
+    gbar = torch.tensor(inp['gbar_u'])
+    # ROM.__call__ on conductivities, exactly as components.py:298 feeds it
+    x = torch.exp(logX) + 1e-8
+    u, K = rom(x, F, ReturnStiffness=True)
+    u.backward(gbar)
+    out = dict(u=u.detach().numpy(), K=K.detach().numpy(), grad_logX=logX.grad.numpy().copy(),
+               grad_F=F.grad.numpy().copy())
+    # gradient w.r.t. the conductivities themselves (ROM used directly)
+    xd = x.detach().clone().requires_grad_(True)
+    rom(xd, F.detach()).backward(gbar)
+    out['grad_x'] = xd.grad.numpy().copy()
+    # operator: mean and the gradient of sum(w * mu_y) w.r.t. effprop
+    eff = torch.tensor(inp['logX'], requires_grad=True)
+    mu_y, ls_y = op.forward(eff, F.detach())
+    wy = torch.tensor(np.random.RandomState(seed + 1).normal(size=tuple(mu_y.shape)))
+    (mu_y * wy).sum().backward()
+    out.update(mu_y=mu_y.detach().numpy(), gbar_y=wy.numpy(), grad_effprop=eff.grad.numpy().copy(),
+               logsigmas_shape=np.array(ls_y.shape))
+    consts = dict(M=P['M'], W=P['W'], bc_dofs_rom=P['bc_dofs_rom'], free_dofs_rom=P['free_dofs_rom'])
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), nx=nx, refines=refines, kind=kind,
+                        **{'in_' + k: v for k, v in inp.items() if k in ('logX', 'F', 'gbar_u', 'bc_coef')},
+                        **{'out_' + k: v for k, v in out.items()}, **{'const_' + k: v for k, v in consts.items()})
+    print(name, 'u', out['u'].shape, 'max|u|', np.abs(out['u']).max())
+
+
+def vo_case(ref, name, nx, refines, N, kind, seed, ell, n_rbf):
+    VOm = ref['VirtualObservables']
+    P = fem_p1.build_problem(nx, nx, refines)
+    inp = synthetic_inputs(P, N, kind, seed, ell)
+    rng = np.random.RandomState(seed + 7)
+    d = len(P['free_dofs_fom'])
+
+    class BC(object):   # what assemble_system / samplers read from a boundary condition
+        def __init__(self, g):
+            self.g = g
+
+    def assemble(x, bc):
+        return fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], x, P['bc_dofs_fom'], bc.g,
+                                           P['free_dofs_fom'])
+
+    phys = ref_shim.PhysicsLike(P['bc_dofs_fom'], P['free_dofs_fom'], len(P['cells_fom']), assemble)
+    centres = rng.uniform(size=(n_rbf, 2))
+    V = np.hstack([P['W'], fem_p1.rbf_columns(P['coords_fom'], P['free_dofs_fom'], centres, 0.1)])
+    m = V.shape[1]
+    mask = -np.ones(m)
+    mask[-2:] = 1.0    # two learnable-precision observables so that update_vo_precision does work
+
+    class FixedSampler(VOm.BaseSampler):   # constant sampler around the reference's own weak-Galerkin code
+        def __init__(self, qp):
+            super().__init__(qp)
+            self._GA = qp.construct_querry_weak_galerkin(V)
+        m = property(lambda self: V.shape[1])
+        is_constant = property(lambda self: True)
+        precision_mask = property(lambda self: mask)
+
+        def sample(self):
+            return self._GA
+
+    dev = torch.device('cpu')
+    qps = [VOm.QuerryPoint(phys, inp['X_DG'][n], BC(inp['g_fom'][n])) for n in range(N)]
+    qpe = VOm.QuerryPointEnsemble(qps)
+    qe = VOm.QuerryEnsemble([VOm.LinearQuerry(qp, FixedSampler(qp), torch.double, dev) for qp in qps], torch.double, dev)
+    ens = VOm.VirtualObservablesEnsemble(qpe, qe, torch.double, dev)
+
+    Y = rng.normal(size=(N, d)) * 0.1 + (P['W'] @ P['coords_rom'][:, 0])[None]       # something like a solution
+    G1 = torch.tensor(Y)
+    PREC1 = torch.tensor(rng.uniform(50.0, 200.0, size=(N, d)))
+    ens.update(G1, PREC1, 0)
+    mean1, vars1 = ens.mean.numpy().copy(), ens.vars.numpy().copy()
+    G2 = torch.tensor(mean1 + 0.01 * rng.normal(size=(N, d)))
+    PREC2 = torch.tensor(rng.uniform(50.0, 200.0, size=(N, d)))
+    ens.update(G2, PREC2, 1)      # this one runs update_vo_precision (VirtualObservables.py:971-998)
+    out = dict(
+        Gamma=np.stack([q.Gamma.numpy() for q in qe]), alpha=np.stack([q.alpha.numpy() for q in qe]),
+        residual=np.stack([q.Gamma.numpy() @ Y[n] - q.alpha.numpy() for n, q in enumerate(qe)]),
+        mean1=mean1, vars1=vars1, mean2=ens.mean.numpy().copy(), vars2=ens.vars.numpy().copy(),
+        prec_beta=ens._prec_beta.numpy().copy(), mean_vo_variances=ens._mean_vo_variances.numpy().copy(),
+    )
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), nx=nx, refines=refines, kind=kind,
+                        in_X_DG=inp['X_DG'], in_g_fom=inp['g_fom'], in_bc_coef=inp['bc_coef'], in_V=V, in_mask=mask,
+                        in_Y=Y, in_PREC1=PREC1.numpy(), in_G2=G2.numpy(), in_PREC2=PREC2.numpy(),
+                        **{'out_' + k: v for k, v in out.items()})
+    print(name, 'Gamma', out['Gamma'].shape, 'max|r|', np.abs(out['residual']).max())
+
+
+def main():
+    if not ref_shim.available():
+        raise SystemExit('reference tree not found; fixtures can only be regenerated in the build container')
+    ref = ref_shim.load()
+    torch.manual_seed(0)
+    np.random.seed(0)
+    rom_case(ref, 'rom_4x4_ndp', 4, 3, 16, 'NDP', 0, 0.15)      # example.ipynb / highres32 shapes
+    rom_case(ref, 'rom_8x8_nd', 8, 2, 8, 'ND', 1, 0.08)         # highres coarse mesh (fine mesh irrelevant here)
+    vo_case(ref, 'vo_4x4_32_ndp', 4, 3, 3, 'NDP', 2, 0.15, n_rbf=5)
+    vo_case(ref, 'vo_2x2_8_nd', 2, 2, 4, 'ND', 3, 0.3, n_rbf=3)
+
+
+if __name__ == '__main__':
+    main()
