@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of the physics layer on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--dtype f64]
+    python bench.py --impl reference ...          # the reference's CPU arithmetic (oracle port), host cores
+
+A "step" is one pass of the physics layer over one batch of synthetic log-normal fields:
+    coarse-grained model forward (logX, F -> u), its adjoint (gbar_u -> dL/dlogX),
+    and the virtual-observable residual r = V^T (K_fom(a) y~ - f) for the same samples.
+``value`` = samples/s with inputs resident in HBM (each sample = 1 CGM fwd+adjoint solve + 1 VO residual
+evaluation); per-unit rates are reported beside it.  ``e2e`` is the same pass through the public
+module API from pinned HOST buffers, copies included.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "CGM fwd+adjoint solves/s & VO residual evals/s"
+UNIT = "samples/s (1 CGM fwd+adjoint solve + 1 VO residual eval per sample)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--batch", type=int, default=None, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------- CPU arm (oracle port)
+class CpuReference(object):
+    """The reference's own arithmetic on the host cores: bottleneck/ROM.py ops through autograd
+    (oracle/rom_ref.py) and the per-data-point VO route K -> Gamma = V^T K -> Gamma y - alpha
+    (oracle/vo_ref.py), all torch/MKL threads.  FEniCS assembly itself cannot be timed here (not
+    installable); its place is taken by a precomputed-pattern CSR assembly."""
+
+    def __init__(self, w, sample):
+        import numpy as np
+        import torch
+        from oracle import rom_ref, vo_ref
+        self.np, self.torch, self.rom_ref, self.vo_ref = np, torch, rom_ref, vo_ref
+        self.cores = os.cpu_count() or 1
+        torch.set_num_threads(self.cores)
+        self.w, self.sample = w, int(min(sample, w.B))
+        rom, fom = w.physics["rom"], w.physics["fom"]
+        self.M = torch.tensor(rom.mesh.dense_element_tensor())
+        self.bc = torch.tensor(rom.constrained_dofs)
+        self.asm = vo_ref.CsrAssembler(fom.mesh.coords, fom.mesh.cells, fom.constrained_dofs, fom.free_dofs,
+                                       Ke=fom.mesh.element_stiffness())
+        self.pix = fom.mesh.pixel_of_cell()
+
+    def cgm(self, n):
+        t = self.torch
+        w = self.w
+        t0 = time.perf_counter()
+        self.rom_ref.rom_fwd_adjoint(self.M, self.bc, t.tensor(w.logX[:n]), t.tensor(w.F[:n]), t.tensor(w.gbar_u[:n]))
+        return time.perf_counter() - t0
+
+    def vo(self, n):
+        np_, w = self.np, self.w
+        t0 = time.perf_counter()
+        for b in range(n):   # Python loop over data points, as VirtualObservables.py:895 / :985
+            K, f = self.asm.assemble(np_.exp(w.log_image[b][self.pix]), w.g_fom[b])
+            Gamma, alpha = self.vo_ref.construct_querry_weak_galerkin(K, f, w.V)
+            _ = Gamma @ w.y[b] - alpha
+        return time.perf_counter() - t0
+
+    def step(self):
+        """One bounded sample: CGM fwd+adjoint on the whole batch, VO on ``sample`` data points."""
+        t_cgm = self.cgm(self.w.B)
+        t_vo = self.vo(self.sample)
+        per_sample = t_cgm / self.w.B + t_vo / self.sample
+        return per_sample, t_cgm / self.w.B, t_vo / self.sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import gpde_b200  # noqa: F401
+    from gpde_b200.workloads import Workload
+    w = Workload(args.workload, B=args.batch, seed=0)
+    sample = 64 if w.d <= 4095 else 8
+    ref = CpuReference(w, sample)
+    for _ in range(min(args.warmup, 2)):
+        ref.step()
+    acc, acc_c, acc_v = 0.0, 0.0, 0.0
+    t0 = time.perf_counter()
+    steps = 0
+    for _ in range(max(1, args.steps)):
+        p, c, v = ref.step()
+        acc += p; acc_c += c; acc_v += v
+        steps += 1
+        if time.perf_counter() - t0 > 120.0:
+            break
+    per = acc / steps
+    value = 1.0 / per
+    sample_desc = "per step: CGM fwd+adjoint on %d samples (torch, %d threads) + VO route on %d data points" % (
+        w.B, ref.cores, sample)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * per * w.B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "impl": "reference",
+        "config": dict(w.describe(), parallelism="host cores only"),
+        "components": {"cgm_solves_per_s": steps / acc_c, "vo_evals_per_s": steps / acc_v},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------- clocks sampler
+class ClockSampler(threading.Thread):
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for ln in self.proc.stdout:
+                self.samples.append((time.perf_counter(), ln.strip()))
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self, t0, t1):
+        rows = [s for (t, s) in self.samples if t0 <= t <= t1] or [s for (_, s) in self.samples]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            p = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except Exception:
+                continue
+            for nm, val in zip(names, p[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------- B200 arm
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic(workload, dtype):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh).get("%s_%s" % (workload, dtype))
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gpde_b200  # noqa: F401
+    from gpde_b200 import ROM as rom_mod
+    from gpde_b200.components import ReducedOrderModelOperator
+    from gpde_b200.VirtualObservables import VoPlan
+    from gpde_b200.workloads import Workload
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    s = 8 if args.dtype == "f64" else 4
+
+    # per-GPU shard of the sample-sharded batch (weak scaling: every rank owns a full workload batch)
+    w = Workload(args.workload, B=args.batch, seed=rank)
+    B = w.B
+    op = ReducedOrderModelOperator.FromPhysics(w.physics, dtype=tdt, device=dev)
+    rom = op.rom
+    rom.deferred_checks = True
+    plan = rom._get_plan()
+    vplan = VoPlan.cached(w.physics["fom"], dev, pixel_input=True)
+
+    host = dict(logX=w.logX, F=w.F, gbar=w.gbar_u, a=w.log_image, y=w.y,
+                g=(w.g_fom[0] if w.ptype == "ND" else w.g_fom), V=w.V)
+    pinned = {k: torch.tensor(v, dtype=tdt).pin_memory() for k, v in host.items()}
+    d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+    torch.cuda.synchronize()
+
+    def step_resident():
+        u, factor = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
+        gX, _ = rom_mod._launch_adjoint(plan, d["logX"], u, factor, d["gbar"], True, want_gradF=False)
+        r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
+        return u, gX, r
+
+    launches_per_step = 1 + 1 + vplan.launches_per_residual(w.m)    # rom_forward, rom_adjoint, vo residual
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    start.record()
+    for k in range(K):
+        ev[k][0].record()
+        u, factor = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
+        ev[k][1].record()
+        gX, _ = rom_mod._launch_adjoint(plan, d["logX"], u, factor, d["gbar"], True, want_gradF=False)
+        ev[k][2].record()
+        r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
+        ev[k][3].record()
+    end.record()
+    torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
+    rom.check()
+    elapsed_ms = start.elapsed_time(end)
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+    ms_per_step = elapsed_ms / K
+    t_fwd = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K)) / K
+    t_adj = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(K)) / K
+    t_vo = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(K)) / K
+
+    # ---- end to end through the public module API from pinned host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        outs = dict(u=torch.empty((B, w.n), dtype=tdt).pin_memory(), gX=torch.empty((B, w.E), dtype=tdt).pin_memory(),
+                    r=torch.empty((B, w.m), dtype=tdt).pin_memory())
+        names_in = ("logX", "F", "gbar", "a", "y", "g")
+        bytes_in = sum(pinned[k].numel() * pinned[k].element_size() for k in names_in)
+        bytes_out = sum(t.numel() * t.element_size() for t in outs.values())
+
+        def step_e2e():
+            dd = {k: pinned[k].to(dev, non_blocking=True) for k in names_in}
+            lX = dd["logX"].requires_grad_(True)
+            uu = rom.solve_log(lX, dd["F"])            # public API: autograd.Function forward
+            uu.backward(dd["gbar"])                      # ... and its adjoint
+            rr = vplan.residual(dd["a"], dd["y"], dd["g"], d["V"])
+            outs["u"].copy_(uu.detach(), non_blocking=True)
+            outs["gX"].copy_(lX.grad, non_blocking=True)
+            outs["r"].copy_(rr, non_blocking=True)
+
+        Ke = max(3, min(K, 10))
+        for _ in range(2):
+            step_e2e()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(Ke):
+            step_e2e()
+        e1.record()
+        torch.cuda.synchronize()
+        e_ms = e0.elapsed_time(e1) / Ke
+        if world > 1:
+            tt = torch.tensor([e_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e_ms = float(tt.item())
+        e2e = {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_in),
+               "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e_ms, "steps": Ke}
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    vo_bytes = w.vo_bytes_per_eval(s) * B
+    achieved = vo_bytes / (t_vo * 1e-3) / 1e9
+    cgm_bytes = w.cgm_bytes_per_solve(s) * B
+    line = {
+        "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": dict(w.describe(), per_gpu_batch=B, global_batch=world * B,
+                       parallelism="sample-sharded x%d, no data-path collective" % world,
+                       l2="inputs larger than L2: %.0f MB streamed per step per GPU" % ((vo_bytes + cgm_bytes) / 1e6)),
+        "components": {
+            "cgm_solves_per_s": world * B / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": world * B / (t_vo * 1e-3),
+            "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo,
+            "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
+        },
+        "roofline": {"kernel": "vo_fused_kernel" if vplan.launches_per_residual(w.m) == 1 else "vo_matvec_kernel + vo_contract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes},
+        "gpu_launches": launches_per_step * K,
+        "clocks": sampler.summary(t_wall0, t_wall1) if sampler else None,
+        "e2e": e2e,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        ref = CpuReference(w, 32 if w.d <= 4095 else 4)
+        ref.step()
+        t0, n, acc = time.perf_counter(), 0, 0.0
+        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 20):
+            acc += ref.step()[0]
+            n += 1
+        line["cpu_baseline"] = {
+            "value": n / acc, "unit": UNIT, "cores": ref.cores, "kind": "port",
+            "sample": "%d x (CGM fwd+adjoint on %d samples via torch autograd + VO per-data-point route on %d samples)"
+                      % (n, B, ref.sample)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -61,6 +61,7 @@ class VoPlan(object):
         info = (ctypes.c_int64 * 8)()
         _lib.check(self._lib.gpde_vo_plan_info(self.handle, info), "gpde_vo_plan_info")
         self.n_nodes, self.n_cells, self.n_inputs, self.d, self.n_bc, self.slots_per_row = (int(v) for v in info[:6])
+        self.fused_smem_bytes = int(info[7])   # 0: this mesh only runs on the unfused version-1 kernels
         self._scratch = None
 
     def __del__(self):
@@ -83,6 +84,12 @@ class VoPlan(object):
             else:
                 store[key] = cls(physics, device)
         return store[key]
+
+    def launches_per_residual(self, m):
+        """Kernels launched by one residual() call (for bench.py's gpu_launches count)."""
+        import os
+        fused = self.fused_smem_bytes > 0 and 0 < m <= 32 and os.environ.get("GPDE_VO_PATH") != "v1"
+        return 1 if fused else (2 if m > 0 else 1)
 
     def _workspace(self, B, m):
         need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, B, m)))

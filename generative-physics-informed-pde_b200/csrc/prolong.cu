@@ -71,8 +71,9 @@ static cudaError_t track_p(gpde_prolong_plan *pl, const T **dst, const std::vect
 
 template <typename T>
 static int prolong_apply(const gpde_prolong_plan *pl, const T *u, T *y, int64_t B, gpde_stream_t stream, bool transpose) {
-    if (!pl || !u || !y || B < 0) return fail(GPDE_ERR_ARG, "prolong_apply: bad argument");
+    if (!pl || B < 0) return fail(GPDE_ERR_ARG, "prolong_apply: bad argument");
     if (B == 0) return GPDE_OK;
+    if (!u || !y) return fail(GPDE_ERR_ARG, "prolong_apply: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     const int nsm = sm_count(pl->device);

@@ -345,8 +345,9 @@ static int launch_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, con
 template <typename T>
 static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const T *F, T *u, double *factor,
                        int *info, int64_t B, gpde_stream_t stream) {
-    if (!pl || !X || !F || !u || B < 0) return fail(GPDE_ERR_ARG, "rom_forward: null argument or negative batch");
+    if (!pl || B < 0) return fail(GPDE_ERR_ARG, "rom_forward: null plan or negative batch");
     if (B == 0) return GPDE_OK;
+    if (!X || !F || !u) return fail(GPDE_ERR_ARG, "rom_forward: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     switch (pl->lanes) {
@@ -359,9 +360,9 @@ static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
 template <typename T>
 static int rom_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, const T *u, const double *factor,
                        const T *gbar, T *gradX, T *gradF, int64_t B, gpde_stream_t stream) {
-    if (!pl || !X || !u || !gbar || !gradX || B < 0)
-        return fail(GPDE_ERR_ARG, "rom_adjoint: null argument or negative batch");
+    if (!pl || B < 0) return fail(GPDE_ERR_ARG, "rom_adjoint: null plan or negative batch");
     if (B == 0) return GPDE_OK;
+    if (!X || !u || !gbar || !gradX) return fail(GPDE_ERR_ARG, "rom_adjoint: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     switch (pl->lanes) {
@@ -576,8 +577,9 @@ int gpde_rom_adjoint_f32(const gpde_rom_plan *pl, const float *X, int x_is_log, 
 
 int gpde_rom_stiffness_f64(const gpde_rom_plan *pl, const double *X, double *K, int dirichlet, int64_t B,
                            gpde_stream_t stream) {
-    if (!pl || !X || !K || B < 0) return fail(GPDE_ERR_ARG, "rom_stiffness: null argument");
+    if (!pl || B < 0) return fail(GPDE_ERR_ARG, "rom_stiffness: null plan or negative batch");
     if (B == 0) return GPDE_OK;
+    if (!X || !K) return fail(GPDE_ERR_ARG, "rom_stiffness: null argument");
     DeviceGuard guard(pl->device);
     const long long total = (long long)pl->dev.n * pl->dev.n * B;
     const int threads = 256;

@@ -11,6 +11,8 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 
 namespace gpde {
 
@@ -25,18 +27,26 @@ struct VoDev {
 
 }  // namespace gpde
 
-struct gpde_vo_plan {
-    gpde::VoDev dev;
-    int device;
-    std::vector<void *> allocs;
-};
-
 namespace gpde {
 
 __device__ __forceinline__ double ldd(const double *p) { return *p; }
 __device__ __forceinline__ double ldd(const float *p) { return (double)*p; }
 
 constexpr int kVoThreads = 256;
+
+}  // namespace gpde
+
+#include "vo_fused.cuh"
+
+struct gpde_vo_plan {
+    gpde::VoDev dev;
+    gpde::VoTiles tiles;
+    size_t fused_smem;
+    int device;
+    std::vector<void *> allocs;
+};
+
+namespace gpde {
 
 // rho[b,i] for S samples per CTA.  ea (shared) = conductivities of the S samples, exp() applied.
 template <typename Ta, typename Ty, typename To, int S>
@@ -161,6 +171,121 @@ static cudaError_t track_vo(gpde_vo_plan *pl, const T **dst, const std::vector<T
     return e;
 }
 
+// Edge form + tile staging lists for the fused kernels.  Leaves pl->tiles.ok = 0 when the mesh does not
+// qualify (element matrices without zero row sums, an edge shared by more than two cells, or rings that
+// would not fit in shared memory); the version-1 kernels then serve every call.
+static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells, const int32_t *cell_dofs,
+                                     const double *Ke, const int32_t *cell_to_input, int d,
+                                     const std::vector<int> &src) {
+    VoTiles &Tl = pl->tiles;
+    memset(&Tl, 0, sizeof(Tl));
+    pl->fused_smem = 0;
+    double kmax = 0.0;
+    for (size_t k = 0; k < (size_t)n_cells * 9; ++k) kmax = std::max(kmax, fabs(Ke[k]));
+    for (int c = 0; c < n_cells; ++c)
+        for (int l = 0; l < 3; ++l)
+            if (fabs(Ke[9 * c + 3 * l] + Ke[9 * c + 3 * l + 1] + Ke[9 * c + 3 * l + 2]) > 1e-13 * kmax)
+                return cudaSuccess;   // not a pure diffusion operator
+    struct Nb { int node, in0, in1, ncell; double s0, s1; };
+    std::vector<std::vector<Nb>> nbs(d);
+    for (int c = 0; c < n_cells; ++c)
+        for (int l = 0; l < 3; ++l) {
+            const int v = cell_dofs[3 * c + l];
+            if (src[v] < 0) continue;
+            std::vector<Nb> &list = nbs[src[v]];
+            for (int l2 = 0; l2 < 3; ++l2) {
+                if (l2 == l) continue;
+                const double coef = Ke[9 * c + 3 * l + l2];
+                if (coef == 0.0) continue;
+                const int w = cell_dofs[3 * c + l2];
+                Nb *hit = nullptr;
+                for (Nb &nb : list)
+                    if (nb.node == w) hit = &nb;
+                if (!hit) {
+                    list.push_back(Nb{w, cell_to_input[c], cell_to_input[c], 1, coef, 0.0});
+                } else if (hit->ncell == 1) {
+                    hit->in1 = cell_to_input[c];
+                    hit->s1 = coef;
+                    hit->ncell = 2;
+                } else {
+                    return cudaSuccess;   // edge shared by > 2 cells
+                }
+            }
+        }
+    int nnb = 1;
+    for (int i = 0; i < d; ++i) nnb = std::max(nnb, (int)nbs[i].size());
+    std::vector<int> row_node(d);
+    for (int v = 0; v < n_nodes; ++v)
+        if (src[v] >= 0) row_node[src[v]] = v;
+    const int nt = (d + kFR - 1) / kFR;
+    std::vector<int> ulo(nt, INT32_MAX), uhi(nt, -1), alo(nt, INT32_MAX), ahi(nt, -1);
+    for (int i = 0; i < d; ++i) {
+        const int t = i / kFR;
+        ulo[t] = std::min(ulo[t], row_node[i]);
+        uhi[t] = std::max(uhi[t], row_node[i] + 1);
+        for (const Nb &nb : nbs[i]) {
+            ulo[t] = std::min(ulo[t], nb.node);
+            uhi[t] = std::max(uhi[t], nb.node + 1);
+            alo[t] = std::min(alo[t], std::min(nb.in0, nb.in1));
+            ahi[t] = std::max(ahi[t], std::max(nb.in0, nb.in1) + 1);
+        }
+    }
+    for (int t = 0; t < nt; ++t)
+        if (ahi[t] < 0) { alo[t] = 0; ahi[t] = 1; }   // a tile of isolated rows
+    RangeRing ru = build_ring(ulo, uhi), ra = build_ring(alo, ahi);
+    const size_t smem = sizeof(double) * kFS * ((size_t)ru.ring + ra.ring + kRhoPitch);
+    if (smem > 110 * 1024) return cudaSuccess;   // keep two CTAs per SM; otherwise fall back
+    const size_t tot = (size_t)nnb * d;
+    std::vector<int> row_u(d), nb_u(tot), nb_a0(tot), nb_a1(tot);
+    std::vector<double> nb_s0(tot, 0.0), nb_s1(tot, 0.0);
+    for (int i = 0; i < d; ++i) {
+        const int t = i / kFR;
+        row_u[i] = ru.offset_of(t, row_node[i]);
+        const int pad_in = nbs[i].empty() ? alo[t] : nbs[i][0].in0;
+        for (int k = 0; k < nnb; ++k) {
+            const size_t p = (size_t)k * d + i;
+            if (k < (int)nbs[i].size()) {
+                const Nb &nb = nbs[i][k];
+                nb_u[p] = ru.offset_of(t, nb.node);
+                nb_a0[p] = ra.offset_of(t, nb.in0);
+                nb_a1[p] = ra.offset_of(t, nb.in1);
+                nb_s0[p] = nb.s0;
+                nb_s1[p] = nb.s1;
+            } else {   // padding: zero conductance to itself
+                nb_u[p] = row_u[i];
+                nb_a0[p] = nb_a1[p] = ra.offset_of(t, pad_in);
+            }
+        }
+    }
+    Tl.n_tiles = nt; Tl.nnb = nnb; Tl.ring_u = ru.ring; Tl.ring_a = ra.ring;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_first, ru.first);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_count, ru.count);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_off, ru.off);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_first, ra.first);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_count, ra.count);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_off, ra.off);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.node_src, src);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.row_u, row_u);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_u, nb_u);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_a0, nb_a0);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_a1, nb_a1);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_s0, nb_s0);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_s1, nb_s1);
+    if (e == cudaSuccess) {
+        pl->fused_smem = smem;
+        Tl.ok = 1;
+    }
+    return e;
+}
+
+// GPDE_VO_PATH=v1 forces the unfused version-1 kernels (A/B testing, fallback check)
+static bool use_fused(const gpde_vo_plan *pl) {
+    if (!pl->tiles.ok) return false;
+    const char *e = getenv("GPDE_VO_PATH");
+    return !(e && strcmp(e, "v1") == 0);
+}
+
 template <typename Ta, typename Ty, typename To>
 static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride, int a_is_log, const Ty *y,
                          const Ta *g, long long g_stride, int sub_f, double *rho_ws, To *rho_out, long long B,
@@ -195,13 +320,32 @@ template <typename T>
 static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int a_is_log, const T *y, const T *g,
                        int64_t g_stride, const T *V, int m, T *r, T *rho, void *workspace, int flags, int64_t B,
                        gpde_stream_t stream) {
-    if (!pl || !a || B < 0 || m < 0) return fail(GPDE_ERR_ARG, "vo_residual: bad argument");
+    if (!pl || B < 0 || m < 0) return fail(GPDE_ERR_ARG, "vo_residual: bad argument");
+    if (B == 0) return GPDE_OK;
+    if (!a) return fail(GPDE_ERR_ARG, "vo_residual: null conductivity field");
     if (m > 0 && (!V || !r)) return fail(GPDE_ERR_ARG, "vo_residual: V and r are required when m > 0");
     if (m > 0 && !workspace) return fail(GPDE_ERR_ARG, "vo_residual: workspace required");
     if (m == 0 && !rho) return fail(GPDE_ERR_ARG, "vo_residual: nothing to compute");
     if (B == 0) return GPDE_OK;
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m > 0 && m <= 32 && use_fused(pl)) {
+        const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
+        const int sub_f = (flags & 1) ? 0 : 1;
+#define GPDE_LAUNCH_FUSED(WN)                                                                                  \
+    {                                                                                                          \
+        auto kern = vo_fused_kernel<T, WN>;                                                                    \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fused_smem)); \
+        kern<<<grid, kFR, pl->fused_smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, y, g,   \
+                                                (long long)g_stride, V, m, r, rho, sub_f, (long long)B);       \
+    }
+        if (m <= 8) GPDE_LAUNCH_FUSED(1)
+        else if (m <= 16) GPDE_LAUNCH_FUSED(2)
+        else GPDE_LAUNCH_FUSED(4)
+#undef GPDE_LAUNCH_FUSED
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
     double *ws = m > 0 ? (double *)workspace : nullptr;
     int rc = launch_matvec<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, (flags & 1) ? 0 : 1, ws, rho, B, st);
     if (rc != GPDE_OK) return rc;
@@ -216,11 +360,20 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
 template <typename T>
 static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int a_is_log, const T *V, int m,
                          const T *s, T *q, void *workspace, int64_t B, gpde_stream_t stream) {
-    if (!pl || !a || !V || !s || !q || !workspace || m <= 0 || B < 0)
-        return fail(GPDE_ERR_ARG, "vo_residual_T: bad argument");
+    if (!pl || m <= 0 || B < 0) return fail(GPDE_ERR_ARG, "vo_residual_T: bad argument");
     if (B == 0) return GPDE_OK;
+    if (!a || !V || !s || !q || !workspace) return fail(GPDE_ERR_ARG, "vo_residual_T: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_fused(pl) && pl->fused_smem + sizeof(double) * kFS * (size_t)m <= 220 * 1024) {
+        const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
+        const size_t smem = pl->fused_smem + sizeof(double) * kFS * (size_t)m;
+        auto kern = vo_fused_T_kernel<T>;
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kFR, smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, V, m, s, q, (long long)B);
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
     double *w = (double *)workspace;
     const long long total = B * (long long)pl->dev.d;
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 16);
@@ -303,6 +456,7 @@ int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c1, c1);
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c2, c2);
     if (e == cudaSuccess) e = track_vo(pl, &D.f_free, f_free);
+    if (e == cudaSuccess) e = build_fused_tiles(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, d, src);
     if (e != cudaSuccess) {
         gpde_vo_plan_destroy(pl);
         return fail(GPDE_ERR_CUDA, "vo_plan_create: upload failed: %s", cudaGetErrorString(e));
@@ -322,7 +476,8 @@ int gpde_vo_plan_destroy(gpde_vo_plan *pl) {
 int gpde_vo_plan_info(const gpde_vo_plan *pl, int64_t out[8]) {
     if (!pl || !out) return fail(GPDE_ERR_ARG, "vo_plan_info: null");
     out[0] = pl->dev.n_nodes; out[1] = pl->dev.n_cells; out[2] = pl->dev.n_inputs; out[3] = pl->dev.d;
-    out[4] = pl->dev.n_bc; out[5] = pl->dev.nslots; out[6] = pl->device; out[7] = 0;
+    out[4] = pl->dev.n_bc; out[5] = pl->dev.nslots; out[6] = pl->device;
+    out[7] = pl->tiles.ok ? (int64_t)pl->fused_smem : 0;   // bytes of shared memory of the fused path (0 = unavailable)
     return GPDE_OK;
 }
 

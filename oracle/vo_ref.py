@@ -93,3 +93,42 @@ def energy_vo_update(K, f, prec, g, mean0, Vs, temperature=1.0):
         Mm = np.array(V.T @ A @ V)
         mean = mean - V @ np.linalg.solve(Mm, V.T @ np.array(A @ mean - b).flatten())
     return mean, vars_
+
+
+class CsrAssembler(object):
+    """Vectorised restatement of ``assemble_system`` for timing the CPU route fairly: the sparsity
+    pattern of K_ff / K_fc is fixed by the mesh, so K.data = S @ a with a precomputed sparse S
+    (what FEniCS' assemble does per data point, physics/LinearElliptic.py:144-157, without the
+    form-compiler overhead).  Checked against fem_p1.assemble_system_free in the tests."""
+
+    def __init__(self, coords, cells, bc_dofs, free_dofs, Ke=None):
+        import scipy.sparse as sp
+        from . import fem_p1
+        N, E = len(coords), len(cells)
+        if Ke is None:
+            Ke = fem_p1.element_stiffness_all(coords, cells)
+        rows = np.repeat(cells, 3, axis=1).ravel()
+        cols = np.tile(cells, (1, 3)).ravel()
+        cell = np.repeat(np.arange(E), 9)
+        vals = Ke.reshape(-1)
+        keep = vals != 0
+        rows, cols, cell, vals = rows[keep], cols[keep], cell[keep], vals[keep]
+        pattern = sp.coo_matrix((np.ones_like(vals), (rows, cols)), shape=(N, N)).tocsr()
+        pattern.sum_duplicates()
+        pattern.sort_indices()
+        # position of every (row, col) contribution inside pattern.data
+        pos = np.empty(len(rows), dtype=np.int64)
+        indptr, indices = pattern.indptr, pattern.indices
+        for k in range(len(rows)):
+            lo, hi = indptr[rows[k]], indptr[rows[k] + 1]
+            pos[k] = lo + np.searchsorted(indices[lo:hi], cols[k])
+        self._S = sp.coo_matrix((vals, (pos, cell)), shape=(pattern.nnz, E)).tocsr()
+        self._pattern = pattern
+        self._free, self._bc = np.asarray(free_dofs), np.asarray(bc_dofs)
+        self._sp = sp
+
+    def assemble(self, a_cell, g):
+        K = self._sp.csr_matrix((self._S @ a_cell, self._pattern.indices, self._pattern.indptr),
+                                shape=self._pattern.shape)
+        Kf = K[self._free]
+        return Kf[:, self._free], -(Kf[:, self._bc] @ g)

@@ -1,0 +1,300 @@
+"""GPU parity of the virtual-observable path (csrc/vo.cu through the C ABI and the VirtualObservables
+mirrors) against the oracle and the reference-generated golden vectors (FP64 <= 1e-10, FP32 <= 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+def _setup(g, dev, kind=None):
+    from gpde_b200.physics import setup_physics, BoundaryConditionEnsemble
+    ph = setup_physics(int(g['nx']), int(g['nx']), int(g['refines']), str(g['kind']))
+    N = g['in_X_DG'].shape[0]
+    bce = BoundaryConditionEnsemble(ph, N, str(g['kind']), coefficients=g['in_bc_coef'])
+    assert np.allclose(bce.constrained_dofs_values('fom'), g['in_g_fom'], atol=1e-15)
+    return ph, bce
+
+
+@pytest.mark.parametrize("name", ["vo_4x4_32_ndp", "vo_2x2_8_nd"])
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_residual_kernels_against_reference_vectors(name, dtype, dev):
+    from gpde_b200.VirtualObservables import VoPlan
+    g = load_golden(name)
+    ph, bce = _setup(g, dev)
+    plan = VoPlan.cached(ph['fom'], dev)
+    a = torch.tensor(g['in_X_DG'], dtype=dtype, device=dev)
+    y = torch.tensor(g['in_Y'], dtype=dtype, device=dev)
+    gv = torch.tensor(g['in_g_fom'], dtype=dtype, device=dev)
+    V = torch.tensor(g['in_V'], dtype=dtype, device=dev)
+    r, rho = plan.residual(a, y, gv, V, want_rho=True)
+    if dtype == torch.float64:
+        want_r = g['out_residual']
+        Gam, alp = g['out_Gamma'], g['out_alpha']
+        tol = 1e-10
+    else:   # oracle on the float32-rounded inputs
+        from oracle import fem_p1, vo_ref
+        P = fem_p1.build_problem(int(g['nx']), int(g['nx']), int(g['refines']))
+        Vd = V.double().cpu().numpy()
+        want_r, Gam, alp = [], [], []
+        for n in range(a.shape[0]):
+            K, f = fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], np.exp(a[n].double().cpu().numpy()),
+                                               P['bc_dofs_fom'], gv[n].double().cpu().numpy(), P['free_dofs_fom'])
+            Ga, al = vo_ref.construct_querry_weak_galerkin(K, f, Vd)
+            Gam.append(Ga); alp.append(al)
+            want_r.append(Ga @ y[n].double().cpu().numpy() - al)
+        want_r, Gam, alp = np.stack(want_r), np.stack(Gam), np.stack(alp)
+        tol = 1e-5
+    assert rel_err(r.cpu(), want_r) < tol
+    # rho is the fine residual itself: r = rho V
+    assert rel_err((rho.double() @ V.double()).cpu(), want_r) < (1e-10 if dtype == torch.float64 else 1e-5)
+    # transposed application q = K_ff V s = Gamma^T s
+    s = torch.tensor(np.random.RandomState(0).normal(size=(a.shape[0], V.shape[1])), dtype=dtype, device=dev)
+    q = plan.residual_T(a, V, s)
+    want_q = np.einsum('nmd,nm->nd', Gam, s.double().cpu().numpy())
+    assert rel_err(q.cpu(), want_q) < tol
+    # shared field (a_stride = 0) and shared Dirichlet data
+    r0 = plan.residual(a[0], y, gv[0], V)
+    r0_ref = np.stack([Gam[0] @ y[n].double().cpu().numpy() - alp[0] for n in range(a.shape[0])])
+    assert rel_err(r0.cpu(), r0_ref) < tol
+
+
+@pytest.mark.parametrize("name", ["vo_4x4_32_ndp", "vo_2x2_8_nd"])
+def test_gamma_alpha_and_posterior_update_against_reference_vectors(name, dev):
+    from gpde_b200 import VirtualObservables as VO
+    g = load_golden(name)
+    ph, bce = _setup(g, dev)
+    V, mask = g['in_V'], g['in_mask']
+
+    class FixedSampler(VO.BaseSampler):
+        is_constant = True
+
+        def __init__(self, qp):
+            super().__init__(qp)
+            self.m = V.shape[1]
+
+        precision_mask = property(lambda self: mask)
+
+        def _sample(self):
+            return V
+
+    qpe = VO.QuerryPointEnsemble.FromArrays(g['in_X_DG'], bce, ph['fom'], device=dev)
+    qe = VO.QuerryEnsemble([VO.LinearQuerry(qp, FixedSampler(qp), torch.double, dev) for qp in qpe], torch.double, dev)
+    for n, q in enumerate(qe):
+        assert q.Gamma.dtype == torch.double and q.Gamma.shape == g['out_Gamma'][n].shape
+        assert rel_err(q.Gamma.cpu(), g['out_Gamma'][n]) < 1e-12
+        assert rel_err(q.alpha.cpu(), g['out_alpha'][n]) < 1e-11
+        assert torch.equal(q.GammaTransposed, q.Gamma.t())
+    Gn, an = qpe[0].construct_querry_weak_galerkin(V)          # numpy flavour of the reference API
+    assert isinstance(Gn, np.ndarray) and rel_err(Gn, g['out_Gamma'][0]) < 1e-12 and rel_err(an, g['out_alpha'][0]) < 1e-11
+
+    ens = VO.VirtualObservablesEnsemble(qpe, qe, torch.double, dev)
+    assert ens.N == g['in_Y'].shape[0] and ens.m == V.shape[1] and ens.dim_out == g['in_Y'].shape[1]
+    assert not ens.fixed_precision
+    ens.update(torch.tensor(g['in_Y'], device=dev), torch.tensor(g['in_PREC1'], device=dev), 0)
+    assert rel_err(ens.mean.cpu(), g['out_mean1']) < 1e-9
+    assert rel_err(ens.vars.cpu(), g['out_vars1']) < 1e-8
+    ens.update(torch.tensor(g['in_G2'], device=dev), torch.tensor(g['in_PREC2'], device=dev), 1)
+    assert rel_err(ens._prec_beta.cpu(), g['out_prec_beta']) < 1e-8
+    assert rel_err(ens._mean_vo_variances.cpu(), g['out_mean_vo_variances']) < 1e-8
+    assert rel_err(ens.mean.cpu(), g['out_mean2']) < 1e-8
+    assert rel_err(ens.vars.cpu(), g['out_vars2']) < 1e-7
+    assert rel_err(ens.logsigma.cpu(), 0.5 * np.log(g['out_vars2'])) < 1e-7
+    # single data point through VirtualObservable.update == the batched ensemble pass
+    vo = ens[1]
+    keep = vo.mean.clone()
+    vo.update(torch.tensor(g['in_G2'][1], device=dev), torch.tensor(g['in_PREC2'][1], device=dev), 1, ForceUpdate=True)
+    assert rel_err(vo.mean.cpu(), keep.cpu()) < 1e-12
+    with pytest.raises(RuntimeError):
+        vo.update(None, None, 0)
+    # all residuals of the ensemble in one launch
+    r = ens.residuals(torch.tensor(g['in_Y'], device=dev), V)
+    assert rel_err(r.cpu(), g['out_residual']) < 1e-10
+
+
+def test_reference_style_construction_and_samplers(dev):
+    """QuerryEnsemble.FromQuerryPointEnsemble with CGR + Gaussian + RBF samplers, resample()."""
+    from gpde_b200 import VirtualObservables as VO
+    from oracle import fem_p1, vo_ref
+    g = load_golden("vo_2x2_8_nd")
+    ph, bce = _setup(g, dev)
+    qpe = VO.QuerryPointEnsemble.FromArrays(g['in_X_DG'], bce, ph['fom'])
+    np.random.seed(5)
+    qe = VO.QuerryEnsemble.FromQuerryPointEnsemble(qpe, ph, CGR=True, flux=False, N_gaussian=2, N_rbf=3, l_rbf=0.2,
+                                                   dtype=torch.double, device=dev)
+    assert qe.N == len(qpe) and qe[0].m == ph['W'].shape[1] + 5 and qe.m == qe.N * qe[0].m
+    assert np.all(qe.precision_mask < 0)
+    ens = VO.VirtualObservablesEnsemble(qpe, qe, torch.double, dev)
+    assert ens.fixed_precision
+    P = fem_p1.build_problem(2, 2, 2)
+    K, f = fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], np.exp(g['in_X_DG'][0]), P['bc_dofs_fom'],
+                                       g['in_g_fom'][0], P['free_dofs_fom'])
+    # the CGR block of Gamma is W^T K
+    Gam0, al0 = vo_ref.construct_querry_weak_galerkin(K, f, ph['W'])
+    assert rel_err(qe[0].Gamma[:ph['W'].shape[1]].cpu(), Gam0) < 1e-12
+    before = qe[0].Gamma.clone()
+    ens.resample()
+    after = qe[0].Gamma
+    assert rel_err(after[:ph['W'].shape[1]].cpu(), Gam0) < 1e-12
+    assert not torch.equal(before[-5:], after[-5:])               # random samplers were redrawn
+    # infinite precision: the posterior mean satisfies Gamma mean = alpha
+    N, d = g['in_Y'].shape
+    ens.update(torch.tensor(g['in_Y'], device=dev), torch.full((N, d), 100.0, dtype=torch.double, device=dev), 0)
+    for n in range(N):
+        res = qe[n].Gamma @ ens.mean[n] - qe[n].alpha
+        assert res.abs().max() < 1e-8
+    with pytest.raises(NotImplementedError):
+        VO.QuerryEnsemble.FromQuerryPointEnsemble(qpe, ph, True, True, 0, 0, dtype=torch.double, device=dev)
+
+
+def test_pixel_input_plan_matches_cell_input_plan(dev):
+    from gpde_b200.VirtualObservables import VoPlan
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg1", B=7, seed=3)
+    fom = w.physics['fom']
+    pix_plan, cell_plan = VoPlan.cached(fom, dev, pixel_input=True), VoPlan.cached(fom, dev)
+    img = torch.tensor(w.log_image, device=dev)
+    X_DG = img[:, torch.tensor(fom.mesh.pixel_of_cell(), device=dev)]
+    y, gv, V = (torch.tensor(t, device=dev) for t in (w.y, w.g_fom, w.V))
+    assert torch.equal(pix_plan.residual(img, y, gv, V), cell_plan.residual(X_DG, y, gv, V))
+    assert pix_plan.n_inputs == 1024 and cell_plan.n_inputs == 2048 and pix_plan.slots_per_row == 6
+
+
+def test_autograd_through_residual(dev):
+    from gpde_b200.VirtualObservables import VoPlan, VoResidualFn
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg1", B=2, seed=1)
+    plan = VoPlan.cached(w.physics['fom'], dev, pixel_input=True)
+    a, gv, V = (torch.tensor(t, device=dev) for t in (w.log_image, w.g_fom, w.V[:, :4].copy()))
+    y = torch.tensor(w.y, device=dev, requires_grad=True)
+    # 0.5 |r|^2 -> dL/dy = K_ff V r; compare with finite differences along a random direction
+    r = VoResidualFn.apply(y, a, gv, V, plan, True)
+    (0.5 * (r ** 2).sum()).backward()
+    dirn = torch.randn_like(y)
+    eps = 1e-6
+    lp = 0.5 * (plan.residual(a, y.detach() + eps * dirn, gv, V) ** 2).sum()
+    lm = 0.5 * (plan.residual(a, y.detach() - eps * dirn, gv, V) ** 2).sum()
+    fd = (lp - lm) / (2 * eps)
+    assert abs(fd.item() - (y.grad * dirn).sum().item()) < 1e-6 * max(1.0, abs(fd.item()))
+
+
+@pytest.mark.parametrize("diag", ["right", "alternating"])
+def test_other_fine_mesh_patterns(diag, dev):
+    """The fine connectivity is an input of the plan (refine() may give either)."""
+    from gpde_b200.physics import setup_physics, BoundaryConditionEnsemble
+    from gpde_b200.VirtualObservables import VoPlan
+    from oracle import fem_p1, vo_ref
+    ph = setup_physics(2, 2, 3, "NDP", diagonal=diag)
+    rng = np.random.RandomState(2)
+    bce = BoundaryConditionEnsemble(ph, 3, "NDP", rng=rng)
+    fom = ph['fom']
+    X = rng.normal(0.4, 0.8, size=(3, fom.dim_in))
+    Y = rng.normal(size=(3, fom.dim_out))
+    V = rng.normal(size=(fom.dim_out, 7))
+    plan = VoPlan(fom, dev)
+    r = plan.residual(torch.tensor(X, device=dev), torch.tensor(Y, device=dev),
+                      torch.tensor(bce.constrained_dofs_values('fom'), device=dev), torch.tensor(V, device=dev))
+    c, cells = fem_p1.unit_square_mesh(16, 16, diag)
+    bc, _, free = fem_p1.dirichlet_left_right(c, 'ND')
+    for n in range(3):
+        K, f = fem_p1.assemble_system_free(c, cells, np.exp(X[n]), bc, bce.constrained_dofs_values('fom')[n], free)
+        assert rel_err(r[n].cpu(), vo_ref.vo_residual(K, f, V, Y[n])) < 1e-10
+    assert plan.slots_per_row == (6 if diag == "right" else 8)
+
+
+def test_full_size_properties_config2(dev):
+    """64x64 FOM, batch 4096 (BASELINE config 2): closed-form zero residual, linearity, r = rho V."""
+    from gpde_b200.VirtualObservables import VoPlan
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg2", B=4096, seed=0)
+    fom = w.physics['fom']
+    plan = VoPlan.cached(fom, dev, pixel_input=True)
+    V = torch.tensor(w.V, device=dev)
+    gv = torch.tensor(w.g_fom[0], device=dev)            # ND: shared Dirichlet data
+    B = w.B
+    gen = torch.Generator().manual_seed(1)
+    # uniform medium (a different constant per sample): y = x-coordinate solves the PDE exactly
+    a_u = torch.randn(B, 1, generator=gen, dtype=torch.float64).expand(B, w.P).contiguous().to(dev)
+    yx = torch.tensor(fom.mesh.coords[fom.free_dofs, 0], device=dev).expand(B, -1).contiguous()
+    r, rho = plan.residual(a_u, yx, gv, V, want_rho=True)
+    assert rho.abs().max() < 1e-11 and r.abs().max() < 1e-11
+    # linearity in (y, g): r(y1 + y2, 2g) - r(y1, g) - r(y2, g) = 0, random log-normal fields
+    a = torch.tensor(w.log_image, device=dev)
+    y1 = torch.tensor(w.y, device=dev)
+    y2 = torch.randn(B, w.d, generator=gen, dtype=torch.float64).to(dev)
+    r1, r2, r12 = plan.residual(a, y1, gv, V), plan.residual(a, y2, gv, V), plan.residual(a, y1 + y2, 2 * gv, V)
+    assert rel_err((r1 + r2).cpu(), r12.cpu()) < 1e-12
+    # sample independence (bitwise) and r = rho V
+    perm = torch.randperm(B, generator=gen).to(dev)
+    assert torch.equal(plan.residual(a[perm], y1[perm], gv, V), r1[perm])
+    _, rho1 = plan.residual(a, y1, gv, V, want_rho=True)
+    assert rel_err((rho1 @ V).cpu(), r1.cpu()) < 1e-12
+    # transposed op is the adjoint of the residual map: <s, Gamma y> = <Gamma^T s, y>  (g = 0, no load)
+    s = torch.randn(B, w.m, generator=gen, dtype=torch.float64).to(dev)
+    lhs = (s * plan.residual(a, y2, None, V, ignore_load=True)).sum(dim=1)
+    rhs = (plan.residual_T(a, V, s) * y2).sum(dim=1)
+    assert rel_err(lhs.cpu(), rhs.cpu()) < 1e-11
+
+
+def test_schedules_and_guards(dev):
+    from gpde_b200 import VirtualObservables as VO, _lib
+    lin = VO.LinearTemperatureSchedule(1.0, 1e-4, 11)
+    assert lin.get_temperature(0) == 1.0 and abs(lin.get_temperature(10) - 1e-4) < 1e-15
+    ex = VO.ExponentialTemperatureSchedule(1.0, 1e-4, 11)
+    assert abs(ex.get_temperature(5) - 1e-2) < 1e-12
+    with pytest.raises(RuntimeError):
+        lin.get_temperature(12)
+    from gpde_b200.physics import setup_physics
+    ph = setup_physics(2, 2, 1)
+    with pytest.raises(_lib.GpdeLibraryError):        # no CPU fallback
+        VO.VoPlan(ph['fom'], torch.device("cpu"))
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
+    """The fused (edge form + ring staging + FP64 MMA) kernel against the version-1 kernels, including a
+    ragged batch (B % 8 != 0), every column-tile variant (m <= 8, 16, 32) and m > 32 (unfused only)."""
+    from gpde_b200.VirtualObservables import VoPlan
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg1", B=21, seed=5)
+    plan = VoPlan.cached(w.physics['fom'], dev, pixel_input=True)
+    assert plan.fused_smem_bytes > 0
+    a, y, gv = (torch.tensor(t, dtype=dtype, device=dev) for t in (w.log_image, w.y, w.g_fom))
+    rng = np.random.RandomState(0)
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    for m in (1, 7, 8, 13, 16, 25, 32, 40):
+        V = torch.tensor(rng.normal(size=(w.d, m)), dtype=dtype, device=dev)
+        s = torch.tensor(rng.normal(size=(21, m)), dtype=dtype, device=dev)
+        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        r2, rho2 = plan.residual(a, y, gv, V, want_rho=True)
+        q2 = plan.residual_T(a, V, s)
+        monkeypatch.setenv("GPDE_VO_PATH", "v1")
+        assert plan.launches_per_residual(m) == 2
+        r1, rho1 = plan.residual(a, y, gv, V, want_rho=True)
+        q1 = plan.residual_T(a, V, s)
+        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        assert rel_err(r2.cpu(), r1.cpu()) < tol, m
+        assert rel_err(rho2.cpu(), rho1.cpu()) < tol, m
+        assert rel_err(q2.cpu(), q1.cpu()) < tol, m
+    # rho only (no weighting matrix)
+    _, rho = plan.residual(a, y, gv, None)
+    assert rel_err(rho.cpu(), rho1.cpu()) < tol
+
+
+def test_unfused_kernels_against_reference_vectors(dev, monkeypatch):
+    from gpde_b200.VirtualObservables import VoPlan
+    monkeypatch.setenv("GPDE_VO_PATH", "v1")
+    g = load_golden("vo_4x4_32_ndp")
+    ph, bce = _setup(g, dev)
+    plan = VoPlan(ph['fom'], dev)
+    a, y, gv, V = (torch.tensor(g[k], device=dev) for k in ('in_X_DG', 'in_Y', 'in_g_fom', 'in_V'))
+    assert rel_err(plan.residual(a, y, gv, V).cpu(), g['out_residual']) < 1e-10
