@@ -176,7 +176,7 @@ static cudaError_t track_vo(gpde_vo_plan *pl, const T **dst, const std::vector<T
 // would not fit in shared memory); the version-1 kernels then serve every call.
 static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells, const int32_t *cell_dofs,
                                      const double *Ke, const int32_t *cell_to_input, int d,
-                                     const std::vector<int> &src) {
+                                     const std::vector<int> &src, const std::vector<double> &pl_f_free) {
     VoTiles &Tl = pl->tiles;
     memset(&Tl, 0, sizeof(Tl));
     pl->fused_smem = 0;
@@ -214,18 +214,18 @@ static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells,
         }
     int nnb = 1;
     for (int i = 0; i < d; ++i) nnb = std::max(nnb, (int)nbs[i].size());
-    std::vector<int> row_node(d);
-    for (int v = 0; v < n_nodes; ++v)
-        if (src[v] >= 0) row_node[src[v]] = v;
     const int nt = (d + kFR - 1) / kFR;
+    // u ring holds y by free index; a ring holds the conductivity inputs
     std::vector<int> ulo(nt, INT32_MAX), uhi(nt, -1), alo(nt, INT32_MAX), ahi(nt, -1);
     for (int i = 0; i < d; ++i) {
         const int t = i / kFR;
-        ulo[t] = std::min(ulo[t], row_node[i]);
-        uhi[t] = std::max(uhi[t], row_node[i] + 1);
+        ulo[t] = std::min(ulo[t], i);
+        uhi[t] = std::max(uhi[t], i + 1);
         for (const Nb &nb : nbs[i]) {
-            ulo[t] = std::min(ulo[t], nb.node);
-            uhi[t] = std::max(uhi[t], nb.node + 1);
+            if (src[nb.node] >= 0) {
+                ulo[t] = std::min(ulo[t], src[nb.node]);
+                uhi[t] = std::max(uhi[t], src[nb.node] + 1);
+            }
             alo[t] = std::min(alo[t], std::min(nb.in0, nb.in1));
             ahi[t] = std::max(ahi[t], std::max(nb.in0, nb.in1) + 1);
         }
@@ -233,45 +233,59 @@ static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells,
     for (int t = 0; t < nt; ++t)
         if (ahi[t] < 0) { alo[t] = 0; ahi[t] = 1; }   // a tile of isolated rows
     RangeRing ru = build_ring(ulo, uhi), ra = build_ring(alo, ahi);
-    const size_t smem = sizeof(double) * kFS * ((size_t)ru.ring + ra.ring + kRhoPitch);
+    const int n_bc = pl->dev.n_bc;
+    const int block_bytes = nnb * kFR * 32 + kFR * 8;
+    const int g_base = ru.ring * kPitchB;
+    const int a_base = g_base + n_bc * kPitchB;
+    const int rs_base = a_base + ra.ring * kPitchB;
+    const int rec_base = rs_base + (int)sizeof(double) * kFS * kRhoPitch;
+    const int meta_base = rec_base + block_bytes;
+    const size_t smem = (size_t)meta_base + (size_t)nt * sizeof(TileMeta);
     if (smem > 110 * 1024) return cudaSuccess;   // keep two CTAs per SM; otherwise fall back
-    const size_t tot = (size_t)nnb * d;
-    std::vector<int> row_u(d), nb_u(tot), nb_a0(tot), nb_a1(tot);
-    std::vector<double> nb_s0(tot, 0.0), nb_s1(tot, 0.0);
-    for (int i = 0; i < d; ++i) {
-        const int t = i / kFR;
-        row_u[i] = ru.offset_of(t, row_node[i]);
-        const int pad_in = nbs[i].empty() ? alo[t] : nbs[i][0].in0;
-        for (int k = 0; k < nnb; ++k) {
-            const size_t p = (size_t)k * d + i;
-            if (k < (int)nbs[i].size()) {
-                const Nb &nb = nbs[i][k];
-                nb_u[p] = ru.offset_of(t, nb.node);
-                nb_a0[p] = ra.offset_of(t, nb.in0);
-                nb_a1[p] = ra.offset_of(t, nb.in1);
-                nb_s0[p] = nb.s0;
-                nb_s1[p] = nb.s1;
-            } else {   // padding: zero conductance to itself
-                nb_u[p] = row_u[i];
-                nb_a0[p] = nb_a1[p] = ra.offset_of(t, pad_in);
+    std::vector<TileMeta> meta(nt);
+    std::vector<char> blocks((size_t)nt * block_bytes, 0);
+    for (int t = 0; t < nt; ++t) {
+        meta[t] = TileMeta{ru.first[t], ru.count[t], ru.off[t], ra.first[t], ra.count[t], ra.off[t], 0, 0};
+        char *blk = blocks.data() + (size_t)t * block_bytes;
+        int4 *ro = reinterpret_cast<int4 *>(blk);
+        double2 *rc = reinterpret_cast<double2 *>(blk + (size_t)nnb * kFR * 16);
+        double *fo = reinterpret_cast<double *>(blk + (size_t)nnb * kFR * 32);
+        for (int k = 0; k < kFR; ++k) {
+            const int i = t * kFR + k;
+            if (i >= d) {   // rows past the end: harmless offsets, zero coefficients
+                for (int s = 0; s < nnb; ++s) {
+                    ro[s * kFR + k] = make_int4(0, a_base, a_base, 0);
+                    rc[s * kFR + k] = make_double2(0.0, 0.0);
+                }
+                fo[k] = 0.0;
+                continue;
             }
+            const int own = ru.offset_of(t, i) * kPitchB;
+            const int pad_in = nbs[i].empty() ? alo[t] : nbs[i][0].in0;
+            for (int s = 0; s < nnb; ++s) {
+                if (s < (int)nbs[i].size()) {
+                    const Nb &nb = nbs[i][s];
+                    const int sj = src[nb.node];
+                    const int ou = sj >= 0 ? ru.offset_of(t, sj) * kPitchB : g_base + (-sj - 1) * kPitchB;
+                    ro[s * kFR + k] = make_int4(ou, a_base + ra.offset_of(t, nb.in0) * kPitchB,
+                                                a_base + ra.offset_of(t, nb.in1) * kPitchB, own);
+                    rc[s * kFR + k] = make_double2(nb.s0, nb.s1);
+                } else {   // padding: zero conductance to itself
+                    const int oa = a_base + ra.offset_of(t, pad_in) * kPitchB;
+                    ro[s * kFR + k] = make_int4(own, oa, oa, own);
+                    rc[s * kFR + k] = make_double2(0.0, 0.0);
+                }
+            }
+            fo[k] = pl_f_free[i];
         }
     }
-    Tl.n_tiles = nt; Tl.nnb = nnb; Tl.ring_u = ru.ring; Tl.ring_a = ra.ring;
+    Tl.n_tiles = nt; Tl.nnb = nnb; Tl.ring_u = ru.ring; Tl.ring_a = ra.ring; Tl.n_bc = n_bc;
+    Tl.g_base = g_base; Tl.a_base = a_base; Tl.rs_base = rs_base;
+    Tl.rec_base = rec_base; Tl.meta_base = meta_base; Tl.block_bytes = block_bytes;
+    Tl.async_ok = (ru.mode != 0 && ra.mode != 0) ? 1 : 0;
     cudaError_t e = cudaSuccess;
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_first, ru.first);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_count, ru.count);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.u_off, ru.off);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_first, ra.first);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_count, ra.count);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.a_off, ra.off);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.node_src, src);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.row_u, row_u);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_u, nb_u);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_a0, nb_a0);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_a1, nb_a1);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_s0, nb_s0);
-    if (e == cudaSuccess) e = track_vo(pl, &Tl.nb_s1, nb_s1);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.meta, meta);
+    if (e == cudaSuccess) e = track_vo(pl, &Tl.blocks, blocks);
     if (e == cudaSuccess) {
         pl->fused_smem = smem;
         Tl.ok = 1;
@@ -332,11 +346,13 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
     if (m > 0 && m <= 32 && use_fused(pl)) {
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
         const int sub_f = (flags & 1) ? 0 : 1;
+        constexpr bool kCanAsync = sizeof(T) == 8;
+        const bool use_async = kCanAsync && pl->tiles.async_ok && !getenv("GPDE_VO_SYNC_STAGING");
 #define GPDE_LAUNCH_FUSED(WN)                                                                                  \
     {                                                                                                          \
-        auto kern = vo_fused_kernel<T, WN>;                                                                    \
+        auto kern = use_async ? vo_fused_kernel<T, WN, kCanAsync> : vo_fused_kernel<T, WN, false>;             \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->fused_smem)); \
-        kern<<<grid, kFR, pl->fused_smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, y, g,   \
+        kern<<<grid, kFT, pl->fused_smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, y, g,   \
                                                 (long long)g_stride, V, m, r, rho, sub_f, (long long)B);       \
     }
         if (m <= 8) GPDE_LAUNCH_FUSED(1)
@@ -365,12 +381,12 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     if (!a || !V || !s || !q || !workspace) return fail(GPDE_ERR_ARG, "vo_residual_T: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (use_fused(pl) && pl->fused_smem + sizeof(double) * kFS * (size_t)m <= 220 * 1024) {
+    if (use_fused(pl) && sizeof(double) * kFS * (size_t)m <= sizeof(double) * kFS * kRhoPitch) {
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
-        const size_t smem = pl->fused_smem + sizeof(double) * kFS * (size_t)m;
+        const size_t smem = pl->fused_smem;   // the coefficient vectors live in the (unused) rho tile
         auto kern = vo_fused_T_kernel<T>;
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kFR, smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, V, m, s, q, (long long)B);
+        kern<<<grid, kFT, smem, st>>>(pl->dev, pl->tiles, a, (long long)a_stride, a_is_log, V, m, s, q, (long long)B);
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
     }
@@ -456,7 +472,7 @@ int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c1, c1);
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c2, c2);
     if (e == cudaSuccess) e = track_vo(pl, &D.f_free, f_free);
-    if (e == cudaSuccess) e = build_fused_tiles(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, d, src);
+    if (e == cudaSuccess) e = build_fused_tiles(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, d, src, f_free);
     if (e != cudaSuccess) {
         gpde_vo_plan_destroy(pl);
         return fail(GPDE_ERR_CUDA, "vo_plan_create: upload failed: %s", cudaGetErrorString(e));

@@ -288,6 +288,11 @@ def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
     # rho only (no weighting matrix)
     _, rho = plan.residual(a, y, gv, None)
     assert rel_err(rho.cpu(), rho1.cpu()) < tol
+    # synchronous staging flavour of the fused kernel (what FP32 inputs and non-monotone rings use)
+    monkeypatch.setenv("GPDE_VO_SYNC_STAGING", "1")
+    r3 = plan.residual(a, y, gv, V)
+    monkeypatch.delenv("GPDE_VO_SYNC_STAGING", raising=False)
+    assert torch.equal(r3, plan.residual(a, y, gv, V))
 
 
 def test_unfused_kernels_against_reference_vectors(dev, monkeypatch):
