@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Turns an .ncu-rep (from `ncu --set full`) into the small text summary committed under profiles/.
+
+    python profiles/tools/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/r1_xxx.ncu.txt
+
+Reads the report with `ncu -i ... --page raw --csv` (works without a GPU) and prints, per profiled launch,
+the counters DESIGN.md and bench.py's roofline object refer to.
+"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    "gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
+    "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__bytes_read.sum.per_second",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fp64.sum", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    print("# %s" % path)
+    for n, r in enumerate(rows[2:]):
+        print("\n## launch %d: %s" % (n, r[col["Kernel Name"]][:110]))
+        for k in KEYS:
+            if k in col:
+                print("%-82s %16s %s" % (k, r[col[k]], units[col[k]]))
+        try:
+            rd = float(r[col["dram__bytes_read.sum"]]); wr = float(r[col["dram__bytes_write.sum"]])
+            ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            print("%-82s %16.0f byte" % ("traffic = dram read + write (per launch)", rd * scale[ur] + wr * scale[uw]))
+        except Exception:
+            pass
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
