@@ -234,7 +234,7 @@ def run_b200(args):
         r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
         return u, gX, r
 
-    launches_per_step = 1 + 1 + vplan.launches_per_residual(w.m)    # rom_forward, rom_adjoint, vo residual
+    launches_per_step = 1 + 1 + vplan.launches_per_residual(w.m, tdt)    # rom_forward, rom_adjoint, vo residual
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -333,7 +333,8 @@ def run_b200(args):
             "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
         },
-        "roofline": {"kernel": "vo_fused_kernel" if vplan.launches_per_residual(w.m) == 1 else "vo_matvec_kernel + vo_contract_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": {2: "vo_grid_kernel (+ vo_grid_pack_kernel)", 1: "vo_fused_kernel"}.get(
+                         vplan.kernel_path(w.m, tdt), "vo_matvec_kernel + vo_contract_kernel"), "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes},
         "gpu_launches": launches_per_step * K,

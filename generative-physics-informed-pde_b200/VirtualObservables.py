@@ -85,11 +85,14 @@ class VoPlan(object):
                 store[key] = cls(physics, device)
         return store[key]
 
-    def launches_per_residual(self, m):
+    def kernel_path(self, m, dtype=torch.float64):
+        """2 = structured-grid kernel, 1 = generic fused kernel, 0 = version-1 kernels (include/gpde_b200.h)."""
+        return int(self._lib.gpde_vo_plan_kernel_path(self.handle, int(m), 8 if dtype == torch.float64 else 4))
+
+    def launches_per_residual(self, m, dtype=torch.float64):
         """Kernels launched by one residual() call (for bench.py's gpu_launches count)."""
-        import os
-        fused = self.fused_smem_bytes > 0 and 0 < m <= 32 and os.environ.get("GPDE_VO_PATH") != "v1"
-        return 1 if fused else (2 if m > 0 else 1)
+        path = self.kernel_path(m, dtype)
+        return {2: 2, 1: 1}.get(path, 2 if m > 0 else 1)
 
     def _workspace(self, B, m):
         need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, B, m)))

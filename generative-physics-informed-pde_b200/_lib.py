@@ -43,6 +43,7 @@ SIGNATURES = {
                                     c_vp, c_i32]),
     "gpde_vo_plan_destroy": (c_i32, [c_vp]),
     "gpde_vo_plan_info": (c_i32, [c_vp, c_vp]),
+    "gpde_vo_plan_kernel_path": (c_i32, [c_vp, c_i32, c_i32]),
     "gpde_vo_workspace_bytes": (c_sz, [c_vp, c_i64, c_i32]),
     "gpde_vo_residual_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp,
                                      c_vp, c_i32, c_i64, c_vp]),

@@ -37,10 +37,12 @@ constexpr int kVoThreads = 256;
 }  // namespace gpde
 
 #include "vo_fused.cuh"
+#include "vo_grid.cuh"
 
 struct gpde_vo_plan {
     gpde::VoDev dev;
     gpde::VoTiles tiles;
+    gpde::GridDev grid;
     size_t fused_smem;
     int device;
     std::vector<void *> allocs;
@@ -293,11 +295,162 @@ static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells,
     return e;
 }
 
+
+// Structured-grid detection for vo_grid.cuh.  Leaves pl->grid.ok = 0 unless the element data is exactly the
+// 5-point pixel operator the grid kernel evaluates (every check below is against the arrays the caller
+// passed, nothing is assumed from names):
+//   nodes (nx+1) x (ny+1) numbered x-fastest; Dirichlet dofs = the columns ix = 0 and ix = nx, listed row by
+//   row (left, right); free dofs = all other nodes ascending; two cells per pixel sharing one input entry
+//   in0 + cy*sy + cx; horizontal / vertical couplings uniform (chs / cvs), hypotenuse couplings zero.
+static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, const int32_t *cell_dofs,
+                                   const double *Ke, const int32_t *cell_to_input, int n_inputs,
+                                   const int64_t *free_dofs, int d, const int64_t *bc_dofs, int n_bc,
+                                   const std::vector<double> &f_free) {
+    GridDev &G = pl->grid;
+    memset(&G, 0, sizeof(G));
+    if (n_bc < 4 || (n_bc & 1) || bc_dofs[0] != 0) return cudaSuccess;
+    const long long nxn = bc_dofs[1] + 1;               // nodes per row
+    if (nxn < 3 || n_nodes % nxn != 0) return cudaSuccess;
+    const int nx = (int)nxn - 1, nyn = (int)(n_nodes / nxn), ny = nyn - 1, ncol = nx - 1;
+    if (ny < 1 || n_bc != 2 * nyn || d != ncol * nyn || n_cells != 2 * nx * ny || n_inputs != nx * ny) return cudaSuccess;
+    if ((nx & 1) || ncol > 256) return cudaSuccess;       // pixel rows must be whole 16-byte units
+    for (int r = 0; r < nyn; ++r)
+        if (bc_dofs[2 * r] != (long long)r * nxn || bc_dofs[2 * r + 1] != (long long)r * nxn + nx) return cudaSuccess;
+    for (int i = 0; i < d; ++i)
+        if (free_dofs[i] != (long long)(i / ncol) * nxn + 1 + i % ncol) return cudaSuccess;
+    double kmax = 0.0;
+    for (size_t k = 0; k < (size_t)n_cells * 9; ++k) kmax = std::max(kmax, fabs(Ke[k]));
+    if (!(kmax > 0.0)) return cudaSuccess;
+    const double tol = 1e-13 * kmax;
+    std::vector<int> sq_input((size_t)nx * ny, -1), sq_count((size_t)nx * ny, 0);
+    // side coverage per square: bottom, top (horizontal), left, right (vertical)
+    std::vector<unsigned char> side((size_t)nx * ny * 4, 0);
+    double chs = 0.0, cvs = 0.0;
+    bool have_h = false, have_v = false;
+    for (int c = 0; c < n_cells; ++c) {
+        int ix[3], iy[3];
+        for (int l = 0; l < 3; ++l) {
+            ix[l] = cell_dofs[3 * c + l] % (int)nxn;
+            iy[l] = cell_dofs[3 * c + l] / (int)nxn;
+        }
+        const int cx = std::min(ix[0], std::min(ix[1], ix[2])), cy = std::min(iy[0], std::min(iy[1], iy[2]));
+        if (cx >= nx || cy >= ny) return cudaSuccess;
+        for (int l = 0; l < 3; ++l)
+            if (ix[l] - cx > 1 || iy[l] - cy > 1) return cudaSuccess;
+        const size_t sq = (size_t)cy * nx + cx;
+        if (sq_count[sq] == 0) sq_input[sq] = cell_to_input[c];
+        else if (sq_input[sq] != cell_to_input[c]) return cudaSuccess;   // per-cell input: generic kernels
+        if (++sq_count[sq] > 2) return cudaSuccess;
+        for (int l = 0; l < 3; ++l) {
+            double rs = 0.0;
+            for (int l2 = 0; l2 < 3; ++l2) rs += Ke[9 * c + 3 * l + l2];
+            if (fabs(rs) > tol) return cudaSuccess;                     // not a pure diffusion operator
+            for (int l2 = 0; l2 < 3; ++l2) {
+                if (l2 == l) continue;
+                const double v = Ke[9 * c + 3 * l + l2];
+                if (fabs(v - Ke[9 * c + 3 * l2 + l]) > tol) return cudaSuccess;
+                const int dx = ix[l2] - ix[l], dy = iy[l2] - iy[l];
+                if (dx != 0 && dy != 0) {
+                    if (fabs(v) > tol) return cudaSuccess;               // hypotenuse must not couple
+                } else if (dy == 0) {
+                    if (!have_h) { chs = v; have_h = true; }
+                    if (fabs(v - chs) > tol) return cudaSuccess;
+                    if (l < l2) side[sq * 4 + (iy[l] == cy ? 0 : 1)]++;
+                } else {
+                    if (!have_v) { cvs = v; have_v = true; }
+                    if (fabs(v - cvs) > tol) return cudaSuccess;
+                    if (l < l2) side[sq * 4 + 2 + (ix[l] == cx ? 0 : 1)]++;
+                }
+            }
+        }
+    }
+    if (!have_h || !have_v || chs == 0.0 || cvs == 0.0) return cudaSuccess;
+    for (size_t k = 0; k < side.size(); ++k)
+        if (side[k] != 1) return cudaSuccess;                          // every pixel side carried by exactly one cell
+    for (size_t sq = 0; sq < sq_count.size(); ++sq)
+        if (sq_count[sq] != 2) return cudaSuccess;
+    const long long in0 = sq_input[0];
+    const long long sy = ny > 1 ? (long long)sq_input[nx] - in0 : nx;
+    if (sy != nx && sy != -nx) return cudaSuccess;
+    for (int cy = 0; cy < ny; ++cy)
+        for (int cx = 0; cx < nx; ++cx)
+            if (sq_input[(size_t)cy * nx + cx] != in0 + cy * sy + cx) return cudaSuccess;
+    if ((in0 & 1) || (sy & 1)) return cudaSuccess;
+
+    int nstrips = 1;
+    while (nstrips * 16 < ncol) nstrips *= 2;
+    G.nx = nx; G.ny = ny; G.ncol = ncol; G.nstrips = nstrips; G.groups = 16 / nstrips;
+    G.in0 = in0; G.sy = sy; G.rh = chs / cvs; G.scale = cvs;
+    const int S = 8 * G.groups;
+    G.a_stride = nx + 2;
+    G.y_stride = 16 * nstrips + 4;
+    G.a_off = 0;
+    G.y_off = S * G.a_stride * 8;
+    G.v_off = (G.y_off + S * G.y_stride * 8 + 127) & ~127;
+    G.has_load = 0;
+    std::vector<double> f_over(d);
+    for (int i = 0; i < d; ++i) {
+        f_over[i] = f_free[i] / cvs;
+        if (f_free[i] != 0.0) G.has_load = 1;
+    }
+    cudaError_t e = track_vo(pl, &G.f_over, f_over);
+    if (e == cudaSuccess) G.ok = 1;
+    return e;
+}
+
+// bytes of one pipeline stage / of the packed V for NT n-tiles
+static inline size_t grid_stage_bytes(const GridDev &G, int NT) { return (size_t)G.v_off + (size_t)G.nstrips * 4 * NT * 32 * 8; }
+static inline size_t grid_packed_bytes(const GridDev &G, int NT) { return (size_t)(G.ny + 1) * G.nstrips * 4 * NT * 32 * 8; }
+
 // GPDE_VO_PATH=v1 forces the unfused version-1 kernels (A/B testing, fallback check)
 static bool use_fused(const gpde_vo_plan *pl) {
     if (!pl->tiles.ok) return false;
     const char *e = getenv("GPDE_VO_PATH");
     return !(e && strcmp(e, "v1") == 0);
+}
+
+// GPDE_VO_PATH=fused keeps the structured-grid kernel out as well (generic fused kernel instead)
+static bool use_grid(const gpde_vo_plan *pl) {
+    if (!pl->grid.ok) return false;
+    const char *e = getenv("GPDE_VO_PATH");
+    return !(e && (strcmp(e, "v1") == 0 || strcmp(e, "fused") == 0));
+}
+
+// Structured-grid path (FP64 I/O only).  Returns 1 if it served the call, 0 if the caller should use the
+// generic kernels (alignment / size conditions not met), <0 on error.
+static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
+                       const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
+                       int sub_f, long long B, cudaStream_t st) {
+    GridDev G = pl->grid;
+    if (!y || m < 1 || m > 32) return 0;
+    if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
+    const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
+    const size_t stage = grid_stage_bytes(G, NT);
+    const size_t budget = 225 * 1024 - 512;
+    int NS = (int)std::min<size_t>(4, budget / stage);
+    if (NS < 2) return 0;
+    if (!sub_f) G.has_load = 0;
+    double *Vp = (double *)workspace;
+    {
+        const long long total = (long long)grid_packed_bytes(G, NT) / 8;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+        vo_grid_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, Vp);
+    }
+    const int S = 8 * G.groups;
+    const unsigned grid = (unsigned)((B + S - 1) / S);
+    const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
+#define GPDE_LAUNCH_GRID(NTV)                                                                                    \
+    {                                                                                                            \
+        auto kern = vo_grid_kernel<NTV>;                                                                         \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage); \
+    }
+    if (NT == 1) GPDE_LAUNCH_GRID(1)
+    else if (NT == 2) GPDE_LAUNCH_GRID(2)
+    else GPDE_LAUNCH_GRID(4)
+#undef GPDE_LAUNCH_GRID
+    GPDE_CUDA_OK(cudaGetLastError());
+    return 1;
 }
 
 template <typename Ta, typename Ty, typename To>
@@ -343,6 +496,14 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
     if (B == 0) return GPDE_OK;
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if constexpr (sizeof(T) == 8) {
+        if (m > 0 && !rho && use_grid(pl)) {
+            const int rc = launch_grid(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y,
+                                       (const double *)g, (long long)g_stride, (const double *)V, m, (double *)r,
+                                       workspace, (flags & 1) ? 0 : 1, (long long)B, st);
+            if (rc != 0) return rc < 0 ? rc : GPDE_OK;
+        }
+    }
     if (m > 0 && m <= 32 && use_fused(pl)) {
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
         const int sub_f = (flags & 1) ? 0 : 1;
@@ -473,6 +634,9 @@ int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c2, c2);
     if (e == cudaSuccess) e = track_vo(pl, &D.f_free, f_free);
     if (e == cudaSuccess) e = build_fused_tiles(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, d, src, f_free);
+    if (e == cudaSuccess)
+        e = build_grid_plan(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, n_inputs, free_dofs, d, bc_dofs, n_bc,
+                            f_free);
     if (e != cudaSuccess) {
         gpde_vo_plan_destroy(pl);
         return fail(GPDE_ERR_CUDA, "vo_plan_create: upload failed: %s", cudaGetErrorString(e));
@@ -497,10 +661,18 @@ int gpde_vo_plan_info(const gpde_vo_plan *pl, int64_t out[8]) {
     return GPDE_OK;
 }
 
+int gpde_vo_plan_kernel_path(const gpde_vo_plan *pl, int m, int elem_bytes) {
+    if (!pl) return fail(GPDE_ERR_ARG, "vo_plan_kernel_path: null");
+    if (m > 0 && m <= 32 && elem_bytes == 8 && use_grid(pl)) return 2;
+    if (m > 0 && m <= 32 && use_fused(pl)) return 1;
+    return 0;
+}
+
 size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
-    (void)m;
     if (!pl || B < 0) return 0;
-    return sizeof(double) * (size_t)pl->dev.d * (size_t)B;
+    size_t need = sizeof(double) * (size_t)pl->dev.d * (size_t)B;   // version-1 kernels: rho / V s round trip
+    if (pl->grid.ok && m > 0 && m <= 32) need = std::max(need, grid_packed_bytes(pl->grid, 4));   // packed V
+    return need;
 }
 
 int gpde_vo_residual_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, int a_is_log, const double *y,

@@ -1,0 +1,379 @@
+// Structured-grid virtual-observable residual kernel (sm_100a).  Included by vo.cu.
+//
+// When the fine mesh is the reference's own (pixels of two P1 triangles on an nx x ny grid,
+// factories/model.py:130-133; Dirichlet data on the left/right edges, LinearEllipticFactories.py:173-179,
+// 239-281) and the conductivity comes per pixel (bottleneck/utils.py:41-98), K_fom(a) is a 5-point
+// operator: the coupling of two horizontally adjacent nodes is chs * (a[pixel below] + a[pixel above]),
+// of two vertically adjacent ones cvs * (a[pixel left] + a[pixel right]); the hypotenuse couplings of
+// right-angled P1 triangles vanish.  gpde_vo_plan_create verifies this against the element data it is
+// given and otherwise leaves the generic kernels (vo_fused.cuh / version 1) in charge.
+//
+//   r[b,:] = V^T (K_fom(a_b) u~_b - f)_free        (VirtualObservables.py:61-69, 662, 990)
+//
+// Work decomposition (FP64 pipe and HBM are co-limiting at m = 25):
+//   * a CTA of 16 warps owns S = 8*groups samples and marches over the node rows bottom to top;
+//   * row t of y, pixel row t-1 of a (all S samples) and row t-1 of the fragment-packed V form one
+//     pipeline stage, brought into shared memory by 1-D bulk copies (cp.async.bulk, completion on an
+//     mbarrier) issued NS-1 stages ahead by warp 0: every input byte crosses HBM once, nothing waits
+//     on a global load;
+//   * warp (group, strip): 8 samples x 16 node columns; lane (s = lane/4, k = lane%4) owns the 4
+//     columns 16*strip + 4k .. +3 of sample s and keeps the row below (u, conductivities, vertical
+//     fluxes) in registers, so a step reads 6 + 5 doubles from shared memory for 4 nodes;
+//   * flux form: S_i = rh (Fh_right - Fh_left) + (Fv_up - Fv_down), rho_i = cvs * S_i - f_i;
+//   * the 4 values a lane produces ARE its A fragments of four mma.sync.m8n8k4.f64 k-steps
+//     (M = 8 samples, K = 4 lanes' columns, N = 8 columns of V); the B fragments come from the packed
+//     V row with conflict-free 8-byte loads; accumulators stay in registers for the whole pass;
+//   * exp() of the log-field: 2^(k/16) table in shared memory + degree-6 polynomial (11 FP64 ops).
+// Algorithmic HBM bytes per sample: 8 * (n_pixels + d + n_bc + m)   (SURVEY.md 8d).
+#pragma once
+
+namespace gpde {
+
+struct GridDev {
+    int ok;
+    int nx, ny;          // pixels per row, pixel rows; nodes are (nx+1) x (ny+1)
+    int ncol;            // free node columns per row (nx - 1)
+    int nstrips;         // strips of 16 columns, rounded up to a power of two (<= 16)
+    int groups;          // sample groups (8 samples each) per CTA = 16 / nstrips
+    long long in0, sy;   // conductivity entry of pixel (cx, cy) = in0 + cy * sy + cx
+    double rh, scale;    // rh = chs / cvs, scale = cvs
+    int has_load;
+    const double *f_over;   // [d] f_i / cvs
+    int a_stride, y_stride;   // doubles per sample inside a stage
+    int a_off, y_off, v_off;  // byte offsets inside a stage
+};
+
+constexpr int kGridThreads = 512;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (TMA engine, 1-D); bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__constant__ double kExp16Tab[16] = {1.0,
+                                     1.0442737824274138,
+                                     1.0905077326652577,
+                                     1.1387886347566916,
+                                     1.189207115002721,
+                                     1.241857812073484,
+                                     1.2968395546510096,
+                                     1.3542555469368927,
+                                     1.4142135623730951,
+                                     1.4768261459394993,
+                                     1.5422108254079407,
+                                     1.6104903319492543,
+                                     1.681792830507429,
+                                     1.7562521603732995,
+                                     1.8340080864093424,
+                                     1.9152065613971474};
+
+// exp(x) = 2^e * T[j] * P6(r),  x = (16 e + j) ln2/16 + r,  |r| <= ln2/32: ~5e-16 relative for |x| <= 700;
+// anything else (huge, inf, NaN) takes the libm path.  tab = the 16-entry table in shared memory (one entry
+// per 8-byte bank: lanes with different j never conflict).
+__device__ __forceinline__ double exp_tab16(double x, const double *tab) {
+    if (!(fabs(x) <= 700.0)) return exp(x);
+    const double t = fma(x, 23.083120654223414, 6755399441055744.0);   // 1.5*2^52: low word = rint(16 x / ln2)
+    const int ki = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -0.04332169877307024, x);
+    r = fma(kd, -1.1926343307941173e-11, r);
+    double p = 1.38888888888888888889e-03;
+    p = fma(p, r, 8.33333333333333333333e-03);
+    p = fma(p, r, 4.16666666666666666667e-02);
+    p = fma(p, r, 1.66666666666666666667e-01);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = p * tab[ki & 15];
+    return __hiloint2double(__double2hiint(v) + ((ki >> 4) << 20), __double2loint(v));
+}
+
+// V[d,m] row-major -> fragment order.  Vp[row t][strip q][k-step jj][n-tile tt][lane]:
+//   lane = 4 n + kk  holds  V[t*ncol + 16 q + 4 kk + jj][8 tt + n]   (0 outside the matrix)
+__global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int m, int NT, double *__restrict__ Vp) {
+    const int per_row = G.nstrips * 4 * NT * 32;
+    const long long total = (long long)(G.ny + 1) * per_row;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(idx / per_row);
+        int rem = (int)(idx - (long long)t * per_row);
+        const int lane = rem & 31;
+        rem >>= 5;
+        const int tt = rem % NT;
+        rem /= NT;
+        const int jj = rem & 3, q = rem >> 2;
+        const int c = 16 * q + 4 * (lane & 3) + jj, col = 8 * tt + (lane >> 2);
+        Vp[idx] = (c < G.ncol && col < m) ? V[((long long)t * G.ncol + c) * m + col] : 0.0;
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(kGridThreads, 1)
+vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
+               const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
+               const double *__restrict__ Vp, int m, double *__restrict__ r, long long B, int NS, int stage_bytes) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char *stages = smem_raw;
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NS * stage_bytes);
+    unsigned long long *empty = full + NS;
+    double *tab = reinterpret_cast<double *>(empty + NS);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp % G.nstrips, grp = warp / G.nstrips;
+    const int s = lane >> 2, k = lane & 3;
+    const int S = 8 * G.groups;
+    const int sl = grp * 8 + s;                       // sample slot inside the CTA
+    const long long cta_b0 = (long long)blockIdx.x * S;
+    long long b = cta_b0 + sl;
+    if (b >= B) b = B - 1;                            // duplicates the last sample; never stored
+    const int ncol = G.ncol, nx = G.nx, ny = G.ny;
+    const long long d = (long long)ncol * (ny + 1);
+    const int c0 = 16 * q + 4 * k;
+    const int n_stages = ny + 2;
+    const int v_row_doubles = G.nstrips * 4 * NT * 32;
+    const unsigned long long y_end16 = ((unsigned long long)(y + B * d)) & ~15ull;   // bulk copies stop here
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NS; ++i) {
+            mbar_init(full + i, 1);
+            mbar_init(empty + i, kGridThreads / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 16) tab[threadIdx.x] = kExp16Tab[threadIdx.x];
+    __syncthreads();
+
+    // ---- producer (warp 0): stage ts = y row ts | pixel row ts-1 | packed V row ts-1
+    auto issue_stage = [&](int ts) {
+        unsigned char *st = stages + (size_t)(ts % NS) * stage_bytes;
+        unsigned long long *bar = full + (ts % NS);
+        unsigned bytes = 0;
+        for (int si = lane; si < S; si += 32) {
+            if (ts <= ny) {
+                long long bs = cta_b0 + si;
+                if (bs >= B) bs = B - 1;
+                const unsigned long long src = (unsigned long long)(y + bs * d + (long long)ts * ncol);
+                const unsigned long long al = src & ~15ull;
+                unsigned long long nb = (((src & 15ull) + (unsigned long long)ncol * 8 + 15ull) & ~15ull);
+                if (al + nb > y_end16) nb = y_end16 - al;
+                bytes += (unsigned)nb;
+            }
+            if (ts >= 1 && ts <= ny) bytes += (unsigned)nx * 8;
+        }
+        if (lane == 0 && ts >= 1) bytes += (unsigned)v_row_doubles * 8;
+        bytes = __reduce_add_sync(0xffffffffu, bytes);
+        if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+        __syncwarp();
+        for (int si = lane; si < S; si += 32) {
+            long long bs = cta_b0 + si;
+            if (bs >= B) bs = B - 1;
+            if (ts <= ny) {
+                const unsigned long long src = (unsigned long long)(y + bs * d + (long long)ts * ncol);
+                const unsigned long long al = src & ~15ull;
+                unsigned long long nb = (((src & 15ull) + (unsigned long long)ncol * 8 + 15ull) & ~15ull);
+                if (al + nb > y_end16) nb = y_end16 - al;
+                if (nb)
+                    bulk_g2s(st + G.y_off + ((size_t)si * G.y_stride + 2 * ((si >> 1) & 1)) * 8, (const void *)al,
+                             (unsigned)nb, bar);
+            }
+            if (ts >= 1 && ts <= ny)
+                bulk_g2s(st + G.a_off + (size_t)si * G.a_stride * 8,
+                         a + bs * a_stride + G.in0 + (long long)(ts - 1) * G.sy, (unsigned)nx * 8, bar);
+        }
+        if (lane == 0 && ts >= 1)
+            bulk_g2s(st + G.v_off, Vp + (size_t)(ts - 1) * v_row_doubles, (unsigned)v_row_doubles * 8, bar);
+    };
+    if (warp == 0)
+        for (int ts = 0; ts < NS - 1 && ts < n_stages; ++ts) issue_stage(ts);
+
+    // ---- per-lane constants
+    // category of columns c0-1 .. c0+4: 0 shared memory, 1 left Dirichlet value, 2 right one, 3 zero
+    int code = 0;
+#pragma unroll
+    for (int p = -1; p <= 4; ++p) {
+        const int c = c0 + p;
+        const int cat = (c == -1) ? 1 : (c < ncol ? 0 : (c == ncol ? 2 : 3));
+        code |= cat << (2 * (p + 1));
+    }
+    const bool edge_lane = code != 0;
+    const bool need_gl = (code & 3) == 1;
+    bool need_gr = false;
+#pragma unroll
+    for (int p = 0; p <= 5; ++p) need_gr |= ((code >> (2 * p)) & 3) == 2;
+    int pixmask = 0, nodemask = 0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) pixmask |= (c0 + j < nx) ? (1 << j) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nodemask |= (c0 + j < ncol) ? (1 << j) : 0;
+    const double *yb = y + b * d;
+    const double *gb = g ? g + b * g_stride : nullptr;
+    // the very last element of y cannot be bulk-copied when the tensor ends off a 16-byte boundary
+    const int tail_p = ncol - 1 - c0;   // window position (-1..4) of the last free column, if inside
+    const bool tail_lane = (((unsigned long long)(y + B * d)) & 15ull) && b == B - 1 && tail_p >= -1 && tail_p <= 4;
+    const int y_slot_off = G.y_off + (sl * G.y_stride + 2 * ((sl >> 1) & 1)) * 8;
+    const int a_slot_off = G.a_off + sl * G.a_stride * 8;
+
+    double acc[NT][2];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+    double uc[4] = {0.0, 0.0, 0.0, 0.0}, ulc = 0.0, urc = 0.0;
+    double ap[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    double fvp[4] = {0.0, 0.0, 0.0, 0.0};
+    double gl_next = (need_gl && gb) ? gb[0] : 0.0, gr_next = (need_gr && gb) ? gb[1] : 0.0;
+
+    for (int t = 0; t < n_stages; ++t) {
+        if (warp == 0) {
+            const int ts = t + NS - 1;
+            if (ts < n_stages) {
+                if (t >= 1) mbar_wait(empty + (ts % NS), ((t - 1) / NS) & 1);
+                issue_stage(ts);
+            }
+        }
+        const unsigned char *st = stages + (size_t)(t % NS) * stage_bytes;
+        mbar_wait(full + (t % NS), (t / NS) & 1);
+
+        // ---- new node row t and pixel row t-1
+        double un[4] = {0.0, 0.0, 0.0, 0.0}, unl = 0.0, unr = 0.0, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if (t <= ny) {
+            const double gl = gl_next, gr = gr_next;
+            if (t < ny && gb) {
+                if (need_gl) gl_next = gb[2 * (t + 1)];
+                if (need_gr) gr_next = gb[2 * (t + 1) + 1];
+            }
+            const double *yr = reinterpret_cast<const double *>(
+                                   st + y_slot_off + (int)(((unsigned long long)(yb + (long long)t * ncol)) & 15ull)) + c0;
+            unl = yr[-1];
+            un[0] = yr[0]; un[1] = yr[1]; un[2] = yr[2]; un[3] = yr[3];
+            unr = yr[4];
+            if (tail_lane && t == ny) {
+                const double v = __ldg(yb + d - 1);
+                if (tail_p == -1) unl = v;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (tail_p == j) un[j] = v;
+                if (tail_p == 4) unr = v;
+            }
+            if (edge_lane) {
+                auto pick = [&](int p, double v) {
+                    const int cat = (code >> (2 * p)) & 3;
+                    return cat == 0 ? v : (cat == 1 ? gl : (cat == 2 ? gr : 0.0));
+                };
+                unl = pick(0, unl);
+                un[0] = pick(1, un[0]); un[1] = pick(2, un[1]); un[2] = pick(3, un[2]); un[3] = pick(4, un[3]);
+                unr = pick(5, unr);
+            }
+        }
+        if (t >= 1 && t <= ny) {
+            const double *ar = reinterpret_cast<const double *>(st + a_slot_off) + c0;
+            const double2 p01 = *reinterpret_cast<const double2 *>(ar);
+            const double2 p23 = *reinterpret_cast<const double2 *>(ar + 2);
+            an[0] = p01.x; an[1] = p01.y; an[2] = p23.x; an[3] = p23.y;
+            an[4] = ar[4];
+            if (pixmask != 31) {   // columns past the last pixel hold stale shared memory
+#pragma unroll
+                for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+            }
+            if (a_is_log) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+            }
+            if (pixmask != 31) {
+#pragma unroll
+                for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+            }
+        }
+
+        // ---- node row t-1: fluxes -> S -> tensor-core contraction with packed V row t-1
+        if (t >= 1) {
+            double fh[5];
+            fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
+            fh[1] = (ap[1] + an[1]) * (uc[1] - uc[0]);
+            fh[2] = (ap[2] + an[2]) * (uc[2] - uc[1]);
+            fh[3] = (ap[3] + an[3]) * (uc[3] - uc[2]);
+            fh[4] = (ap[4] + an[4]) * (urc - uc[3]);
+            double Sv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double fv = (an[j] + an[j + 1]) * (un[j] - uc[j]);
+                Sv[j] = fma(G.rh, fh[j + 1] - fh[j], fv - fvp[j]);
+                fvp[j] = fv;
+            }
+            if (G.has_load) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((nodemask >> j) & 1) Sv[j] -= __ldg(G.f_over + (long long)(t - 1) * ncol + c0 + j);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
+            const double *vs = reinterpret_cast<const double *>(st + G.v_off) + (size_t)q * 4 * NT * 32 + lane;
+            double bf[4][NT];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + (t % NS));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) uc[j] = un[j];
+        ulc = unl; urc = unr;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) ap[j] = an[j];
+    }
+
+    // ---- sum the strips' partial tiles and store r = cvs * sum   (stage memory is free now)
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(stages);   // [groups][nstrips][8 samples][NT*8]
+    {
+        double *dst = red + (((size_t)grp * G.nstrips + q) * 8 + s) * (NT * 8) + 2 * k;
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {
+            dst[tt * 8] = acc[tt][0];
+            dst[tt * 8 + 1] = acc[tt][1];
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < S * NT * 8; idx += kGridThreads) {
+        const int si = idx / (NT * 8), col = idx - si * (NT * 8);
+        const long long bs = cta_b0 + si;
+        if (col < m && bs < B) {
+            const int gi = si >> 3, ss = si & 7;
+            double v = 0.0;
+            for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * (NT * 8) + col];
+            r[bs * m + col] = G.scale * v;
+        }
+    }
+}
+
+}  // namespace gpde

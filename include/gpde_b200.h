@@ -126,6 +126,12 @@ int gpde_vo_plan_destroy(gpde_vo_plan *plan);
 /* out[0]=n_nodes, [1]=n_cells, [2]=n_inputs, [3]=d, [4]=n_bc, [5]=slots per row, [6]=device */
 int gpde_vo_plan_info(const gpde_vo_plan *plan, int64_t out[8]);
 
+/* Which kernels serve gpde_vo_residual_* for m weighting functions and elem_bytes (8 = f64, 4 = f32) I/O:
+ * 2 = structured-grid kernel (V packing launch + one fused launch), 1 = generic fused kernel (one launch),
+ * 0 = version-1 kernels (matvec + contraction).  Informational (launch counting, tests); calls whose
+ * pointers are not 16-byte aligned, that pass y = NULL or that ask for rho fall back from 2 to 1. */
+int gpde_vo_plan_kernel_path(const gpde_vo_plan *plan, int m, int elem_bytes);
+
 /* scratch bytes for residual / residual_T on B samples with m weighting functions */
 size_t gpde_vo_workspace_bytes(const gpde_vo_plan *plan, int64_t B, int m);
 

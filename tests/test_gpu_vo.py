@@ -165,7 +165,9 @@ def test_pixel_input_plan_matches_cell_input_plan(dev):
     img = torch.tensor(w.log_image, device=dev)
     X_DG = img[:, torch.tensor(fom.mesh.pixel_of_cell(), device=dev)]
     y, gv, V = (torch.tensor(t, device=dev) for t in (w.y, w.g_fom, w.V))
-    assert torch.equal(pix_plan.residual(img, y, gv, V), cell_plan.residual(X_DG, y, gv, V))
+    # pixel input runs on the structured-grid kernel, cell input on the generic fused kernel
+    assert pix_plan.kernel_path(V.shape[1]) == 2 and cell_plan.kernel_path(V.shape[1]) == 1
+    assert rel_err(pix_plan.residual(img, y, gv, V).cpu(), cell_plan.residual(X_DG, y, gv, V).cpu()) < 1e-12
     assert pix_plan.n_inputs == 1024 and cell_plan.n_inputs == 2048 and pix_plan.slots_per_row == 6
 
 
@@ -274,11 +276,14 @@ def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
     for m in (1, 7, 8, 13, 16, 25, 32, 40):
         V = torch.tensor(rng.normal(size=(w.d, m)), dtype=dtype, device=dev)
         s = torch.tensor(rng.normal(size=(21, m)), dtype=dtype, device=dev)
-        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        monkeypatch.setenv("GPDE_VO_PATH", "fused")
+        assert plan.kernel_path(m, dtype) == (1 if m <= 32 else 0)
         r2, rho2 = plan.residual(a, y, gv, V, want_rho=True)
         q2 = plan.residual_T(a, V, s)
+        if m <= 32:
+            assert rel_err(plan.residual(a, y, gv, V).cpu(), r2.cpu()) == 0.0    # rho output does not change r
         monkeypatch.setenv("GPDE_VO_PATH", "v1")
-        assert plan.launches_per_residual(m) == 2
+        assert plan.launches_per_residual(m) == 2 and plan.kernel_path(m, dtype) == 0
         r1, rho1 = plan.residual(a, y, gv, V, want_rho=True)
         q1 = plan.residual_T(a, V, s)
         monkeypatch.delenv("GPDE_VO_PATH", raising=False)
@@ -289,10 +294,82 @@ def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
     _, rho = plan.residual(a, y, gv, None)
     assert rel_err(rho.cpu(), rho1.cpu()) < tol
     # synchronous staging flavour of the fused kernel (what FP32 inputs and non-monotone rings use)
+    monkeypatch.setenv("GPDE_VO_PATH", "fused")
+    V = torch.tensor(rng.normal(size=(w.d, 25)), dtype=dtype, device=dev)
     monkeypatch.setenv("GPDE_VO_SYNC_STAGING", "1")
     r3 = plan.residual(a, y, gv, V)
     monkeypatch.delenv("GPDE_VO_SYNC_STAGING", raising=False)
     assert torch.equal(r3, plan.residual(a, y, gv, V))
+    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+
+
+def _grid_case(nx, ny, ptype, B, seed, dev, load=False):
+    """Pixel-input plan on an nx x ny fine grid with random fields / data."""
+    from gpde_b200 import fem
+    from gpde_b200.physics import LinearEllipticPhysics, BoundaryConditionEnsemble
+    from gpde_b200.VirtualObservables import VoPlan
+    rng = np.random.RandomState(seed)
+    mesh = fem.P1Mesh(nx, ny, "right")
+    fom = LinearEllipticPhysics("fom", ptype, mesh)
+    f = rng.normal(size=mesh.num_nodes) if load else None
+    plan = VoPlan(fom, dev, mesh.pixel_of_cell(), nx * ny, load=f)
+    bc = mesh.dirichlet_dofs()[0]
+    g = rng.uniform(-0.5, 0.5, size=(B, bc.size))
+    a = rng.normal(0.4, 0.8, size=(B, nx * ny))
+    y = rng.normal(size=(B, fom.dim_out))
+    return plan, fom, a, y, g, rng
+
+
+@pytest.mark.parametrize("nx,ny,B", [(64, 64, 37), (32, 32, 64), (8, 8, 3), (2, 1, 5), (4, 7, 9), (18, 5, 33),
+                                     (34, 3, 8), (66, 2, 17), (128, 16, 19), (130, 4, 16), (200, 3, 9)])
+def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
+    """Structured-grid kernel (bulk-copy pipeline + register-resident flux form + FP64 MMA) against the generic
+    kernels on the same inputs: widths that are / are not multiples of 16, tiny grids, ragged batches,
+    every column-tile variant, odd batch x odd d (y ends off a 16-byte boundary), shared field / Dirichlet
+    data, conductivity (not log) input, load vector on / off."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 1000 + ny, dev, load=True)
+    T = lambda t: torch.tensor(t, device=dev)
+    for m in (1, 8, 9, 16, 25, 32):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        assert plan.kernel_path(m) == 2 and plan.launches_per_residual(m) == 2
+        variants = [
+            dict(a=T(a), y=T(y), g=T(g)),
+            dict(a=T(a[0]), y=T(y), g=T(g[0])),                  # shared field and Dirichlet data
+            dict(a=T(np.exp(a)), y=T(y), g=None, a_is_log=False),
+            dict(a=T(a), y=T(y), g=T(g), ignore_load=True),
+        ]
+        for kw in variants:
+            aa, yy, gg = kw.pop('a'), kw.pop('y'), kw.pop('g')
+            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            r_grid = plan.residual(aa, yy, gg, V, **kw)
+            monkeypatch.setenv("GPDE_VO_PATH", "v1")
+            r_v1 = plan.residual(aa, yy, gg, V, **kw)
+            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            assert rel_err(r_grid.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
+    # unaligned views (odd storage offsets) are served by the generic kernels, same numbers
+    V = T(rng.normal(size=(fom.dim_out, 25)))
+    big = torch.zeros(B * fom.dim_out + 1, dtype=torch.float64, device=dev)
+    yv = big[1:].view(B, fom.dim_out)
+    yv.copy_(T(y))
+    assert rel_err(plan.residual(T(a), yv, T(g), V).cpu(), plan.residual(T(a), T(y), T(g), V).cpu()) < 1e-12
+
+
+def test_grid_kernel_against_oracle(dev):
+    """Grid kernel against the CPU oracle (restated FEniCS assembly + reference VO arithmetic), 1e-10."""
+    from oracle import fem_p1, vo_ref
+    nx, ny, B = 24, 10, 11
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, 7, dev)
+    V = rng.normal(size=(fom.dim_out, 25))
+    assert plan.kernel_path(25) == 2
+    r = plan.residual(torch.tensor(a, device=dev), torch.tensor(y, device=dev), torch.tensor(g, device=dev),
+                      torch.tensor(V, device=dev)).cpu().numpy()
+    c, cells = fem_p1.unit_square_mesh(nx, ny, "right")
+    bc, _, free = fem_p1.dirichlet_left_right(c, 'ND')
+    pix = fom.mesh.pixel_of_cell()
+    for n in range(B):
+        K, f = fem_p1.assemble_system_free(c, cells, np.exp(a[n][pix]), bc, g[n], free)
+        assert rel_err(r[n], vo_ref.vo_residual(K, f, V, y[n])) < 1e-10
 
 
 def test_unfused_kernels_against_reference_vectors(dev, monkeypatch):
