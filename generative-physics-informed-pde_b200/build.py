@@ -13,7 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpde_b200.so")
 SOURCES = ["rom.cu", "vo.cu", "prolong.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(os.path.dirname(HERE), "include", "gpde_b200.h")]
+HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
+          [os.path.join(os.path.dirname(HERE), "include", "gpde_b200.h")]
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17",

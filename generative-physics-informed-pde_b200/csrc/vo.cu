@@ -437,13 +437,14 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
         vo_grid_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, Vp);
     }
     const int S = 8 * G.groups;
+    const int dbg = getenv("GPDE_GRID_DEBUG") ? atoi(getenv("GPDE_GRID_DEBUG")) : 0;   // timing experiments only
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
 #define GPDE_LAUNCH_GRID(NTV)                                                                                    \
     {                                                                                                            \
         auto kern = vo_grid_kernel<NTV>;                                                                         \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage); \
+        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
     }
     if (NT == 1) GPDE_LAUNCH_GRID(1)
     else if (NT == 2) GPDE_LAUNCH_GRID(2)

@@ -13,9 +13,9 @@
 // Work decomposition (FP64 pipe and HBM are co-limiting at m = 25):
 //   * a CTA of 16 warps owns S = 8*groups samples and marches over the node rows bottom to top;
 //   * row t of y, pixel row t-1 of a (all S samples) and row t-1 of the fragment-packed V form one
-//     pipeline stage, brought into shared memory by 1-D bulk copies (cp.async.bulk, completion on an
-//     mbarrier) issued NS-1 stages ahead by warp 0: every input byte crosses HBM once, nothing waits
-//     on a global load;
+//     pipeline stage, brought into shared memory NS-1 stages ahead: a / y rows by 16-byte cp.async shared
+//     out over all threads, the packed V row by one bulk copy (cp.async.bulk); both complete on the
+//     stage's mbarrier.  Every input byte crosses HBM once, nothing waits on a global load;
 //   * warp (group, strip): 8 samples x 16 node columns; lane (s = lane/4, k = lane%4) owns the 4
 //     columns 16*strip + 4k .. +3 of sample s and keeps the row below (u, conductivities, vertical
 //     fluxes) in registers, so a step reads 6 + 5 doubles from shared memory for 4 nodes;
@@ -43,7 +43,8 @@ struct GridDev {
     int a_off, y_off, v_off;  // byte offsets inside a stage
 };
 
-constexpr int kGridThreads = 512;
+constexpr int kGridWarps = 16;
+constexpr int kGridThreads = kGridWarps * 32;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -65,7 +66,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity)   // (a suspend-time hint made wake-ups ~10x slower on B200: measured, not used)
             : "memory");
     } while (!done);
 }
@@ -95,10 +96,9 @@ __constant__ double kExp16Tab[16] = {1.0,
                                      1.9152065613971474};
 
 // exp(x) = 2^e * T[j] * P6(r),  x = (16 e + j) ln2/16 + r,  |r| <= ln2/32: ~5e-16 relative for |x| <= 700;
-// anything else (huge, inf, NaN) takes the libm path.  tab = the 16-entry table in shared memory (one entry
-// per 8-byte bank: lanes with different j never conflict).
+// the caller routes anything else (huge, inf, NaN) to libm exp().  tab = the 16-entry table in shared memory
+// (one entry per 8-byte bank: lanes with different j never conflict).
 __device__ __forceinline__ double exp_tab16(double x, const double *tab) {
-    if (!(fabs(x) <= 700.0)) return exp(x);
     const double t = fma(x, 23.083120654223414, 6755399441055744.0);   // 1.5*2^52: low word = rint(16 x / ln2)
     const int ki = __double2loint(t);
     const double kd = t - 6755399441055744.0;
@@ -114,6 +114,9 @@ __device__ __forceinline__ double exp_tab16(double x, const double *tab) {
     const double v = p * tab[ki & 15];
     return __hiloint2double(__double2hiint(v) + ((ki >> 4) << 20), __double2loint(v));
 }
+// |x| <= 700 (false for NaN / inf) from the high word alone: integer pipe, no FP64 compare
+__device__ __forceinline__ int exp_arg_hi(double x) { return __double2hiint(x) & 0x7fffffff; }
+constexpr int kExpHiMax = 0x4085e000;   // high word of 700.0
 
 // V[d,m] row-major -> fragment order.  Vp[row t][strip q][k-step jj][n-tile tt][lane]:
 //   lane = 4 n + kk  holds  V[t*ncol + 16 q + 4 kk + jj][8 tt + n]   (0 outside the matrix)
@@ -138,7 +141,8 @@ template <int NT>
 __global__ void __launch_bounds__(kGridThreads, 1)
 vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
-               const double *__restrict__ Vp, int m, double *__restrict__ r, long long B, int NS, int stage_bytes) {
+               const double *__restrict__ Vp, int m, double *__restrict__ r, long long B, int NS,
+               int stage_bytes, int dbg) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char *stages = smem_raw;
     unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)NS * stage_bytes);
@@ -158,60 +162,68 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     const int c0 = 16 * q + 4 * k;
     const int n_stages = ny + 2;
     const int v_row_doubles = G.nstrips * 4 * NT * 32;
-    const unsigned long long y_end16 = ((unsigned long long)(y + B * d)) & ~15ull;   // bulk copies stop here
+    const unsigned long long y_end16 = ((unsigned long long)(y + B * d)) & ~15ull;   // 16-byte copies stop here
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
-            mbar_init(full + i, 1);
-            mbar_init(empty + i, kGridThreads / 32);
+            mbar_init(full + i, kGridThreads + 1);
+            mbar_init(empty + i, kGridWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 16) tab[threadIdx.x] = kExp16Tab[threadIdx.x];
     __syncthreads();
 
-    // ---- producer (warp 0): stage ts = y row ts | pixel row ts-1 | packed V row ts-1
-    auto issue_stage = [&](int ts) {
-        unsigned char *st = stages + (size_t)(ts % NS) * stage_bytes;
-        unsigned long long *bar = full + (ts % NS);
-        unsigned bytes = 0;
-        for (int si = lane; si < S; si += 32) {
-            if (ts <= ny) {
-                long long bs = cta_b0 + si;
-                if (bs >= B) bs = B - 1;
-                const unsigned long long src = (unsigned long long)(y + bs * d + (long long)ts * ncol);
-                const unsigned long long al = src & ~15ull;
-                unsigned long long nb = (((src & 15ull) + (unsigned long long)ncol * 8 + 15ull) & ~15ull);
-                if (al + nb > y_end16) nb = y_end16 - al;
-                bytes += (unsigned)nb;
+    // ---- staging: stage ts = y row ts | pixel row ts-1 | packed V row ts-1, NS stages in a ring, issued
+    // NS-1 stages ahead of their use.  The a / y rows are 512-byte pieces: too small for the bulk-copy engine
+    // (measured: ~130 cycles per request) and one warp can keep only a few cp.async in flight (measured: a
+    // single staging warp delivers 4 GB/s), so EVERY warp stages the rows of its samples w, w+16, ... with
+    // 16-byte cp.async (LDGSTS, L2 -> shared, no registers; one row per warp instruction) whose completion
+    // arrives on the stage's mbarrier; the 16 KB packed V row is ONE bulk copy by thread 0.  y rows start on
+    // 8-byte boundaries: the copy runs from the enclosing 16-byte boundary and the consumer adds the same shift.
+    // Running pointers (advanced once per stage) keep the per-stage address arithmetic to a few instructions.
+    const int a_ops = nx >> 1;                                       // 16-byte pieces per pixel row
+    const double *a_src = a + G.in0 - G.sy + 2 * lane;               // pixel row ts-1, this lane's piece, sample 0
+    const double *y_src = y;                                         // node row ts, sample 0
+    auto issue_stage = [&](int ts, int slot) {
+        unsigned char *st = stages + (size_t)slot * stage_bytes;
+        unsigned long long *bar = full + slot;
+        if (!(dbg & 2)) {
+            const bool has_a = ts >= 1 && ts <= ny, has_y = ts <= ny;
+            for (int si = warp; si < S; si += kGridWarps) {
+                const long long bs = min(cta_b0 + si, B - 1);
+                if (has_a) {
+                    const double *src = a_src + bs * a_stride;
+                    unsigned char *dst = st + G.a_off + si * (G.a_stride * 8) + 16 * lane;
+                    for (int ch = lane; ch < a_ops; ch += 32, src += 64, dst += 512) cp_async16(dst, src);
+                }
+                if (has_y) {
+                    const unsigned long long src = (unsigned long long)(y_src + bs * d);
+                    const unsigned long long end = min(src + (unsigned long long)ncol * 8, y_end16 - 8);
+                    unsigned long long piece = (src & ~15ull) + 16ull * lane;
+                    unsigned char *dst = st + G.y_off + (si * G.y_stride + 2 * ((si >> 1) & 1)) * 8 + 16 * lane;
+                    for (; piece < end; piece += 512, dst += 512) cp_async16(dst, (const void *)piece);
+                }
             }
-            if (ts >= 1 && ts <= ny) bytes += (unsigned)nx * 8;
         }
-        if (lane == 0 && ts >= 1) bytes += (unsigned)v_row_doubles * 8;
-        bytes = __reduce_add_sync(0xffffffffu, bytes);
-        if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
-        __syncwarp();
-        for (int si = lane; si < S; si += 32) {
-            long long bs = cta_b0 + si;
-            if (bs >= B) bs = B - 1;
-            if (ts <= ny) {
-                const unsigned long long src = (unsigned long long)(y + bs * d + (long long)ts * ncol);
-                const unsigned long long al = src & ~15ull;
-                unsigned long long nb = (((src & 15ull) + (unsigned long long)ncol * 8 + 15ull) & ~15ull);
-                if (al + nb > y_end16) nb = y_end16 - al;
-                if (nb)
-                    bulk_g2s(st + G.y_off + ((size_t)si * G.y_stride + 2 * ((si >> 1) & 1)) * 8, (const void *)al,
-                             (unsigned)nb, bar);
+        a_src += G.sy;
+        y_src += ncol;
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        if (threadIdx.x == 0) {
+            if (ts >= 1 && !(dbg & 4)) {
+                mbar_arrive_expect_tx(bar, (unsigned)v_row_doubles * 8);
+                bulk_g2s(st + G.v_off, Vp + (size_t)(ts - 1) * v_row_doubles, (unsigned)v_row_doubles * 8, bar);
+            } else {
+                mbar_arrive(bar);
             }
-            if (ts >= 1 && ts <= ny)
-                bulk_g2s(st + G.a_off + (size_t)si * G.a_stride * 8,
-                         a + bs * a_stride + G.in0 + (long long)(ts - 1) * G.sy, (unsigned)nx * 8, bar);
         }
-        if (lane == 0 && ts >= 1)
-            bulk_g2s(st + G.v_off, Vp + (size_t)(ts - 1) * v_row_doubles, (unsigned)v_row_doubles * 8, bar);
     };
-    if (warp == 0)
-        for (int ts = 0; ts < NS - 1 && ts < n_stages; ++ts) issue_stage(ts);
+    int i_slot = 0;                  // slot of the next stage to issue
+    unsigned e_par = 0;              // per-slot parity of the next wait on empty[]
+    for (int ts = 0; ts < NS - 1 && ts < n_stages; ++ts) {
+        issue_stage(ts, i_slot);
+        if (++i_slot == NS) i_slot = 0;
+    }
 
     // ---- per-lane constants
     // category of columns c0-1 .. c0+4: 0 shared memory, 1 left Dirichlet value, 2 right one, 3 zero
@@ -234,11 +246,15 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     for (int j = 0; j < 4; ++j) nodemask |= (c0 + j < ncol) ? (1 << j) : 0;
     const double *yb = y + b * d;
     const double *gb = g ? g + b * g_stride : nullptr;
-    // the very last element of y cannot be bulk-copied when the tensor ends off a 16-byte boundary
+    // the very last element of y cannot be copied in a 16-byte piece when the tensor ends off a 16-byte boundary
     const int tail_p = ncol - 1 - c0;   // window position (-1..4) of the last free column, if inside
     const bool tail_lane = (((unsigned long long)(y + B * d)) & 15ull) && b == B - 1 && tail_p >= -1 && tail_p <= 4;
-    const int y_slot_off = G.y_off + (sl * G.y_stride + 2 * ((sl >> 1) & 1)) * 8;
-    const int a_slot_off = G.a_off + sl * G.a_stride * 8;
+    // byte offsets of this lane's first column inside a stage; the y row's 8-byte phase alternates with t when ncol is odd
+    const int y_lane_off = G.y_off + (sl * G.y_stride + 2 * ((sl >> 1) & 1) + c0) * 8;
+    const int a_lane_off = G.a_off + (sl * G.a_stride + c0) * 8;
+    const int v_lane_off = G.v_off + (q * 4 * NT * 32 + lane) * 8;
+    int y_shift = (int)(((unsigned long long)yb) & 15ull);
+    const int y_shift_step = (ncol & 1) * 8;
 
     double acc[NT][2];
 #pragma unroll
@@ -248,16 +264,29 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     double fvp[4] = {0.0, 0.0, 0.0, 0.0};
     double gl_next = (need_gl && gb) ? gb[0] : 0.0, gr_next = (need_gr && gb) ? gb[1] : 0.0;
 
+    int c_slot = 0;                  // slot of stage t
+    unsigned f_par = 0;              // per-slot parity of the next wait on full[]
     for (int t = 0; t < n_stages; ++t) {
-        if (warp == 0) {
+        {
             const int ts = t + NS - 1;
             if (ts < n_stages) {
-                if (t >= 1) mbar_wait(empty + (ts % NS), ((t - 1) / NS) & 1);
-                issue_stage(ts);
+                if (t >= 1) {        // the slot held stage t-1: wait until every warp has released it
+                    mbar_wait(empty + i_slot, (e_par >> i_slot) & 1);
+                    e_par ^= 1u << i_slot;
+                }
+                issue_stage(ts, i_slot);
+                if (++i_slot == NS) i_slot = 0;
             }
         }
-        const unsigned char *st = stages + (size_t)(t % NS) * stage_bytes;
-        mbar_wait(full + (t % NS), (t / NS) & 1);
+        const unsigned char *st = stages + (size_t)c_slot * stage_bytes;
+        mbar_wait(full + c_slot, (f_par >> c_slot) & 1);
+        f_par ^= 1u << c_slot;
+        if (dbg & 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + c_slot);
+            if (++c_slot == NS) c_slot = 0;
+            continue;
+        }
 
         // ---- new node row t and pixel row t-1
         double un[4] = {0.0, 0.0, 0.0, 0.0}, unl = 0.0, unr = 0.0, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
@@ -267,8 +296,7 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 if (need_gl) gl_next = gb[2 * (t + 1)];
                 if (need_gr) gr_next = gb[2 * (t + 1) + 1];
             }
-            const double *yr = reinterpret_cast<const double *>(
-                                   st + y_slot_off + (int)(((unsigned long long)(yb + (long long)t * ncol)) & 15ull)) + c0;
+            const double *yr = reinterpret_cast<const double *>(st + y_lane_off + y_shift);
             unl = yr[-1];
             un[0] = yr[0]; un[1] = yr[1]; un[2] = yr[2]; un[3] = yr[3];
             unr = yr[4];
@@ -290,8 +318,9 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 unr = pick(5, unr);
             }
         }
+        y_shift = (y_shift + y_shift_step) & 15;
         if (t >= 1 && t <= ny) {
-            const double *ar = reinterpret_cast<const double *>(st + a_slot_off) + c0;
+            const double *ar = reinterpret_cast<const double *>(st + a_lane_off);
             const double2 p01 = *reinterpret_cast<const double2 *>(ar);
             const double2 p23 = *reinterpret_cast<const double2 *>(ar + 2);
             an[0] = p01.x; an[1] = p01.y; an[2] = p23.x; an[3] = p23.y;
@@ -301,8 +330,15 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
             }
             if (a_is_log) {
+                const int hmax = max(max(max(exp_arg_hi(an[0]), exp_arg_hi(an[1])), max(exp_arg_hi(an[2]), exp_arg_hi(an[3]))),
+                                     exp_arg_hi(an[4]));
+                if (hmax <= kExpHiMax) {
 #pragma unroll
-                for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                    for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+                }
             }
             if (pixmask != 31) {
 #pragma unroll
@@ -330,9 +366,11 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 for (int j = 0; j < 4; ++j)
                     if ((nodemask >> j) & 1) Sv[j] -= __ldg(G.f_over + (long long)(t - 1) * ncol + c0 + j);
             }
+            if (nodemask != 15) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
-            const double *vs = reinterpret_cast<const double *>(st + G.v_off) + (size_t)q * 4 * NT * 32 + lane;
+                for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
+            }
+            const double *vs = reinterpret_cast<const double *>(st + v_lane_off);
             double bf[4][NT];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
@@ -344,7 +382,8 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + (t % NS));
+        if (lane == 0) mbar_arrive(empty + c_slot);
+        if (++c_slot == NS) c_slot = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) uc[j] = un[j];
         ulc = unl; urc = unr;
