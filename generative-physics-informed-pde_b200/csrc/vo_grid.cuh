@@ -47,6 +47,9 @@ constexpr int kGridWarps = 16;
 constexpr int kGridThreads = kGridWarps * 32;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async16_u32(unsigned smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
 
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -183,6 +186,7 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     // 8-byte boundaries: the copy runs from the enclosing 16-byte boundary and the consumer adds the same shift.
     // Running pointers (advanced once per stage) keep the per-stage address arithmetic to a few instructions.
     const int a_ops = nx >> 1;                                       // 16-byte pieces per pixel row
+    const unsigned stages_u32 = smem_u32(stages);
     const double *a_src = a + G.in0 - G.sy + 2 * lane;               // pixel row ts-1, this lane's piece, sample 0
     const double *y_src = y;                                         // node row ts, sample 0
     auto issue_stage = [&](int ts, int slot) {
@@ -190,19 +194,23 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
         unsigned long long *bar = full + slot;
         if (!(dbg & 2)) {
             const bool has_a = ts >= 1 && ts <= ny, has_y = ts <= ny;
+            const int row_bytes = ncol * 8;
             for (int si = warp; si < S; si += kGridWarps) {
                 const long long bs = min(cta_b0 + si, B - 1);
                 if (has_a) {
                     const double *src = a_src + bs * a_stride;
-                    unsigned char *dst = st + G.a_off + si * (G.a_stride * 8) + 16 * lane;
-                    for (int ch = lane; ch < a_ops; ch += 32, src += 64, dst += 512) cp_async16(dst, src);
+                    const unsigned dst = stages_u32 + slot * stage_bytes + G.a_off + si * (G.a_stride * 8) + 16 * lane;
+                    for (int ch = lane, o = 0; ch < a_ops; ch += 32, o += 512) cp_async16_u32(dst + o, src + (o >> 3));
                 }
                 if (has_y) {
-                    const unsigned long long src = (unsigned long long)(y_src + bs * d);
-                    const unsigned long long end = min(src + (unsigned long long)ncol * 8, y_end16 - 8);
-                    unsigned long long piece = (src & ~15ull) + 16ull * lane;
-                    unsigned char *dst = st + G.y_off + (si * G.y_stride + 2 * ((si >> 1) & 1)) * 8 + 16 * lane;
-                    for (; piece < end; piece += 512, dst += 512) cp_async16(dst, (const void *)piece);
+                    const char *src = reinterpret_cast<const char *>(y_src + bs * d);
+                    const int shift = (int)((unsigned long long)src & 15ull);
+                    const unsigned dst = stages_u32 + slot * stage_bytes + G.y_off + (si * G.y_stride + 2 * ((si >> 1) & 1)) * 8;
+                    // 16-byte pieces at offsets o = 16*lane - shift, + 512, ... from the row start; the last piece of the
+                    // whole tensor may stick out past its end (odd element count): it is left to the tail lanes
+                    const bool last_row = (unsigned long long)src + row_bytes + 8 > y_end16;
+                    for (int o = 16 * lane - shift; o < row_bytes; o += 512)
+                        if (!last_row || (unsigned long long)src + o + 16 <= y_end16) cp_async16_u32(dst + o + shift, src + o);
                 }
             }
         }
@@ -234,16 +242,17 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
         const int cat = (c == -1) ? 1 : (c < ncol ? 0 : (c == ncol ? 2 : 3));
         code |= cat << (2 * (p + 1));
     }
-    const bool edge_lane = code != 0;
-    const bool need_gl = (code & 3) == 1;
-    bool need_gr = false;
-#pragma unroll
-    for (int p = 0; p <= 5; ++p) need_gr |= ((code >> (2 * p)) & 3) == 2;
     int pixmask = 0, nodemask = 0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) pixmask |= (c0 + j < nx) ? (1 << j) : 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) nodemask |= (c0 + j < ncol) ? (1 << j) : 0;
+    asm volatile("" : "+r"(code), "+r"(pixmask), "+r"(nodemask));   // opaque: keep them live instead of recomputing per step
+    const bool edge_lane = code != 0;
+    const bool need_gl = (code & 3) == 1;
+    bool need_gr = false;
+#pragma unroll
+    for (int p = 0; p <= 5; ++p) need_gr |= ((code >> (2 * p)) & 3) == 2;
     const double *yb = y + b * d;
     const double *gb = g ? g + b * g_stride : nullptr;
     // the very last element of y cannot be copied in a 16-byte piece when the tensor ends off a 16-byte boundary
