@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     return ap.parse_args()
 
 
@@ -242,13 +243,13 @@ def run_b200(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     K = args.steps
+
+    # ---- (1) per-kernel times: eager launches bracketed by CUDA events on the launching stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    start.record()
+    e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
+    e_start.record()
     for k in range(K):
         ev[k][0].record()
         u, factor = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
@@ -257,6 +258,49 @@ def run_b200(args):
         ev[k][2].record()
         r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
         ev[k][3].record()
+    e_end.record()
+    t_host1 = time.perf_counter()
+    torch.cuda.synchronize()
+    rom.check()
+    eager_ms = e_start.elapsed_time(e_end) / K
+    host_enqueue_ms = (t_host1 - t_host0) * 1e3 / K
+    t_fwd = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K)) / K
+    t_adj = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(K)) / K
+    t_vo = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(K)) / K
+
+    # ---- (2) the timed region: K steps, each step = the same launches replayed from one CUDA graph (the
+    # step is launch-bound from Python at this batch); falls back to eager launches if capture is refused
+    graph, mode = None, "eager"
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g_out = step_resident()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+            mode = "cuda_graph"
+        except Exception as exc:   # noqa: BLE001 -- report, keep measuring eagerly
+            sys.stderr.write("bench: CUDA graph capture failed (%s); timing eager launches\n" % (exc,))
+            graph = None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    start.record()
+    for k in range(K):
+        if graph is not None:
+            graph.replay()
+        else:
+            step_resident()
     end.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
@@ -267,9 +311,6 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         elapsed_ms = float(tt.item())
     ms_per_step = elapsed_ms / K
-    t_fwd = sum(ev[k][0].elapsed_time(ev[k][1]) for k in range(K)) / K
-    t_adj = sum(ev[k][1].elapsed_time(ev[k][2]) for k in range(K)) / K
-    t_vo = sum(ev[k][2].elapsed_time(ev[k][3]) for k in range(K)) / K
 
     # ---- end to end through the public module API from pinned host buffers ----
     e2e = None
@@ -331,10 +372,12 @@ def run_b200(args):
         "components": {
             "cgm_solves_per_s": world * B / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": world * B / (t_vo * 1e-3),
             "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo,
+            "launch_mode": mode, "ms_per_step_eager": eager_ms, "ms_host_enqueue_per_step": host_enqueue_ms,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
         },
-        "roofline": {"kernel": {2: "vo_grid_kernel (+ vo_grid_pack_kernel)", 1: "vo_fused_kernel"}.get(
-                         vplan.kernel_path(w.m, tdt), "vo_matvec_kernel + vo_contract_kernel"), "bound": "hbm", "achieved": achieved, "peak": peak,
+        "roofline": {"kernel": {3: "vo_grid_kernel<rho> + vo_gemm_kernel", 2: "vo_grid_kernel (+ vo_grid_pack_kernel)",
+                                 1: "vo_fused_kernel"}.get(vplan.kernel_path(w.m, tdt), "vo_matvec_kernel + vo_gemm_kernel"),
+                     "bound": "hbm", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes},
         "gpu_launches": launches_per_step * K,

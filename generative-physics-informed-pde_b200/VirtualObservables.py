@@ -86,13 +86,14 @@ class VoPlan(object):
         return store[key]
 
     def kernel_path(self, m, dtype=torch.float64):
-        """2 = structured-grid kernel, 1 = generic fused kernel, 0 = version-1 kernels (include/gpde_b200.h)."""
+        """3 = grid rho kernel + tensor-core contraction (m > 32), 2 = structured-grid kernel, 1 = generic fused
+        kernel, 0 = version-1 kernels (include/gpde_b200.h)."""
         return int(self._lib.gpde_vo_plan_kernel_path(self.handle, int(m), 8 if dtype == torch.float64 else 4))
 
     def launches_per_residual(self, m, dtype=torch.float64):
         """Kernels launched by one residual() call (for bench.py's gpu_launches count)."""
         path = self.kernel_path(m, dtype)
-        return {2: 2, 1: 1}.get(path, 2 if m > 0 else 1)
+        return {3: 3, 2: 2, 1: 1}.get(path, 3 if m > 0 else 1)
 
     def _workspace(self, B, m):
         need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, B, m)))

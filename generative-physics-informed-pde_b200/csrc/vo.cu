@@ -38,6 +38,7 @@ constexpr int kVoThreads = 256;
 
 #include "vo_fused.cuh"
 #include "vo_grid.cuh"
+#include "vo_gemm.cuh"
 
 struct gpde_vo_plan {
     gpde::VoDev dev;
@@ -55,7 +56,7 @@ template <typename Ta, typename Ty, typename To, int S>
 __global__ void __launch_bounds__(kVoThreads)
 vo_matvec_kernel(VoDev P, const Ta *__restrict__ a, long long a_stride, int a_is_log,
                  const Ty *__restrict__ y, const Ta *__restrict__ g, long long g_stride, int sub_f,
-                 double *__restrict__ rho_ws, To *__restrict__ rho_out, long long B, int stage_a) {
+                 double *__restrict__ rho_ws, int ws_stride, To *__restrict__ rho_out, long long B, int stage_a) {
     extern __shared__ double ea[];   // [S][n_inputs] when stage_a
     const int d = P.d;
     for (long long b0 = (long long)blockIdx.x * S; b0 < B; b0 += (long long)gridDim.x * S) {
@@ -104,48 +105,16 @@ vo_matvec_kernel(VoDev P, const Ta *__restrict__ a, long long a_stride, int a_is
             for (int s = 0; s < S; ++s) {
                 const long long b = b0 + s;
                 if (b < B) {
-                    if (rho_ws) rho_ws[b * d + i] = acc[s];
+                    if (rho_ws) rho_ws[b * ws_stride + i] = acc[s];
                     if (rho_out) rho_out[b * d + i] = (To)acc[s];
                 }
             }
         }
-    }
-}
-
-// R[B,m] = rho[B,d] V[d,m]   (FP64 accumulate).  CTA tile 32 samples x 32 columns, k chunks of 32.
-template <typename Tv, typename To>
-__global__ void __launch_bounds__(256)
-vo_contract_kernel(const double *__restrict__ rho, const Tv *__restrict__ V, To *__restrict__ R,
-                   long long B, int d, int m) {
-    __shared__ double rs[32][33];
-    __shared__ double vs[32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // ty in 0..7
-    const long long b0 = (long long)blockIdx.x * 32;
-    const int n0 = blockIdx.y * 32;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k0 = 0; k0 < d; k0 += 32) {
-        __syncthreads();
+        if (rho_ws)   // zero the K padding the tensor-core contraction reads
+            for (int i = d + threadIdx.x; i < ws_stride; i += kVoThreads)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int row = ty * 4 + r;
-            const long long b = b0 + row;
-            const int k = k0 + tx;
-            rs[row][tx] = (b < B && k < d) ? rho[b * d + k] : 0.0;
-            const int kk = k0 + row, nn = n0 + tx;
-            vs[row][tx] = (kk < d && nn < m) ? ldd(V + (long long)kk * m + nn) : 0.0;
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int k = 0; k < 32; ++k) {
-            const double v = vs[k][tx];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) acc[r] = fma(rs[ty * 4 + r][k], v, acc[r]);
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const long long b = b0 + ty * 4 + r;
-        if (b < B && n0 + tx < m) R[b * m + n0 + tx] = (To)acc[r];
+                for (int s = 0; s < S; ++s)
+                    if (b0 + s < B) rho_ws[(b0 + s) * ws_stride + i] = 0.0;
     }
 }
 
@@ -442,7 +411,7 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
 #define GPDE_LAUNCH_GRID(NTV)                                                                                    \
     {                                                                                                            \
-        auto kern = vo_grid_kernel<NTV>;                                                                         \
+        auto kern = vo_grid_kernel<NTV, false>;                                                                       \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
     }
@@ -454,10 +423,33 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     return 1;
 }
 
+// Structured-grid fine residual rho[B][pitch] (pitch >= d, padding zeroed) for the tensor-core contraction.
+// Returns 1 if it served the call, 0 if the generic matvec kernel should (alignment / size), <0 on error.
+static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
+                           const double *g, long long g_stride, double *rho, int pitch, int sub_f, long long B,
+                           cudaStream_t st) {
+    GridDev G = pl->grid;
+    if (!y) return 0;
+    if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
+    const size_t stage = (size_t)G.v_off;            // no V row in the stage
+    const size_t budget = 225 * 1024 - 512;
+    const int NS = (int)std::min<size_t>(6, budget / stage);
+    if (NS < 2) return 0;
+    if (!sub_f) G.has_load = 0;
+    const int S = 8 * G.groups;
+    const unsigned grid = (unsigned)((B + S - 1) / S);
+    const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
+    auto kern = vo_grid_kernel<1, true>;
+    GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
+    GPDE_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 template <typename Ta, typename Ty, typename To>
 static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride, int a_is_log, const Ty *y,
-                         const Ta *g, long long g_stride, int sub_f, double *rho_ws, To *rho_out, long long B,
-                         cudaStream_t st) {
+                         const Ta *g, long long g_stride, int sub_f, double *rho_ws, int ws_stride, To *rho_out,
+                         long long B, cudaStream_t st) {
     const VoDev &P = pl->dev;
     const size_t per = sizeof(double) * (size_t)P.n_inputs;
     const size_t cap = 200 * 1024;
@@ -474,7 +466,7 @@ static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride
         auto kern = vo_matvec_kernel<Ta, Ty, To, SS>;                                                    \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         kern<<<grid, kVoThreads, smem, st>>>(P, a, a_stride, a_is_log, y, g, g_stride, sub_f, rho_ws,    \
-                                             rho_out, B, stage);                                          \
+                                             ws_stride, rho_out, B, stage);                               \
     }
     if (S == 4) GPDE_LAUNCH_MV(4)
     else if (S == 2) GPDE_LAUNCH_MV(2)
@@ -524,12 +516,40 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
     }
+    // version 1: rho -> K-padded workspace, then the FP64 tensor-core contraction (vo_gemm.cuh)
+    const int d = pl->dev.d, dp = gemm_dp(d);
     double *ws = m > 0 ? (double *)workspace : nullptr;
-    int rc = launch_matvec<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, (flags & 1) ? 0 : 1, ws, rho, B, st);
-    if (rc != GPDE_OK) return rc;
+    int rc = 0;
+    if constexpr (sizeof(T) == 8) {   // structured pixel grid: the marching kernel produces rho (no V inside)
+        if (m > 0 && !rho && use_grid(pl)) {
+            rc = launch_grid_rho(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y, (const double *)g,
+                                 (long long)g_stride, ws, dp, (flags & 1) ? 0 : 1, (long long)B, st);
+            if (rc < 0) return rc;
+        }
+    }
+    if (rc == 0) {
+        rc = launch_matvec<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, (flags & 1) ? 0 : 1, ws, dp, rho, B, st);
+        if (rc != GPDE_OK) return rc;
+    }
     if (m > 0) {
-        dim3 grid((unsigned)((B + 31) / 32), (unsigned)((m + 31) / 32));
-        vo_contract_kernel<T, T><<<grid, 256, 0, st>>>(ws, V, r, B, pl->dev.d, m);
+        const int bn = gemm_bn(m), ldb = gemm_ldb(m);
+        double *Vp = ws + (size_t)B * dp;
+        {
+            const long long total = (long long)dp * ldb;
+            const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 8);
+            vo_gemm_pack_kernel_t<T><<<grid, 256, 0, st>>>(V, d, m, Vp, dp, ldb);
+        }
+        dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
+        const size_t smem = gemm_smem(bn);
+        if (bn == 64) {
+            auto kern = vo_gemm_kernel<64, T>;
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B);
+        } else {
+            auto kern = vo_gemm_kernel<128, T>;
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B);
+        }
         GPDE_CUDA_OK(cudaGetLastError());
     }
     return GPDE_OK;
@@ -557,7 +577,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 16);
     vo_expand_kernel<T><<<grid, 256, 0, st>>>(s, V, w, B, pl->dev.d, m);
     GPDE_CUDA_OK(cudaGetLastError());
-    return launch_matvec<T, double, T>(pl, a, a_stride, a_is_log, w, (const T *)nullptr, 0, 0, (double *)nullptr,
+    return launch_matvec<T, double, T>(pl, a, a_stride, a_is_log, w, (const T *)nullptr, 0, 0, (double *)nullptr, 0,
                                        q, B, st);
 }
 
@@ -665,13 +685,16 @@ int gpde_vo_plan_info(const gpde_vo_plan *pl, int64_t out[8]) {
 int gpde_vo_plan_kernel_path(const gpde_vo_plan *pl, int m, int elem_bytes) {
     if (!pl) return fail(GPDE_ERR_ARG, "vo_plan_kernel_path: null");
     if (m > 0 && m <= 32 && elem_bytes == 8 && use_grid(pl)) return 2;
+    if (m > 32 && elem_bytes == 8 && use_grid(pl)) return 3;
     if (m > 0 && m <= 32 && use_fused(pl)) return 1;
     return 0;
 }
 
 size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
     if (!pl || B < 0) return 0;
-    size_t need = sizeof(double) * (size_t)pl->dev.d * (size_t)B;   // version-1 kernels: rho / V s round trip
+    // version-1 kernels: K-padded rho [B][dp] + padded V [dp][ldb] (residual), V s [B][d] (residual_T)
+    const size_t dp = (size_t)gemm_dp(pl->dev.d);
+    size_t need = sizeof(double) * (dp * (size_t)B + dp * (size_t)gemm_ldb(std::max(m, 1)));
     if (pl->grid.ok && m > 0 && m <= 32) need = std::max(need, grid_packed_bytes(pl->grid, 4));   // packed V
     return need;
 }

@@ -1,0 +1,142 @@
+// FP64 tensor-core contraction  R[B,m] = rho[B,d] V[d,m]  for many weighting functions (m > 32), sm_100a.
+// Included by vo.cu.
+//
+// This is the (Gamma y - alpha) step of VirtualObservables.py:61-69, 662, 990 once the fine residual rho is
+// known; at BASELINE config 3 (d = 16383, m = 256, B = 16384) it is 137 GFLOP of FP64 and bounds the whole VO
+// evaluation (FP64 pipe: 37 TFLOP/s measured => 3.7 ms floor; tcgen05 has no FP64 kind, so the tool is
+// mma.sync.m8n8k4.f64 = DMMA.8x8x4, issued at the full FP64 rate).
+//
+// Layout: rho comes from the matvec kernel in a K-padded workspace [B][dp] (dp = d rounded up to 16, pad = 0);
+// V is copied once per call into [dp][ldb] (ldb = m rounded up to the column tile, pad = 0), so every tile load
+// is a full 16-byte cp.async with no bounds logic in the main loop.
+// CTA tile 128 samples x BN columns, 8 warps as 4 (M) x 2 (N), warp tile 32 x BN/2 => 4 x BN/16 DMMA tiles
+// whose accumulators stay in registers; K in chunks of 16 through a 4-stage cp.async ring.  Shared-memory row
+// pitches are = 4 (mod 16) doubles, which makes both fragment loads conflict-free.
+#pragma once
+
+namespace gpde {
+
+constexpr int kGemmBM = 128, kGemmKC = 16, kGemmStages = 4, kGemmThreads = 256;
+constexpr int kGemmLdA = kGemmKC + 4;   // doubles per A row in shared memory
+
+__device__ __forceinline__ void cp_async_wait_n(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    }
+}
+
+// Vp[dp][ldb] <- V[d][m], zero padded
+__global__ void vo_gemm_pack_kernel(const double *__restrict__ V, int d, int m, double *__restrict__ Vp, int dp, int ldb) {
+    const long long total = (long long)dp * ldb;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / ldb), c = (int)(idx - (long long)i * ldb);
+        Vp[idx] = (i < d && c < m) ? V[(long long)i * m + c] : 0.0;
+    }
+}
+template <typename T>
+__global__ void vo_gemm_pack_kernel_t(const T *__restrict__ V, int d, int m, double *__restrict__ Vp, int dp, int ldb) {
+    const long long total = (long long)dp * ldb;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / ldb), c = (int)(idx - (long long)i * ldb);
+        Vp[idx] = (i < d && c < m) ? (double)V[(long long)i * m + c] : 0.0;
+    }
+}
+
+template <int BN, typename To>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ Vp, int ldb, To *__restrict__ R, int m,
+               long long B) {
+    constexpr int LdB = BN + 4;                    // doubles per B row in shared memory
+    constexpr int NT = BN / 16;                    // 8-column DMMA tiles per warp
+    constexpr int A_STAGE = kGemmBM * kGemmLdA, B_STAGE = kGemmKC * LdB;
+    extern __shared__ __align__(16) double gsm[];
+    double *As = gsm, *Bs = gsm + kGemmStages * A_STAGE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 3, wn = warp >> 2;       // 4 x 2 warps
+    const long long row0 = (long long)blockIdx.x * kGemmBM;
+    const int col0 = blockIdx.y * BN;
+    const int nchunks = dp / kGemmKC;
+
+    // cp.async assignments: A chunk = 128 rows x 8 pieces, B chunk = 16 rows x BN/2 pieces (16 bytes each)
+    auto load_chunk = [&](int kc, int stage) {
+        double *as = As + stage * A_STAGE, *bs = Bs + stage * B_STAGE;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int p = threadIdx.x + i * kGemmThreads;      // 0..1023
+            const int rr = p >> 3, pc = p & 7;
+            long long row = row0 + rr;
+            if (row >= B) row = B - 1;
+            cp_async16(as + rr * kGemmLdA + 2 * pc, A + row * dp + (long long)kc * kGemmKC + 2 * pc);
+        }
+#pragma unroll
+        for (int i = 0; i < (kGemmKC * BN / 2) / kGemmThreads; ++i) {
+            const int p = threadIdx.x + i * kGemmThreads;
+            const int kr = p / (BN / 2), pc = p - kr * (BN / 2);
+            cp_async16(bs + kr * LdB + 2 * pc, Vp + ((long long)kc * kGemmKC + kr) * ldb + col0 + 2 * pc);
+        }
+    };
+
+    double acc[4][NT][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    for (int s = 0; s < kGemmStages - 1; ++s) {
+        if (s < nchunks) load_chunk(s, s);
+        cp_async_commit();
+    }
+    // fragment source of this lane inside a stage
+    const int a_lane = (wm * 32 + (lane >> 2)) * kGemmLdA + (lane & 3);          // + mt*8*LdA + ks*4
+    const int b_lane = (lane & 3) * LdB + wn * (BN / 2) + (lane >> 2);           // + ks*4*LdB + nt*8
+    for (int kc = 0; kc < nchunks; ++kc) {
+        cp_async_wait_n(kGemmStages - 2);
+        __syncthreads();
+        {   // refill the stage consumed in the previous iteration
+            const int nk = kc + kGemmStages - 1;
+            if (nk < nchunks) load_chunk(nk, nk % kGemmStages);
+            cp_async_commit();
+        }
+        const double *as = As + (kc % kGemmStages) * A_STAGE + a_lane;
+        const double *bs = Bs + (kc % kGemmStages) * B_STAGE + b_lane;
+#pragma unroll
+        for (int ks = 0; ks < kGemmKC / 4; ++ks) {
+            double af[4], bf[NT];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) af[mt] = as[mt * 8 * kGemmLdA + ks * 4];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) bf[nt] = bs[ks * 4 * LdB + nt * 8];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+        }
+    }
+    cp_async_wait_n(0);
+    // epilogue: lane holds C[row = lane/4][cols 2*(lane%4), +1] of every 8x8 tile
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+        const long long row = row0 + wm * 32 + mt * 8 + (lane >> 2);
+        if (row >= B) continue;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int col = col0 + wn * (BN / 2) + nt * 8 + 2 * (lane & 3);
+            if (col < m) R[row * m + col] = (To)acc[mt][nt][0];
+            if (col + 1 < m) R[row * m + col + 1] = (To)acc[mt][nt][1];
+        }
+    }
+}
+
+static inline int gemm_bn(int m) { return m <= 64 ? 64 : 128; }
+static inline int gemm_ldb(int m) { const int bn = gemm_bn(m); return (m + bn - 1) / bn * bn; }
+static inline int gemm_dp(int d) { return (d + kGemmKC - 1) / kGemmKC * kGemmKC; }
+static inline size_t gemm_smem(int bn) {
+    return sizeof(double) * (size_t)kGemmStages * ((size_t)kGemmBM * kGemmLdA + (size_t)kGemmKC * (bn + 4));
+}
+
+}  // namespace gpde

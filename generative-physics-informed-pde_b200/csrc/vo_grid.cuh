@@ -140,7 +140,10 @@ __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int
     }
 }
 
-template <int NT>
+// RHO = false: contraction with V inside the kernel (NT n-tiles, m <= 32), output r[B,m].
+// RHO = true : no contraction; the fine residual rho[b, i] = cvs * S_i - f_i goes to r (row pitch = m doubles,
+//              K padding [d, m) zeroed) for the tensor-core GEMM of vo_gemm.cuh (m > 32).  Vp is unused.
+template <int NT, bool RHO>
 __global__ void __launch_bounds__(kGridThreads, 1)
 vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
@@ -159,6 +162,7 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     const int sl = grp * 8 + s;                       // sample slot inside the CTA
     const long long cta_b0 = (long long)blockIdx.x * S;
     long long b = cta_b0 + sl;
+    const bool b_valid = b < B;
     if (b >= B) b = B - 1;                            // duplicates the last sample; never stored
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
     const long long d = (long long)ncol * (ny + 1);
@@ -218,7 +222,7 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
         y_src += ncol;
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
         if (threadIdx.x == 0) {
-            if (ts >= 1 && !(dbg & 4)) {
+            if (!RHO && ts >= 1 && !(dbg & 4)) {
                 mbar_arrive_expect_tx(bar, (unsigned)v_row_doubles * 8);
                 bulk_g2s(st + G.v_off, Vp + (size_t)(ts - 1) * v_row_doubles, (unsigned)v_row_doubles * 8, bar);
             } else {
@@ -379,16 +383,25 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
 #pragma unroll
                 for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
             }
-            const double *vs = reinterpret_cast<const double *>(st + v_lane_off);
-            double bf[4][NT];
+            if constexpr (RHO) {
+                if (b_valid) {
+                    double *dst = r + b * (long long)m + (long long)(t - 1) * ncol + c0;
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+                    for (int j = 0; j < 4; ++j)
+                        if ((nodemask >> j) & 1) dst[j] = G.scale * Sv[j];
+                }
+            } else {
+                const double *vs = reinterpret_cast<const double *>(st + v_lane_off);
+                double bf[4][NT];
 #pragma unroll
-                for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
+                for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
+                    for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
 #pragma unroll
-                for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+                for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                    for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + c_slot);
@@ -400,6 +413,15 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
         for (int j = 0; j < 5; ++j) ap[j] = an[j];
     }
 
+    if constexpr (RHO) {
+        // zero the K padding [d, m) of this CTA's rows
+        const int pad = m - (int)d;
+        for (int idx = threadIdx.x; idx < S * pad; idx += kGridThreads) {
+            const int si = idx / pad, c = idx - si * pad;
+            if (cta_b0 + si < B) r[(cta_b0 + si) * (long long)m + d + c] = 0.0;
+        }
+        return;
+    }
     // ---- sum the strips' partial tiles and store r = cvs * sum   (stage memory is free now)
     __syncthreads();
     double *red = reinterpret_cast<double *>(stages);   // [groups][nstrips][8 samples][NT*8]
