@@ -350,12 +350,6 @@ static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, c
     while (nstrips * 16 < ncol) nstrips *= 2;
     G.nx = nx; G.ny = ny; G.ncol = ncol; G.nstrips = nstrips; G.groups = 16 / nstrips;
     G.in0 = in0; G.sy = sy; G.rh = chs / cvs; G.scale = cvs;
-    const int S = 8 * G.groups;
-    G.a_stride = nx + 2;
-    G.y_stride = 16 * nstrips + 4;
-    G.a_off = 0;
-    G.y_off = S * G.a_stride * 8;
-    G.v_off = (G.y_off + S * G.y_stride * 8 + 127) & ~127;
     G.has_load = 0;
     std::vector<double> f_over(d);
     for (int i = 0; i < d; ++i) {
@@ -367,9 +361,31 @@ static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, c
     return e;
 }
 
-// bytes of one pipeline stage / of the packed V for NT n-tiles
-static inline size_t grid_stage_bytes(const GridDev &G, int NT) { return (size_t)G.v_off + (size_t)G.nstrips * 4 * NT * 32 * 8; }
+// Shared-memory layout of one pipeline stage holding R node rows (see vo_grid.cuh): per-sample regions of
+// a_stride / y_stride doubles (pitches chosen so that the 8 samples of a warp hit distinct banks), then the
+// packed V rows.  Returns the stage size in bytes for NT n-tiles (NT = 0: no V in the stage).
+static inline size_t grid_layout(GridDev &G, int R, int NT) {
+    const int S = 8 * G.groups;
+    G.a_stride = R * G.nx + 2;
+    G.y_stride = ((R - 1) * G.ncol + 16 * G.nstrips + 4 + 3) & ~3;
+    G.a_off = 0;
+    G.y_off = S * G.a_stride * 8;
+    G.v_off = (G.y_off + S * G.y_stride * 8 + 127) & ~127;
+    return (size_t)G.v_off + (size_t)R * G.nstrips * 4 * NT * 32 * 8;
+}
 static inline size_t grid_packed_bytes(const GridDev &G, int NT) { return (size_t)(G.ny + 1) * G.nstrips * 4 * NT * 32 * 8; }
+// rows per stage and ring depth that fit the 227 KB of a CTA: two rows per stage halve the per-row barrier and
+// staging overhead (GPDE_GRID_R forces 1 or 2 for experiments)
+static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, size_t &stage) {
+    const size_t budget = 225 * 1024 - 512;
+    const char *e = getenv("GPDE_GRID_R");
+    for (R = (e ? atoi(e) : 2); R >= 1; --R) {
+        stage = grid_layout(G, R, NT);
+        NS = (int)std::min<size_t>(R == 2 ? 3 : 4, budget / stage);
+        if (NS >= 2) return true;
+    }
+    return false;
+}
 
 // GPDE_VO_PATH=v1 forces the unfused version-1 kernels (A/B testing, fallback check)
 static bool use_fused(const gpde_vo_plan *pl) {
@@ -394,10 +410,9 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     if (!y || m < 1 || m > 32) return 0;
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
-    const size_t stage = grid_stage_bytes(G, NT);
-    const size_t budget = 225 * 1024 - 512;
-    int NS = (int)std::min<size_t>(4, budget / stage);
-    if (NS < 2) return 0;
+    int R, NS;
+    size_t stage;
+    if (!grid_pick(G, NT, R, NS, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     double *Vp = (double *)workspace;
     {
@@ -409,15 +424,21 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     const int dbg = getenv("GPDE_GRID_DEBUG") ? atoi(getenv("GPDE_GRID_DEBUG")) : 0;   // timing experiments only
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-#define GPDE_LAUNCH_GRID(NTV)                                                                                    \
+#define GPDE_LAUNCH_GRID(NTV, RV)                                                                                \
     {                                                                                                            \
-        auto kern = vo_grid_kernel<NTV, false>;                                                                       \
+        auto kern = vo_grid_kernel<NTV, false, RV>;                                                              \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
     }
-    if (NT == 1) GPDE_LAUNCH_GRID(1)
-    else if (NT == 2) GPDE_LAUNCH_GRID(2)
-    else GPDE_LAUNCH_GRID(4)
+    if (R == 2) {
+        if (NT == 1) GPDE_LAUNCH_GRID(1, 2)
+        else if (NT == 2) GPDE_LAUNCH_GRID(2, 2)
+        else GPDE_LAUNCH_GRID(4, 2)
+    } else {
+        if (NT == 1) GPDE_LAUNCH_GRID(1, 1)
+        else if (NT == 2) GPDE_LAUNCH_GRID(2, 1)
+        else GPDE_LAUNCH_GRID(4, 1)
+    }
 #undef GPDE_LAUNCH_GRID
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
@@ -431,17 +452,22 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
     GridDev G = pl->grid;
     if (!y) return 0;
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
-    const size_t stage = (size_t)G.v_off;            // no V row in the stage
-    const size_t budget = 225 * 1024 - 512;
-    const int NS = (int)std::min<size_t>(6, budget / stage);
-    if (NS < 2) return 0;
+    int R, NS;
+    size_t stage;                                     // no V rows in the stage
+    if (!grid_pick(G, 0, R, NS, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     const int S = 8 * G.groups;
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-    auto kern = vo_grid_kernel<1, true>;
-    GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
+    if (R == 2) {
+        auto kern = vo_grid_kernel<1, true, 2>;
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
+    } else {
+        auto kern = vo_grid_kernel<1, true, 1>;
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
+    }
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
 }

@@ -71,6 +71,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
             : "=r"(done)
             : "r"(addr), "r"(parity)   // (a suspend-time hint made wake-ups ~10x slower on B200: measured, not used)
             : "memory");
+        if (!done) __nanosleep(40);
     } while (!done);
 }
 // global -> shared bulk copy (TMA engine, 1-D); bytes % 16 == 0, both addresses 16-byte aligned
@@ -143,7 +144,9 @@ __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int
 // RHO = false: contraction with V inside the kernel (NT n-tiles, m <= 32), output r[B,m].
 // RHO = true : no contraction; the fine residual rho[b, i] = cvs * S_i - f_i goes to r (row pitch = m doubles,
 //              K padding [d, m) zeroed) for the tensor-core GEMM of vo_gemm.cuh (m > 32).  Vp is unused.
-template <int NT, bool RHO>
+// R = node rows per pipeline stage: stage ts holds y rows [R ts, R ts + R), pixel rows and packed V rows
+//     [R ts - 1, R ts + R - 1) (clipped to the mesh); barrier traffic and staging overhead are per stage.
+template <int NT, bool RHO, int R>
 __global__ void __launch_bounds__(kGridThreads, 1)
 vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
@@ -167,9 +170,10 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
     const long long d = (long long)ncol * (ny + 1);
     const int c0 = 16 * q + 4 * k;
-    const int n_stages = ny + 2;
-    const int v_row_doubles = G.nstrips * 4 * NT * 32;
-    const unsigned long long y_end16 = ((unsigned long long)(y + B * d)) & ~15ull;   // 16-byte copies stop here
+    const int n_steps = ny + 2;                       // node rows 0..ny are produced at steps 1..ny+1
+    const int n_stages = (n_steps + R - 1) / R;
+    const int v_row_bytes = G.nstrips * 4 * NT * 32 * 8;
+    const int row_bytes = ncol * 8, prow_bytes = nx * 8;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -181,50 +185,63 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     if (threadIdx.x < 16) tab[threadIdx.x] = kExp16Tab[threadIdx.x];
     __syncthreads();
 
-    // ---- staging: stage ts = y row ts | pixel row ts-1 | packed V row ts-1, NS stages in a ring, issued
-    // NS-1 stages ahead of their use.  The a / y rows are 512-byte pieces: too small for the bulk-copy engine
-    // (measured: ~130 cycles per request) and one warp can keep only a few cp.async in flight (measured: a
-    // single staging warp delivers 4 GB/s), so EVERY warp stages the rows of its samples w, w+16, ... with
-    // 16-byte cp.async (LDGSTS, L2 -> shared, no registers; one row per warp instruction) whose completion
-    // arrives on the stage's mbarrier; the 16 KB packed V row is ONE bulk copy by thread 0.  y rows start on
-    // 8-byte boundaries: the copy runs from the enclosing 16-byte boundary and the consumer adds the same shift.
-    // Running pointers (advanced once per stage) keep the per-stage address arithmetic to a few instructions.
-    const int a_ops = nx >> 1;                                       // 16-byte pieces per pixel row
+    // ---- staging, NS stages in a ring, issued NS-1 stages ahead of their use.  The a / y rows are 0.5 KB
+    // pieces per sample: too small for the bulk-copy engine (measured: ~130 cycles per request) and one warp can
+    // keep only a few cp.async in flight (measured: a single staging warp delivers 4 GB/s), so EVERY warp stages
+    // the rows of its samples w, w+16, ... with 16-byte cp.async (LDGSTS, L2 -> shared, no registers) whose
+    // completion arrives on the stage's mbarrier; the packed V rows are ONE bulk copy by thread 0.  The R rows of
+    // a sample are contiguous in global memory and are copied as one block; y rows start on 8-byte boundaries:
+    // the block is copied from the enclosing 16-byte boundary and the consumer adds the same shift.
     const unsigned stages_u32 = smem_u32(stages);
-    const double *a_src = a + G.in0 - G.sy + 2 * lane;               // pixel row ts-1, this lane's piece, sample 0
-    const double *y_src = y;                                         // node row ts, sample 0
+    // this warp stages samples cta_b0 + warp + 16 i (i < n_mine); samples past the batch are not staged (their
+    // lanes compute on stale shared memory and are never stored)
+    const int n_mine = (int)max(0ll, min((long long)(S - warp + kGridWarps - 1) / kGridWarps,
+                                         (B - cta_b0 - warp + kGridWarps - 1) / kGridWarps));
+    const double *a_w = a + (cta_b0 + warp) * a_stride + G.in0;                      // pixel (0,0) of the first sample
+    const char *y_w = reinterpret_cast<const char *>(y + (cta_b0 + warp) * d);        // node row 0
+    const long long a_step = (long long)kGridWarps * a_stride, y_step = (long long)kGridWarps * d * 8;
+    const unsigned dst_a0 = G.a_off + warp * (G.a_stride * 8);
+    const unsigned dst_y0 = G.y_off + (warp * G.y_stride + 2 * ((warp >> 1) & 1)) * 8;
+    const bool y_end_odd = (((unsigned long long)(y + B * d)) & 15ull) != 0;
     auto issue_stage = [&](int ts, int slot) {
         unsigned char *st = stages + (size_t)slot * stage_bytes;
         unsigned long long *bar = full + slot;
+        const int t0 = R * ts;
         if (!(dbg & 2)) {
-            const bool has_a = ts >= 1 && ts <= ny, has_y = ts <= ny;
-            const int row_bytes = ncol * 8;
-            for (int si = warp; si < S; si += kGridWarps) {
-                const long long bs = min(cta_b0 + si, B - 1);
-                if (has_a) {
-                    const double *src = a_src + bs * a_stride;
-                    const unsigned dst = stages_u32 + slot * stage_bytes + G.a_off + si * (G.a_stride * 8) + 16 * lane;
-                    for (int ch = lane, o = 0; ch < a_ops; ch += 32, o += 512) cp_async16_u32(dst + o, src + (o >> 3));
-                }
-                if (has_y) {
-                    const char *src = reinterpret_cast<const char *>(y_src + bs * d);
+            const unsigned sbase = stages_u32 + slot * stage_bytes;
+            const int plo = max(0, t0 - 1), phi = min(ny, t0 - 1 + R);           // pixel rows [plo, phi)
+            if (phi > plo) {
+                const int first = G.sy > 0 ? plo : phi - 1;                        // lowest address
+                const int pos = G.sy > 0 ? plo - (t0 - 1) : R - 1 - (phi - 1 - (t0 - 1));
+                const int bytes = (phi - plo) * prow_bytes;
+                const char *src = reinterpret_cast<const char *>(a_w + (long long)first * G.sy);
+                unsigned dst = sbase + dst_a0 + pos * prow_bytes;
+                for (int i = 0; i < n_mine; ++i, src += a_step * 8, dst += kGridWarps * G.a_stride * 8)
+                    for (int o = 16 * lane; o < bytes; o += 512) cp_async16_u32(dst + o, src + o);
+            }
+            const int yhi = min(ny + 1, t0 + R);                                   // node rows [t0, yhi)
+            if (yhi > t0) {
+                const int bytes = (yhi - t0) * row_bytes;
+                const char *src = y_w + (long long)t0 * row_bytes;
+                unsigned dst = sbase + dst_y0;
+                for (int i = 0; i < n_mine; ++i, src += y_step, dst += kGridWarps * G.y_stride * 8) {
                     const int shift = (int)((unsigned long long)src & 15ull);
-                    const unsigned dst = stages_u32 + slot * stage_bytes + G.y_off + (si * G.y_stride + 2 * ((si >> 1) & 1)) * 8;
-                    // 16-byte pieces at offsets o = 16*lane - shift, + 512, ... from the row start; the last piece of the
-                    // whole tensor may stick out past its end (odd element count): it is left to the tail lanes
-                    const bool last_row = (unsigned long long)src + row_bytes + 8 > y_end16;
-                    for (int o = 16 * lane - shift; o < row_bytes; o += 512)
-                        if (!last_row || (unsigned long long)src + o + 16 <= y_end16) cp_async16_u32(dst + o + shift, src + o);
+                    // 16-byte pieces at offsets o = 16*lane - shift, + 512, ... from the block start; the last piece
+                    // of the whole tensor may stick out past its end (odd element count): left to the tail lanes
+                    const bool last = y_end_odd && yhi == ny + 1 && cta_b0 + warp + kGridWarps * i == B - 1;
+                    for (int o = 16 * lane - shift; o < bytes; o += 512)
+                        if (!last || o + 24 <= bytes) cp_async16_u32(dst + o + shift, src + o);
                 }
             }
         }
-        a_src += G.sy;
-        y_src += ncol;
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
         if (threadIdx.x == 0) {
-            if (!RHO && ts >= 1 && !(dbg & 4)) {
-                mbar_arrive_expect_tx(bar, (unsigned)v_row_doubles * 8);
-                bulk_g2s(st + G.v_off, Vp + (size_t)(ts - 1) * v_row_doubles, (unsigned)v_row_doubles * 8, bar);
+            const int vlo = max(0, t0 - 1), vhi = min(ny + 1, t0 - 1 + R);       // packed V rows [vlo, vhi)
+            if (!RHO && vhi > vlo && !(dbg & 4)) {
+                const unsigned bytes = (unsigned)(vhi - vlo) * v_row_bytes;
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_g2s(st + G.v_off + (vlo - (t0 - 1)) * v_row_bytes,
+                         reinterpret_cast<const char *>(Vp) + (size_t)vlo * v_row_bytes, bytes, bar);
             } else {
                 mbar_arrive(bar);
             }
@@ -261,13 +278,14 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     const double *gb = g ? g + b * g_stride : nullptr;
     // the very last element of y cannot be copied in a 16-byte piece when the tensor ends off a 16-byte boundary
     const int tail_p = ncol - 1 - c0;   // window position (-1..4) of the last free column, if inside
-    const bool tail_lane = (((unsigned long long)(y + B * d)) & 15ull) && b == B - 1 && tail_p >= -1 && tail_p <= 4;
-    // byte offsets of this lane's first column inside a stage; the y row's 8-byte phase alternates with t when ncol is odd
+    const bool tail_lane = y_end_odd && b == B - 1 && tail_p >= -1 && tail_p <= 4;
+    // byte offsets of this lane's first column inside a stage; the 8-byte phase of a stage's first y row
+    // alternates from stage to stage when R * ncol is odd
     const int y_lane_off = G.y_off + (sl * G.y_stride + 2 * ((sl >> 1) & 1) + c0) * 8;
     const int a_lane_off = G.a_off + (sl * G.a_stride + c0) * 8;
     const int v_lane_off = G.v_off + (q * 4 * NT * 32 + lane) * 8;
     int y_shift = (int)(((unsigned long long)yb) & 15ull);
-    const int y_shift_step = (ncol & 1) * 8;
+    const int y_shift_step = ((R * ncol) & 1) * 8;
 
     double acc[NT][2];
 #pragma unroll
@@ -277,140 +295,140 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     double fvp[4] = {0.0, 0.0, 0.0, 0.0};
     double gl_next = (need_gl && gb) ? gb[0] : 0.0, gr_next = (need_gr && gb) ? gb[1] : 0.0;
 
-    int c_slot = 0;                  // slot of stage t
+    int c_slot = 0;                  // slot of the stage being consumed
     unsigned f_par = 0;              // per-slot parity of the next wait on full[]
-    for (int t = 0; t < n_stages; ++t) {
+    for (int ts = 0; ts < n_stages; ++ts) {
         {
-            const int ts = t + NS - 1;
-            if (ts < n_stages) {
-                if (t >= 1) {        // the slot held stage t-1: wait until every warp has released it
+            const int tn = ts + NS - 1;
+            if (tn < n_stages) {
+                if (ts >= 1) {       // the slot held stage ts-1: wait until every warp has released it
                     mbar_wait(empty + i_slot, (e_par >> i_slot) & 1);
                     e_par ^= 1u << i_slot;
                 }
-                issue_stage(ts, i_slot);
+                issue_stage(tn, i_slot);
                 if (++i_slot == NS) i_slot = 0;
             }
         }
         const unsigned char *st = stages + (size_t)c_slot * stage_bytes;
         mbar_wait(full + c_slot, (f_par >> c_slot) & 1);
         f_par ^= 1u << c_slot;
-        if (dbg & 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(empty + c_slot);
-            if (++c_slot == NS) c_slot = 0;
-            continue;
-        }
 
-        // ---- new node row t and pixel row t-1
-        double un[4] = {0.0, 0.0, 0.0, 0.0}, unl = 0.0, unr = 0.0, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        if (t <= ny) {
-            const double gl = gl_next, gr = gr_next;
-            if (t < ny && gb) {
-                if (need_gl) gl_next = gb[2 * (t + 1)];
-                if (need_gr) gr_next = gb[2 * (t + 1) + 1];
-            }
-            const double *yr = reinterpret_cast<const double *>(st + y_lane_off + y_shift);
-            unl = yr[-1];
-            un[0] = yr[0]; un[1] = yr[1]; un[2] = yr[2]; un[3] = yr[3];
-            unr = yr[4];
-            if (tail_lane && t == ny) {
-                const double v = __ldg(yb + d - 1);
-                if (tail_p == -1) unl = v;
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (tail_p == j) un[j] = v;
-                if (tail_p == 4) unr = v;
-            }
-            if (edge_lane) {
-                auto pick = [&](int p, double v) {
-                    const int cat = (code >> (2 * p)) & 3;
-                    return cat == 0 ? v : (cat == 1 ? gl : (cat == 2 ? gr : 0.0));
-                };
-                unl = pick(0, unl);
-                un[0] = pick(1, un[0]); un[1] = pick(2, un[1]); un[2] = pick(3, un[2]); un[3] = pick(4, un[3]);
-                unr = pick(5, unr);
-            }
-        }
-        y_shift = (y_shift + y_shift_step) & 15;
-        if (t >= 1 && t <= ny) {
-            const double *ar = reinterpret_cast<const double *>(st + a_lane_off);
-            const double2 p01 = *reinterpret_cast<const double2 *>(ar);
-            const double2 p23 = *reinterpret_cast<const double2 *>(ar + 2);
-            an[0] = p01.x; an[1] = p01.y; an[2] = p23.x; an[3] = p23.y;
-            an[4] = ar[4];
-            if (pixmask != 31) {   // columns past the last pixel hold stale shared memory
-#pragma unroll
-                for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
-            }
-            if (a_is_log) {
-                const int hmax = max(max(max(exp_arg_hi(an[0]), exp_arg_hi(an[1])), max(exp_arg_hi(an[2]), exp_arg_hi(an[3]))),
-                                     exp_arg_hi(an[4]));
-                if (hmax <= kExpHiMax) {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+        for (int rr = 0; rr < R; ++rr) {
+            const int t = R * ts + rr;
+            if (t >= n_steps || (dbg & 1)) break;
+            // ---- new node row t and pixel row t-1
+            double un[4] = {0.0, 0.0, 0.0, 0.0}, unl = 0.0, unr = 0.0, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            if (t <= ny) {
+                const double gl = gl_next, gr = gr_next;
+                if (t < ny && gb) {
+                    if (need_gl) gl_next = gb[2 * (t + 1)];
+                    if (need_gr) gr_next = gb[2 * (t + 1) + 1];
                 }
-            }
-            if (pixmask != 31) {
-#pragma unroll
-                for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
-            }
-        }
-
-        // ---- node row t-1: fluxes -> S -> tensor-core contraction with packed V row t-1
-        if (t >= 1) {
-            double fh[5];
-            fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
-            fh[1] = (ap[1] + an[1]) * (uc[1] - uc[0]);
-            fh[2] = (ap[2] + an[2]) * (uc[2] - uc[1]);
-            fh[3] = (ap[3] + an[3]) * (uc[3] - uc[2]);
-            fh[4] = (ap[4] + an[4]) * (urc - uc[3]);
-            double Sv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double fv = (an[j] + an[j + 1]) * (un[j] - uc[j]);
-                Sv[j] = fma(G.rh, fh[j + 1] - fh[j], fv - fvp[j]);
-                fvp[j] = fv;
-            }
-            if (G.has_load) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((nodemask >> j) & 1) Sv[j] -= __ldg(G.f_over + (long long)(t - 1) * ncol + c0 + j);
-            }
-            if (nodemask != 15) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
-            }
-            if constexpr (RHO) {
-                if (b_valid) {
-                    double *dst = r + b * (long long)m + (long long)(t - 1) * ncol + c0;
+                const double *yr = reinterpret_cast<const double *>(st + y_lane_off + y_shift + rr * row_bytes);
+                unl = yr[-1];
+                un[0] = yr[0]; un[1] = yr[1]; un[2] = yr[2]; un[3] = yr[3];
+                unr = yr[4];
+                if (tail_lane && t == ny) {
+                    const double v = __ldg(yb + d - 1);
+                    if (tail_p == -1) unl = v;
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if ((nodemask >> j) & 1) dst[j] = G.scale * Sv[j];
+                        if (tail_p == j) un[j] = v;
+                    if (tail_p == 4) unr = v;
                 }
-            } else {
-                const double *vs = reinterpret_cast<const double *>(st + v_lane_off);
-                double bf[4][NT];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                    for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+                if (edge_lane) {
+                    auto pick = [&](int p, double v) {
+                        const int cat = (code >> (2 * p)) & 3;
+                        return cat == 0 ? v : (cat == 1 ? gl : (cat == 2 ? gr : 0.0));
+                    };
+                    unl = pick(0, unl);
+                    un[0] = pick(1, un[0]); un[1] = pick(2, un[1]); un[2] = pick(3, un[2]); un[3] = pick(4, un[3]);
+                    unr = pick(5, unr);
+                }
             }
+            if (t >= 1 && t <= ny) {
+                const int pos = G.sy > 0 ? rr : R - 1 - rr;
+                const double *ar = reinterpret_cast<const double *>(st + a_lane_off + pos * prow_bytes);
+                const double2 p01 = *reinterpret_cast<const double2 *>(ar);
+                const double2 p23 = *reinterpret_cast<const double2 *>(ar + 2);
+                an[0] = p01.x; an[1] = p01.y; an[2] = p23.x; an[3] = p23.y;
+                an[4] = ar[4];
+                if (pixmask != 31) {   // columns past the last pixel hold stale shared memory
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+                }
+                if (a_is_log) {
+                    const int hmax = max(max(max(exp_arg_hi(an[0]), exp_arg_hi(an[1])), max(exp_arg_hi(an[2]), exp_arg_hi(an[3]))),
+                                         exp_arg_hi(an[4]));
+                    if (hmax <= kExpHiMax) {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+                    }
+                }
+                if (pixmask != 31) {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+                }
+            }
+
+            // ---- node row t-1: fluxes -> S -> tensor-core contraction with packed V row t-1 (or rho output)
+            if (t >= 1) {
+                double fh[5];
+                fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
+                fh[1] = (ap[1] + an[1]) * (uc[1] - uc[0]);
+                fh[2] = (ap[2] + an[2]) * (uc[2] - uc[1]);
+                fh[3] = (ap[3] + an[3]) * (uc[3] - uc[2]);
+                fh[4] = (ap[4] + an[4]) * (urc - uc[3]);
+                double Sv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double fv = (an[j] + an[j + 1]) * (un[j] - uc[j]);
+                    Sv[j] = fma(G.rh, fh[j + 1] - fh[j], fv - fvp[j]);
+                    fvp[j] = fv;
+                }
+                if (G.has_load) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((nodemask >> j) & 1) Sv[j] -= __ldg(G.f_over + (long long)(t - 1) * ncol + c0 + j);
+                }
+                if (nodemask != 15) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
+                }
+                if constexpr (RHO) {
+                    if (b_valid) {
+                        double *dst = r + b * (long long)m + (long long)(t - 1) * ncol + c0;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            if ((nodemask >> j) & 1) dst[j] = G.scale * Sv[j];
+                    }
+                } else {
+                    const double *vs = reinterpret_cast<const double *>(st + v_lane_off + rr * v_row_bytes);
+                    double bf[4][NT];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                        for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) uc[j] = un[j];
+            ulc = unl; urc = unr;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) ap[j] = an[j];
         }
+        y_shift = (y_shift + y_shift_step) & 15;
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + c_slot);
         if (++c_slot == NS) c_slot = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) uc[j] = un[j];
-        ulc = unl; urc = unr;
-#pragma unroll
-        for (int j = 0; j < 5; ++j) ap[j] = an[j];
     }
 
     if constexpr (RHO) {
