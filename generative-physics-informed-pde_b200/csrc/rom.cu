@@ -42,6 +42,10 @@ struct RomDev {
     const int *st_ptr, *st_elem;
     const double *st_coef;
     const unsigned char *is_bc;  // [n]
+    // every table the forward / adjoint kernels read lives in ONE device arena (st_* excluded); the kernels
+    // copy it into shared memory once per CTA and read the tables there (no dependent global loads)
+    const char *arena;
+    int arena_bytes;
 };
 }  // namespace gpde
 
@@ -154,15 +158,41 @@ __device__ __forceinline__ void backward_subst(const RomDev &P, int gl, const do
     }
 }
 
+
+// Copies the plan's table arena into shared memory (once per CTA) and returns a RomDev whose table pointers
+// point at the copy.  sample_smem is set to the first 16-byte aligned address after it.
+__device__ __forceinline__ RomDev stage_tables(const RomDev &P, double *smem, double **sample_smem) {
+    char *dst = reinterpret_cast<char *>(smem);
+    const uint4 *src = reinterpret_cast<const uint4 *>(P.arena);
+    for (int i = threadIdx.x; i < P.arena_bytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(dst)[i] = src[i];
+    __syncthreads();
+    RomDev Q = P;
+    // derive the new pointers from the shared-memory base (not from the kernel-parameter pointers, which the
+    // compiler knows to be global and would keep loading with ld.global)
+#define GPDE_REBASE(f) \
+    Q.f = reinterpret_cast<decltype(Q.f)>(dst + (size_t)(reinterpret_cast<const char *>(P.f) - P.arena))
+    GPDE_REBASE(free_dof); GPDE_REBASE(bc_dof);
+    GPDE_REBASE(band_ptr); GPDE_REBASE(band_elem); GPDE_REBASE(band_coef);
+    GPDE_REBASE(rhs_ptr); GPDE_REBASE(rhs_elem); GPDE_REBASE(rhs_dof); GPDE_REBASE(rhs_coef);
+    GPDE_REBASE(grad_ptr); GPDE_REBASE(grad_i); GPDE_REBASE(grad_j); GPDE_REBASE(grad_coef);
+    GPDE_REBASE(cf_ptr); GPDE_REBASE(cf_elem); GPDE_REBASE(cf_free); GPDE_REBASE(cf_coef);
+    GPDE_REBASE(pair_si); GPDE_REBASE(pair_sj);
+#undef GPDE_REBASE
+    *sample_smem = smem + P.arena_bytes / 8;
+    return Q;
+}
+
 // ---------------------------------------------------------------------------------------------
 // forward:  X, F -> u (+ factor stash)
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 __global__ void __launch_bounds__(kRomThreads)
-rom_forward_kernel(RomDev P, const T *__restrict__ X, int x_is_log, const T *__restrict__ F,
+rom_forward_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__restrict__ F,
                    T *__restrict__ u, double *__restrict__ factor, int *info, long long B,
                    int smem_doubles_per_sample) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem_all[];
+    double *smem;
+    const RomDev P = stage_tables(P0, smem_all, &smem);
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G, gidx = warp * GPW + lane / G;
@@ -213,10 +243,12 @@ rom_forward_kernel(RomDev P, const T *__restrict__ X, int x_is_log, const T *__r
 // ---------------------------------------------------------------------------------------------
 template <typename T, int G>
 __global__ void __launch_bounds__(kRomThreads)
-rom_adjoint_kernel(RomDev P, const T *__restrict__ X, int x_is_log, const T *__restrict__ u,
+rom_adjoint_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__restrict__ u,
                    const double *__restrict__ factor, const T *__restrict__ gbar, T *__restrict__ gradX,
                    T *__restrict__ gradF, long long B, int smem_doubles_per_sample) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem_all[];
+    double *smem;
+    const RomDev P = stage_tables(P0, smem_all, &smem);
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G, gidx = warp * GPW + lane / G;
@@ -319,7 +351,7 @@ static int launch_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, con
                           int *info, int64_t B, cudaStream_t st) {
     const int groups = (kRomThreads / 32) * (32 / G);
     const int per = (int)(pl->smem_fwd / sizeof(double));
-    const size_t smem = (size_t)groups * pl->smem_fwd;
+    const size_t smem = (size_t)groups * pl->smem_fwd + (size_t)pl->dev.arena_bytes;
     auto kern = rom_forward_kernel<T, G>;
     GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (B + groups - 1) / groups;
@@ -333,7 +365,7 @@ static int launch_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, con
                           const T *gbar, T *gradX, T *gradF, int64_t B, cudaStream_t st) {
     const int groups = (kRomThreads / 32) * (32 / G);
     const int per = (int)(pl->smem_adj / sizeof(double));
-    const size_t smem = (size_t)groups * pl->smem_adj;
+    const size_t smem = (size_t)groups * pl->smem_adj + (size_t)pl->dev.arena_bytes;
     auto kern = rom_adjoint_kernel<T, G>;
     GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long grid = (B + groups - 1) / groups;
@@ -508,13 +540,34 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
     D.n = n; D.E = E; D.n_bc = (int)bc_dof.size(); D.n_free = nf; D.hbw = hbw; D.bw1 = bw1; D.n_band = n_band;
     D.n_pairs = (int)pair_si.size();
     int rc = GPDE_OK;
+    // the kernels' tables go into ONE arena (16-byte aligned pieces) that each CTA copies to shared memory
+    std::vector<char> arena;
+    auto put = [&arena](const void *src, size_t bytes) {
+        const size_t off = (arena.size() + 15) & ~(size_t)15;
+        arena.resize(off + bytes);
+        if (bytes) memcpy(arena.data() + off, src, bytes);
+        return off;
+    };
+#define AR(field, vec) const size_t off_##field = put(vec.data(), vec.size() * sizeof(vec[0]))
+    AR(band_coef, band_coef); AR(rhs_coef, rhs_coef); AR(grad_coef, grad_coef); AR(cf_coef, cf_coef);
+    AR(free_dof, free_dof); AR(bc_dof, bc_dof);
+    AR(band_ptr, band_ptr); AR(band_elem, band_elem);
+    AR(rhs_ptr, rhs_ptr); AR(rhs_elem, rhs_elem); AR(rhs_dof, rhs_dof);
+    AR(grad_ptr, grad_ptr); AR(grad_i, grad_i); AR(grad_j, grad_j);
+    AR(cf_ptr, cf_ptr); AR(cf_elem, cf_elem); AR(cf_free, cf_free);
+    AR(pair_si, pair_si); AR(pair_sj, pair_sj);
+#undef AR
+    arena.resize((arena.size() + 15) & ~(size_t)15);
+    const char *arena_dev = nullptr;
+    if (rc == GPDE_OK) rc = track(pl, &arena_dev, arena);
+    D.arena = arena_dev;
+    D.arena_bytes = (int)arena.size();
+#define SET(field) D.field = reinterpret_cast<decltype(D.field)>(arena_dev + off_##field)
+    SET(band_coef); SET(rhs_coef); SET(grad_coef); SET(cf_coef); SET(free_dof); SET(bc_dof);
+    SET(band_ptr); SET(band_elem); SET(rhs_ptr); SET(rhs_elem); SET(rhs_dof);
+    SET(grad_ptr); SET(grad_i); SET(grad_j); SET(cf_ptr); SET(cf_elem); SET(cf_free); SET(pair_si); SET(pair_sj);
+#undef SET
 #define UP(field, vec) if (rc == GPDE_OK) rc = track(pl, &D.field, vec)
-    UP(free_dof, free_dof); UP(bc_dof, bc_dof);
-    UP(band_ptr, band_ptr); UP(band_elem, band_elem); UP(band_coef, band_coef);
-    UP(rhs_ptr, rhs_ptr); UP(rhs_elem, rhs_elem); UP(rhs_dof, rhs_dof); UP(rhs_coef, rhs_coef);
-    UP(grad_ptr, grad_ptr); UP(grad_i, grad_i); UP(grad_j, grad_j); UP(grad_coef, grad_coef);
-    UP(cf_ptr, cf_ptr); UP(cf_elem, cf_elem); UP(cf_free, cf_free); UP(cf_coef, cf_coef);
-    UP(pair_si, pair_si); UP(pair_sj, pair_sj);
     UP(st_ptr, st_ptr); UP(st_elem, st_elem); UP(st_coef, st_coef); UP(is_bc, is_bc);
 #undef UP
     if (rc != GPDE_OK) {
@@ -527,10 +580,10 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
     pl->smem_fwd = sizeof(double) * (size_t)(E + n + n_band + 3 * nf);
     pl->smem_adj = sizeof(double) * (size_t)(2 * E + 2 * n + n_band + 4 * nf);
     const size_t groups = (kRomThreads / 32) * (32 / pl->lanes);
-    if (groups * pl->smem_adj > 227 * 1024) {
+    if (groups * pl->smem_adj + arena.size() > 227 * 1024) {
         gpde_rom_plan_destroy(pl);
         return fail(GPDE_ERR_SIZE, "rom_plan_create: %zu bytes of shared memory per CTA exceed 227 KB",
-                    groups * pl->smem_adj);
+                    groups * pl->smem_adj + arena.size());
     }
     *plan = pl;
     return GPDE_OK;
