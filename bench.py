@@ -362,6 +362,10 @@ def run_b200(args):
     vo_bytes = w.vo_bytes_per_eval(s) * B
     achieved = vo_bytes / (t_vo * 1e-3) / 1e9
     cgm_bytes = w.cgm_bytes_per_solve(s) * B
+    path = vplan.kernel_path(w.m, tdt)
+    # FP64 work of one VO evaluation: exp 11 x 1.25, fluxes 10, contraction m (FMA = 2 flop)
+    vo_flops = 2.0 * w.d * (11 * 1.25 + 10 + w.m) * B
+    fp64_peak = 37.0   # TFLOP/s, DMMA/DFMA rate measured on this pool: profiles/r1_fp64_peak.txt
     line = {
         "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -375,11 +379,17 @@ def run_b200(args):
             "launch_mode": mode, "ms_per_step_eager": eager_ms, "ms_host_enqueue_per_step": host_enqueue_ms,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
         },
-        "roofline": {"kernel": {3: "vo_grid_kernel<rho> + vo_gemm_kernel", 2: "vo_grid_kernel (+ vo_grid_pack_kernel)",
-                                 1: "vo_fused_kernel"}.get(vplan.kernel_path(w.m, tdt), "vo_matvec_kernel + vo_gemm_kernel"),
-                     "bound": "hbm", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes},
+        "roofline": ({"kernel": "vo_grid_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
+                      "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                      "frac": vo_flops / (t_vo * 1e-3) / 1e12 / fp64_peak, "traffic": recorded_traffic(args.workload, args.dtype),
+                      "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
+                      "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
+                     if path in (0, 3) and w.m > 32 else
+                     {"kernel": {2: "vo_grid_kernel (+ vo_grid_pack_kernel)", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
+                      "bound": "hbm", "achieved": achieved, "peak": peak,
+                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
+                      "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes,
+                      "fp64_pipe_frac": vo_flops / (t_vo * 1e-3) / 1e12 / fp64_peak}),
         "gpu_launches": launches_per_step * K,
         "clocks": sampler.summary(t_wall0, t_wall1) if sampler else None,
         "e2e": e2e,
