@@ -348,7 +348,7 @@ static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, c
 
     int nstrips = 1;
     while (nstrips * 16 < ncol) nstrips *= 2;
-    G.nx = nx; G.ny = ny; G.ncol = ncol; G.nstrips = nstrips; G.groups = 16 / nstrips;
+    G.nx = nx; G.ny = ny; G.ncol = ncol; G.nstrips = nstrips; G.groups = kGridWarpsMax / nstrips;
     G.in0 = in0; G.sy = sy; G.rh = chs / cvs; G.scale = cvs;
     G.has_load = 0;
     std::vector<double> f_over(d);
@@ -376,9 +376,11 @@ static inline size_t grid_layout(GridDev &G, int R, int NT) {
 static inline size_t grid_packed_bytes(const GridDev &G, int NT) { return (size_t)(G.ny + 1) * G.nstrips * 4 * NT * 32 * 8; }
 // rows per stage and ring depth that fit the 227 KB of a CTA: two rows per stage halve the per-row barrier and
 // staging overhead (GPDE_GRID_R forces 1 or 2 for experiments)
-static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, size_t &stage) {
-    const size_t budget = 225 * 1024 - 512;
-    const char *e = getenv("GPDE_GRID_R");
+static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t &stage) {
+    const char *e = getenv("GPDE_GRID_R"), *ew = getenv("GPDE_GRID_W");
+    W = (ew && atoi(ew) == 8 && G.nstrips <= 8) ? 8 : 16;    // 8 warps per CTA = two CTAs per SM (experiment switch)
+    G.groups = W / G.nstrips;
+    const size_t budget = (W == 16 ? 225 * 1024 : 112 * 1024) - 512;
     for (R = (e ? atoi(e) : 2); R >= 1; --R) {
         stage = grid_layout(G, R, NT);
         NS = (int)std::min<size_t>(R == 2 ? 3 : 4, budget / stage);
@@ -410,9 +412,9 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     if (!y || m < 1 || m > 32) return 0;
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
-    int R, NS;
+    int R, NS, W;
     size_t stage;
-    if (!grid_pick(G, NT, R, NS, stage)) return 0;
+    if (!grid_pick(G, NT, R, NS, W, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     double *Vp = (double *)workspace;
     {
@@ -424,21 +426,26 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     const int dbg = getenv("GPDE_GRID_DEBUG") ? atoi(getenv("GPDE_GRID_DEBUG")) : 0;   // timing experiments only
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-#define GPDE_LAUNCH_GRID(NTV, RV)                                                                                \
+#define GPDE_LAUNCH_GRID(NTV, RV, WV)                                                                            \
     {                                                                                                            \
-        auto kern = vo_grid_kernel<NTV, false, RV>;                                                              \
+        auto kern = vo_grid_kernel<NTV, false, RV, WV>;                                                          \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
+        kern<<<grid, WV * 32, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
     }
-    if (R == 2) {
-        if (NT == 1) GPDE_LAUNCH_GRID(1, 2)
-        else if (NT == 2) GPDE_LAUNCH_GRID(2, 2)
-        else GPDE_LAUNCH_GRID(4, 2)
+#define GPDE_LAUNCH_GRID_NT(RV, WV)                                                                              \
+    {                                                                                                            \
+        if (NT == 1) GPDE_LAUNCH_GRID(1, RV, WV)                                                                 \
+        else if (NT == 2) GPDE_LAUNCH_GRID(2, RV, WV)                                                            \
+        else GPDE_LAUNCH_GRID(4, RV, WV)                                                                         \
+    }
+    if (W == 16) {
+        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 16)
+        else GPDE_LAUNCH_GRID_NT(1, 16)
     } else {
-        if (NT == 1) GPDE_LAUNCH_GRID(1, 1)
-        else if (NT == 2) GPDE_LAUNCH_GRID(2, 1)
-        else GPDE_LAUNCH_GRID(4, 1)
+        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8)
+        else GPDE_LAUNCH_GRID_NT(1, 8)
     }
+#undef GPDE_LAUNCH_GRID_NT
 #undef GPDE_LAUNCH_GRID
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
@@ -452,22 +459,25 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
     GridDev G = pl->grid;
     if (!y) return 0;
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
-    int R, NS;
+    int R, NS, W;
     size_t stage;                                     // no V rows in the stage
-    if (!grid_pick(G, 0, R, NS, stage)) return 0;
+    if (!grid_pick(G, 0, R, NS, W, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     const int S = 8 * G.groups;
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-    if (R == 2) {
-        auto kern = vo_grid_kernel<1, true, 2>;
-        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
-    } else {
-        auto kern = vo_grid_kernel<1, true, 1>;
-        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<grid, kGridThreads, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0);
+#define GPDE_LAUNCH_RHO(RV, WV)                                                                                  \
+    {                                                                                                            \
+        auto kern = vo_grid_kernel<1, true, RV, WV>;                                                             \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<grid, WV * 32, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0); \
     }
+    if (W == 16) {
+        if (R == 2) GPDE_LAUNCH_RHO(2, 16) else GPDE_LAUNCH_RHO(1, 16)
+    } else {
+        if (R == 2) GPDE_LAUNCH_RHO(2, 8) else GPDE_LAUNCH_RHO(1, 8)
+    }
+#undef GPDE_LAUNCH_RHO
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
 }

@@ -43,8 +43,7 @@ struct GridDev {
     int a_off, y_off, v_off;  // byte offsets inside a stage
 };
 
-constexpr int kGridWarps = 16;
-constexpr int kGridThreads = kGridWarps * 32;
+constexpr int kGridWarpsMax = 16;   // warps per CTA: 16 (one CTA per SM) or 8 (two CTAs per SM)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async16_u32(unsigned smem_dst, const void *gmem_src) {
@@ -146,8 +145,10 @@ __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int
 //              K padding [d, m) zeroed) for the tensor-core GEMM of vo_gemm.cuh (m > 32).  Vp is unused.
 // R = node rows per pipeline stage: stage ts holds y rows [R ts, R ts + R), pixel rows and packed V rows
 //     [R ts - 1, R ts + R - 1) (clipped to the mesh); barrier traffic and staging overhead are per stage.
-template <int NT, bool RHO, int R>
-__global__ void __launch_bounds__(kGridThreads, 1)
+// W = warps per CTA: 16 with one CTA per SM, or 8 with two CTAs per SM (two independent rings per SM break the
+//     per-stage lockstep of a single ring).
+template <int NT, bool RHO, int R, int W>
+__global__ void __launch_bounds__(W * 32, W == 16 ? 1 : 2)
 vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
                const double *__restrict__ Vp, int m, double *__restrict__ r, long long B, int NS,
@@ -158,6 +159,7 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     unsigned long long *empty = full + NS;
     double *tab = reinterpret_cast<double *>(empty + NS);
 
+    constexpr int kGridWarps = W, kGridThreads = W * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int q = warp % G.nstrips, grp = warp / G.nstrips;
     const int s = lane >> 2, k = lane & 3;

@@ -210,3 +210,29 @@ def test_empty_batch(dev):
     rom = _rom_from_golden(g, torch.float64, dev)
     u = rom(torch.ones(0, 32, dtype=torch.float64, device=dev), torch.zeros(0, 25, dtype=torch.float64, device=dev))
     assert u.shape == (0, 25)
+
+
+def test_large_batch_config4_shard(dev):
+    """One GPU's share of BASELINE config 4 at 8 GPUs (131072 / 8 samples... and the whole 131072 batch): forward +
+    adjoint on the full batch equal the same samples solved in a small batch (samples are independent, bitwise)."""
+    from gpde_b200.components import ReducedOrderModelOperator
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg2", B=64, seed=4)
+    op = ReducedOrderModelOperator.FromPhysics(w.physics, dtype=torch.float64, device=dev)
+    B = 131072
+    gen = torch.Generator().manual_seed(0)
+    logX = (0.4 + 0.8 * torch.randn(B, w.E, generator=gen, dtype=torch.float64)).to(dev).requires_grad_(True)
+    F = torch.tensor(w.F[0], device=dev).expand(B, -1).contiguous()
+    gbar = torch.randn(B, w.n, generator=gen, dtype=torch.float64).to(dev)
+    u = op.rom.solve_log(logX, F)
+    u.backward(gbar)
+    idx = torch.tensor([0, 1, 4095, 4096, 65535, 100000, B - 1], device=dev)
+    lx = logX.detach()[idx].clone().requires_grad_(True)
+    us = op.rom.solve_log(lx, F[idx])
+    us.backward(gbar[idx])
+    assert torch.equal(us.detach(), u.detach()[idx]) and torch.equal(lx.grad, logX.grad[idx])
+    assert torch.isfinite(u).all() and torch.isfinite(logX.grad).all()
+    # residual of the solve itself: A(x) u = F on the free rows, through GetStiffness on a slice
+    K = op.rom.GetStiffness(torch.exp(lx.detach()) + 1e-8, DirichletBC=True)          # [n,n,7]
+    res = torch.einsum('ijb,bj->bi', K, us.detach()) - F[idx]
+    assert res.abs().max() < 1e-12

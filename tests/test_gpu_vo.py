@@ -380,3 +380,51 @@ def test_unfused_kernels_against_reference_vectors(dev, monkeypatch):
     plan = VoPlan(ph['fom'], dev)
     a, y, gv, V = (torch.tensor(g[k], device=dev) for k in ('in_X_DG', 'in_Y', 'in_g_fom', 'in_V'))
     assert rel_err(plan.residual(a, y, gv, V).cpu(), g['out_residual']) < 1e-10
+
+
+def test_full_size_properties_config3(dev, monkeypatch):
+    """128x128 FOM with 256 weighting functions (BASELINE config 3 mesh and m; a 384-sample slice of the batch so the
+    test stays short): grid rho kernel + FP64 tensor-core contraction against closed forms and the generic kernels."""
+    from gpde_b200.VirtualObservables import VoPlan
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg3", B=384, seed=0)
+    fom = w.physics['fom']
+    plan = VoPlan.cached(fom, dev, pixel_input=True)
+    assert w.m == 256 and w.d == 16383 and plan.kernel_path(w.m) == 3 and plan.launches_per_residual(w.m) == 3
+    V = torch.tensor(w.V, device=dev)
+    gv = torch.tensor(w.g_fom[0], device=dev)
+    B = w.B
+    gen = torch.Generator().manual_seed(3)
+    # uniform medium: y = x solves the PDE exactly -> r = 0 (relative to the size of the terms that cancel)
+    a_u = torch.randn(B, 1, generator=gen, dtype=torch.float64).expand(B, w.P).contiguous().to(dev)
+    yx = torch.tensor(fom.mesh.coords[fom.free_dofs, 0], device=dev).expand(B, -1).contiguous()
+    assert plan.residual(a_u, yx, gv, V).abs().max() < 1e-10
+    a = torch.tensor(w.log_image, device=dev)
+    y1 = torch.tensor(w.y, device=dev)
+    y2 = torch.randn(B, w.d, generator=gen, dtype=torch.float64).to(dev)
+    r1 = plan.residual(a, y1, gv, V)
+    # against the generic kernels (matvec + the same contraction) on the same inputs
+    monkeypatch.setenv("GPDE_VO_PATH", "v1")
+    r1_v1, rho_v1 = plan.residual(a, y1, gv, V, want_rho=True)
+    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+    assert rel_err(r1.cpu(), r1_v1.cpu()) < 1e-12
+    assert rel_err((rho_v1 @ V).cpu(), r1.cpu()) < 1e-12       # torch / cuBLAS FP64 as a third opinion
+    # linearity, ragged tail (B % 128 != 0 for the 128-row GEMM tiles), sample independence
+    r2, r12 = plan.residual(a, y2, gv, V), plan.residual(a, y1 + y2, 2 * gv, V)
+    assert rel_err((r1 + r2).cpu(), r12.cpu()) < 1e-12
+    assert torch.equal(plan.residual(a[:131], y1[:131], gv, V), r1[:131])
+    # adjointness with the transposed application
+    s = torch.randn(B, w.m, generator=gen, dtype=torch.float64).to(dev)
+    lhs = (s * plan.residual(a, y2, None, V, ignore_load=True)).sum(dim=1)
+    rhs = (plan.residual_T(a, V, s) * y2).sum(dim=1)
+    assert rel_err(lhs.cpu(), rhs.cpu()) < 1e-11
+
+
+def test_empty_batch_and_single_sample(dev):
+    plan, fom, a, y, g, rng = _grid_case(16, 16, "NDP", 3, 11, dev)
+    T = lambda t: torch.tensor(t, device=dev)
+    V = T(rng.normal(size=(fom.dim_out, 25)))
+    r = plan.residual(T(a[:0]), T(y[:0]), T(g[:0]), V)
+    assert r.shape == (0, 25)
+    r1 = plan.residual(T(a[:1]), T(y[:1]), T(g[:1]), V)
+    assert rel_err(r1.cpu(), plan.residual(T(a), T(y), T(g), V)[:1].cpu()) == 0.0
