@@ -346,9 +346,7 @@ static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, c
             if (sq_input[(size_t)cy * nx + cx] != in0 + cy * sy + cx) return cudaSuccess;
     if ((in0 & 1) || (sy & 1)) return cudaSuccess;
 
-    int nstrips = 1;
-    while (nstrips * 16 < ncol) nstrips *= 2;
-    G.nx = nx; G.ny = ny; G.ncol = ncol; G.nstrips = nstrips; G.groups = kGridWarpsMax / nstrips;
+    G.nx = nx; G.ny = ny; G.ncol = ncol; G.cols = 4; G.nstrips = 0; G.groups = 0;   // decomposition: grid_pick()
     G.in0 = in0; G.sy = sy; G.rh = chs / cvs; G.scale = cvs;
     G.has_load = 0;
     std::vector<double> f_over(d);
@@ -366,21 +364,41 @@ static cudaError_t build_grid_plan(gpde_vo_plan *pl, int n_nodes, int n_cells, c
 // packed V rows.  Returns the stage size in bytes for NT n-tiles (NT = 0: no V in the stage).
 static inline size_t grid_layout(GridDev &G, int R, int NT) {
     const int S = 8 * G.groups;
-    G.a_stride = R * G.nx + 2;
-    G.y_stride = ((R - 1) * G.ncol + 16 * G.nstrips + 4 + 3) & ~3;
+    G.a_stride = std::max(R * G.nx, (R - 1) * G.nx + 4 * G.cols * G.nstrips) + 2;
+    G.y_stride = ((R - 1) * G.ncol + 4 * G.cols * G.nstrips + 4 + 3) & ~3;
     G.a_off = 0;
     G.y_off = S * G.a_stride * 8;
     G.v_off = (G.y_off + S * G.y_stride * 8 + 127) & ~127;
-    return (size_t)G.v_off + (size_t)R * G.nstrips * 4 * NT * 32 * 8;
+    return (size_t)G.v_off + (size_t)R * G.nstrips * G.cols * NT * 32 * 8;
 }
-static inline size_t grid_packed_bytes(const GridDev &G, int NT) { return (size_t)(G.ny + 1) * G.nstrips * 4 * NT * 32 * 8; }
+static inline int grid_nstrips(int ncol, int cols) {
+    int n = 1;
+    while (n * 4 * cols < ncol) n *= 2;
+    return n;
+}
+static inline size_t grid_packed_bytes(const GridDev &G, int NT) {
+    const int per_row = std::max(grid_nstrips(G.ncol, 4) * 4, grid_nstrips(G.ncol, 8) * 8);   // either decomposition
+    return (size_t)(G.ny + 1) * per_row * NT * 32 * 8;
+}
 // rows per stage and ring depth that fit the 227 KB of a CTA: two rows per stage halve the per-row barrier and
 // staging overhead (GPDE_GRID_R forces 1 or 2 for experiments)
+// Decomposition: columns per lane C, warps per CTA W, rows per stage R, ring depth NS.
+//   default     C = 4, W = 16 : 16 warps of 128 registers, one CTA per SM          (cfg 2: 156 us)
+//   GPDE_GRID_W=8 (C = 4)     : 8 warps per CTA, two CTAs per SM, R = 1 only       (cfg 2: 174 us)
+//   GPDE_GRID_C=8 (W = 8)     : 8 fat warps, half the per-step overhead per node   (cfg 2: 176 us)
+// The kernel is latency-bound at 4 warps per scheduler: more resident warps win over less overhead per node
+// (measured on B200, round 1).  R = 2 rows per stage when two stages fit, else 1 (GPDE_GRID_R forces it).
 static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t &stage) {
-    const char *e = getenv("GPDE_GRID_R"), *ew = getenv("GPDE_GRID_W");
-    W = (ew && atoi(ew) == 8 && G.nstrips <= 8) ? 8 : 16;    // 8 warps per CTA = two CTAs per SM (experiment switch)
+    const char *e = getenv("GPDE_GRID_R"), *ew = getenv("GPDE_GRID_W"), *ec = getenv("GPDE_GRID_C");
+    int C = (ec && atoi(ec) == 8) ? 8 : 4;
+    if (grid_nstrips(G.ncol, C) > 8) C = 4;
+    W = (C == 8 || (ew && atoi(ew) == 8)) ? 8 : 16;
+    if (grid_nstrips(G.ncol, C) > W) { C = 4; W = 16; }
+    G.cols = C;
+    G.nstrips = grid_nstrips(G.ncol, C);
     G.groups = W / G.nstrips;
-    const size_t budget = (W == 16 ? 225 * 1024 : 112 * 1024) - 512;
+    const bool two_ctas = (W == 8 && C == 4);
+    const size_t budget = (two_ctas ? 112 * 1024 : 225 * 1024) - 512;
     for (R = (e ? atoi(e) : 2); R >= 1; --R) {
         stage = grid_layout(G, R, NT);
         NS = (int)std::min<size_t>(R == 2 ? 3 : 4, budget / stage);
@@ -426,24 +444,27 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     const int dbg = getenv("GPDE_GRID_DEBUG") ? atoi(getenv("GPDE_GRID_DEBUG")) : 0;   // timing experiments only
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-#define GPDE_LAUNCH_GRID(NTV, RV, WV)                                                                            \
+#define GPDE_LAUNCH_GRID(NTV, RV, WV, CV)                                                                        \
     {                                                                                                            \
-        auto kern = vo_grid_kernel<NTV, false, RV, WV>;                                                          \
+        auto kern = vo_grid_kernel<NTV, false, RV, WV, CV>;                                                      \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, WV * 32, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, m, r, B, NS, (int)stage, dbg); \
     }
-#define GPDE_LAUNCH_GRID_NT(RV, WV)                                                                              \
+#define GPDE_LAUNCH_GRID_NT(RV, WV, CV)                                                                          \
     {                                                                                                            \
-        if (NT == 1) GPDE_LAUNCH_GRID(1, RV, WV)                                                                 \
-        else if (NT == 2) GPDE_LAUNCH_GRID(2, RV, WV)                                                            \
-        else GPDE_LAUNCH_GRID(4, RV, WV)                                                                         \
+        if (NT == 1) GPDE_LAUNCH_GRID(1, RV, WV, CV)                                                             \
+        else if (NT == 2) GPDE_LAUNCH_GRID(2, RV, WV, CV)                                                        \
+        else GPDE_LAUNCH_GRID(4, RV, WV, CV)                                                                     \
     }
-    if (W == 16) {
-        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 16)
-        else GPDE_LAUNCH_GRID_NT(1, 16)
+    if (G.cols == 8) {
+        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8, 8)
+        else GPDE_LAUNCH_GRID_NT(1, 8, 8)
+    } else if (W == 16) {
+        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 16, 4)
+        else GPDE_LAUNCH_GRID_NT(1, 16, 4)
     } else {
-        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8)
-        else GPDE_LAUNCH_GRID_NT(1, 8)
+        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8, 4)
+        else GPDE_LAUNCH_GRID_NT(1, 8, 4)
     }
 #undef GPDE_LAUNCH_GRID_NT
 #undef GPDE_LAUNCH_GRID
@@ -466,16 +487,18 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
     const int S = 8 * G.groups;
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
-#define GPDE_LAUNCH_RHO(RV, WV)                                                                                  \
+#define GPDE_LAUNCH_RHO(RV, WV, CV)                                                                              \
     {                                                                                                            \
-        auto kern = vo_grid_kernel<1, true, RV, WV>;                                                             \
+        auto kern = vo_grid_kernel<1, true, RV, WV, CV>;                                                         \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, WV * 32, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0); \
     }
-    if (W == 16) {
-        if (R == 2) GPDE_LAUNCH_RHO(2, 16) else GPDE_LAUNCH_RHO(1, 16)
+    if (G.cols == 8) {
+        if (R == 2) GPDE_LAUNCH_RHO(2, 8, 8) else GPDE_LAUNCH_RHO(1, 8, 8)
+    } else if (W == 16) {
+        if (R == 2) GPDE_LAUNCH_RHO(2, 16, 4) else GPDE_LAUNCH_RHO(1, 16, 4)
     } else {
-        if (R == 2) GPDE_LAUNCH_RHO(2, 8) else GPDE_LAUNCH_RHO(1, 8)
+        if (R == 2) GPDE_LAUNCH_RHO(2, 8, 4) else GPDE_LAUNCH_RHO(1, 8, 4)
     }
 #undef GPDE_LAUNCH_RHO
     GPDE_CUDA_OK(cudaGetLastError());

@@ -33,8 +33,9 @@ struct GridDev {
     int ok;
     int nx, ny;          // pixels per row, pixel rows; nodes are (nx+1) x (ny+1)
     int ncol;            // free node columns per row (nx - 1)
-    int nstrips;         // strips of 16 columns, rounded up to a power of two (<= 16)
-    int groups;          // sample groups (8 samples each) per CTA = 16 / nstrips
+    int cols;            // node columns per lane (4 or 8); a strip = 4 * cols columns
+    int nstrips;         // strips, rounded up to a power of two (<= 16)
+    int groups;          // sample groups (8 samples each) per CTA = warps / nstrips
     long long in0, sy;   // conductivity entry of pixel (cx, cy) = in0 + cy * sy + cx
     double rh, scale;    // rh = chs / cvs, scale = cvs
     int has_load;
@@ -122,9 +123,10 @@ __device__ __forceinline__ int exp_arg_hi(double x) { return __double2hiint(x) &
 constexpr int kExpHiMax = 0x4085e000;   // high word of 700.0
 
 // V[d,m] row-major -> fragment order.  Vp[row t][strip q][k-step jj][n-tile tt][lane]:
-//   lane = 4 n + kk  holds  V[t*ncol + 16 q + 4 kk + jj][8 tt + n]   (0 outside the matrix)
+//   lane = 4 n + kk  holds  V[t*ncol + 4C q + C kk + jj][8 tt + n]   (0 outside the matrix; C = columns per lane)
 __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int m, int NT, double *__restrict__ Vp) {
-    const int per_row = G.nstrips * 4 * NT * 32;
+    const int C = G.cols;
+    const int per_row = G.nstrips * C * NT * 32;
     const long long total = (long long)(G.ny + 1) * per_row;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -134,8 +136,8 @@ __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int
         rem >>= 5;
         const int tt = rem % NT;
         rem /= NT;
-        const int jj = rem & 3, q = rem >> 2;
-        const int c = 16 * q + 4 * (lane & 3) + jj, col = 8 * tt + (lane >> 2);
+        const int jj = rem % C, q = rem / C;
+        const int c = 4 * C * q + C * (lane & 3) + jj, col = 8 * tt + (lane >> 2);
         Vp[idx] = (c < G.ncol && col < m) ? V[((long long)t * G.ncol + c) * m + col] : 0.0;
     }
 }
@@ -147,8 +149,10 @@ __global__ void vo_grid_pack_kernel(GridDev G, const double *__restrict__ V, int
 //     [R ts - 1, R ts + R - 1) (clipped to the mesh); barrier traffic and staging overhead are per stage.
 // W = warps per CTA: 16 with one CTA per SM, or 8 with two CTAs per SM (two independent rings per SM break the
 //     per-stage lockstep of a single ring).
-template <int NT, bool RHO, int R, int W>
-__global__ void __launch_bounds__(W * 32, W == 16 ? 1 : 2)
+// C = node columns per lane: 4 (16 warps of 120 registers) or 8 (8 warps with twice the work per step: half
+//     the per-step overhead per node, 12.5 % instead of 25 % redundant exp()).
+template <int NT, bool RHO, int R, int W, int C>
+__global__ void __launch_bounds__(W * 32, (W == 16 || C == 8) ? 1 : 2)
 vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
                const double *__restrict__ Vp, int m, double *__restrict__ r, long long B, int NS,
@@ -171,10 +175,10 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     if (b >= B) b = B - 1;                            // duplicates the last sample; never stored
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
     const long long d = (long long)ncol * (ny + 1);
-    const int c0 = 16 * q + 4 * k;
+    const int c0 = 4 * C * q + C * k;
     const int n_steps = ny + 2;                       // node rows 0..ny are produced at steps 1..ny+1
     const int n_stages = (n_steps + R - 1) / R;
-    const int v_row_bytes = G.nstrips * 4 * NT * 32 * 8;
+    const int v_row_bytes = G.nstrips * C * NT * 32 * 8;
     const int row_bytes = ncol * 8, prow_bytes = nx * 8;
 
     if (threadIdx.x == 0) {
@@ -260,41 +264,44 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
     // category of columns c0-1 .. c0+4: 0 shared memory, 1 left Dirichlet value, 2 right one, 3 zero
     int code = 0;
 #pragma unroll
-    for (int p = -1; p <= 4; ++p) {
+    for (int p = -1; p <= C; ++p) {
         const int c = c0 + p;
         const int cat = (c == -1) ? 1 : (c < ncol ? 0 : (c == ncol ? 2 : 3));
         code |= cat << (2 * (p + 1));
     }
     int pixmask = 0, nodemask = 0;
 #pragma unroll
-    for (int j = 0; j < 5; ++j) pixmask |= (c0 + j < nx) ? (1 << j) : 0;
+    for (int j = 0; j <= C; ++j) pixmask |= (c0 + j < nx) ? (1 << j) : 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) nodemask |= (c0 + j < ncol) ? (1 << j) : 0;
+    for (int j = 0; j < C; ++j) nodemask |= (c0 + j < ncol) ? (1 << j) : 0;
     asm volatile("" : "+r"(code), "+r"(pixmask), "+r"(nodemask));   // opaque: keep them live instead of recomputing per step
     const bool edge_lane = code != 0;
     const bool need_gl = (code & 3) == 1;
     bool need_gr = false;
 #pragma unroll
-    for (int p = 0; p <= 5; ++p) need_gr |= ((code >> (2 * p)) & 3) == 2;
+    for (int p = 0; p <= C + 1; ++p) need_gr |= ((code >> (2 * p)) & 3) == 2;
     const double *yb = y + b * d;
     const double *gb = g ? g + b * g_stride : nullptr;
     // the very last element of y cannot be copied in a 16-byte piece when the tensor ends off a 16-byte boundary
-    const int tail_p = ncol - 1 - c0;   // window position (-1..4) of the last free column, if inside
-    const bool tail_lane = y_end_odd && b == B - 1 && tail_p >= -1 && tail_p <= 4;
+    const int tail_p = ncol - 1 - c0;   // window position (-1..C) of the last free column, if inside
+    const bool tail_lane = y_end_odd && b == B - 1 && tail_p >= -1 && tail_p <= C;
     // byte offsets of this lane's first column inside a stage; the 8-byte phase of a stage's first y row
     // alternates from stage to stage when R * ncol is odd
     const int y_lane_off = G.y_off + (sl * G.y_stride + 2 * ((sl >> 1) & 1) + c0) * 8;
     const int a_lane_off = G.a_off + (sl * G.a_stride + c0) * 8;
-    const int v_lane_off = G.v_off + (q * 4 * NT * 32 + lane) * 8;
+    const int v_lane_off = G.v_off + (q * C * NT * 32 + lane) * 8;
     int y_shift = (int)(((unsigned long long)yb) & 15ull);
     const int y_shift_step = ((R * ncol) & 1) * 8;
 
     double acc[NT][2];
 #pragma unroll
     for (int tt = 0; tt < NT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
-    double uc[4] = {0.0, 0.0, 0.0, 0.0}, ulc = 0.0, urc = 0.0;
-    double ap[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-    double fvp[4] = {0.0, 0.0, 0.0, 0.0};
+    constexpr int kPixAll = (1 << (C + 1)) - 1, kNodeAll = (1 << C) - 1;
+    double uc[C], ulc = 0.0, urc = 0.0, ap[C + 1], fvp[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) uc[j] = fvp[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j <= C; ++j) ap[j] = 0.0;
     double gl_next = (need_gl && gb) ? gb[0] : 0.0, gr_next = (need_gr && gb) ? gb[1] : 0.0;
 
     int c_slot = 0;                  // slot of the stage being consumed
@@ -320,7 +327,11 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
             const int t = R * ts + rr;
             if (t >= n_steps || (dbg & 1)) break;
             // ---- new node row t and pixel row t-1
-            double un[4] = {0.0, 0.0, 0.0, 0.0}, unl = 0.0, unr = 0.0, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+            double un[C], unl = 0.0, unr = 0.0, an[C + 1];
+#pragma unroll
+            for (int j = 0; j < C; ++j) un[j] = 0.0;
+#pragma unroll
+            for (int j = 0; j <= C; ++j) an[j] = 0.0;
             if (t <= ny) {
                 const double gl = gl_next, gr = gr_next;
                 if (t < ny && gb) {
@@ -329,15 +340,16 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                 }
                 const double *yr = reinterpret_cast<const double *>(st + y_lane_off + y_shift + rr * row_bytes);
                 unl = yr[-1];
-                un[0] = yr[0]; un[1] = yr[1]; un[2] = yr[2]; un[3] = yr[3];
-                unr = yr[4];
+#pragma unroll
+                for (int j = 0; j < C; ++j) un[j] = yr[j];
+                unr = yr[C];
                 if (tail_lane && t == ny) {
                     const double v = __ldg(yb + d - 1);
                     if (tail_p == -1) unl = v;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < C; ++j)
                         if (tail_p == j) un[j] = v;
-                    if (tail_p == 4) unr = v;
+                    if (tail_p == C) unr = v;
                 }
                 if (edge_lane) {
                     auto pick = [&](int p, double v) {
@@ -345,87 +357,93 @@ vo_grid_kernel(GridDev G, const double *__restrict__ a, long long a_stride, int 
                         return cat == 0 ? v : (cat == 1 ? gl : (cat == 2 ? gr : 0.0));
                     };
                     unl = pick(0, unl);
-                    un[0] = pick(1, un[0]); un[1] = pick(2, un[1]); un[2] = pick(3, un[2]); un[3] = pick(4, un[3]);
-                    unr = pick(5, unr);
+#pragma unroll
+                    for (int j = 0; j < C; ++j) un[j] = pick(j + 1, un[j]);
+                    unr = pick(C + 1, unr);
                 }
             }
             if (t >= 1 && t <= ny) {
                 const int pos = G.sy > 0 ? rr : R - 1 - rr;
                 const double *ar = reinterpret_cast<const double *>(st + a_lane_off + pos * prow_bytes);
-                const double2 p01 = *reinterpret_cast<const double2 *>(ar);
-                const double2 p23 = *reinterpret_cast<const double2 *>(ar + 2);
-                an[0] = p01.x; an[1] = p01.y; an[2] = p23.x; an[3] = p23.y;
-                an[4] = ar[4];
-                if (pixmask != 31) {   // columns past the last pixel hold stale shared memory
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+                for (int j = 0; j < C; j += 2) {
+                    const double2 pp = *reinterpret_cast<const double2 *>(ar + j);
+                    an[j] = pp.x; an[j + 1] = pp.y;
+                }
+                an[C] = ar[C];
+                if (pixmask != kPixAll) {   // columns past the last pixel hold stale shared memory
+#pragma unroll
+                    for (int j = 0; j <= C; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
                 }
                 if (a_is_log) {
-                    const int hmax = max(max(max(exp_arg_hi(an[0]), exp_arg_hi(an[1])), max(exp_arg_hi(an[2]), exp_arg_hi(an[3]))),
-                                         exp_arg_hi(an[4]));
+                    int hmax = exp_arg_hi(an[C]);
+#pragma unroll
+                    for (int j = 0; j < C; ++j) hmax = max(hmax, exp_arg_hi(an[j]));
                     if (hmax <= kExpHiMax) {
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                        for (int j = 0; j <= C; ++j) an[j] = exp_tab16(an[j], tab);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+                        for (int j = 0; j <= C; ++j) an[j] = exp(an[j]);
                     }
                 }
-                if (pixmask != 31) {
+                if (pixmask != kPixAll) {
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
+                    for (int j = 0; j <= C; ++j) an[j] = ((pixmask >> j) & 1) ? an[j] : 0.0;
                 }
             }
 
             // ---- node row t-1: fluxes -> S -> tensor-core contraction with packed V row t-1 (or rho output)
             if (t >= 1) {
-                double fh[5];
+                double fh[C + 1];
                 fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
-                fh[1] = (ap[1] + an[1]) * (uc[1] - uc[0]);
-                fh[2] = (ap[2] + an[2]) * (uc[2] - uc[1]);
-                fh[3] = (ap[3] + an[3]) * (uc[3] - uc[2]);
-                fh[4] = (ap[4] + an[4]) * (urc - uc[3]);
-                double Sv[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 1; j < C; ++j) fh[j] = (ap[j] + an[j]) * (uc[j] - uc[j - 1]);
+                fh[C] = (ap[C] + an[C]) * (urc - uc[C - 1]);
+                double Sv[C];
+#pragma unroll
+                for (int j = 0; j < C; ++j) {
                     const double fv = (an[j] + an[j + 1]) * (un[j] - uc[j]);
                     Sv[j] = fma(G.rh, fh[j + 1] - fh[j], fv - fvp[j]);
                     fvp[j] = fv;
                 }
                 if (G.has_load) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < C; ++j)
                         if ((nodemask >> j) & 1) Sv[j] -= __ldg(G.f_over + (long long)(t - 1) * ncol + c0 + j);
                 }
-                if (nodemask != 15) {
+                if (nodemask != kNodeAll) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
+                    for (int j = 0; j < C; ++j) Sv[j] = ((nodemask >> j) & 1) ? Sv[j] : 0.0;
                 }
                 if constexpr (RHO) {
                     if (b_valid) {
                         double *dst = r + b * (long long)m + (long long)(t - 1) * ncol + c0;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
+                        for (int j = 0; j < C; ++j)
                             if ((nodemask >> j) & 1) dst[j] = G.scale * Sv[j];
                     }
                 } else {
                     const double *vs = reinterpret_cast<const double *>(st + v_lane_off + rr * v_row_bytes);
-                    double bf[4][NT];
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
+                    for (int j0 = 0; j0 < C; j0 += 4) {   // B fragments four k-steps at a time
+                        double bf[4][NT];
 #pragma unroll
-                        for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[(jj * NT + tt) * 32];
+                        for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
-                    for (int jj = 0; jj < 4; ++jj)
+                            for (int tt = 0; tt < NT; ++tt) bf[jj][tt] = vs[((j0 + jj) * NT + tt) * 32];
 #pragma unroll
-                        for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj][tt]);
+                        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                            for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[j0 + jj], bf[jj][tt]);
+                    }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) uc[j] = un[j];
+            for (int j = 0; j < C; ++j) uc[j] = un[j];
             ulc = unl; urc = unr;
 #pragma unroll
-            for (int j = 0; j < 5; ++j) ap[j] = an[j];
+            for (int j = 0; j <= C; ++j) ap[j] = an[j];
         }
         y_shift = (y_shift + y_shift_step) & 15;
         __syncwarp();
