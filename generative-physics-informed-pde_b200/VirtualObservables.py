@@ -645,6 +645,134 @@ class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
             writer.add_scalar('Monitor/Mean_VO_variances', torch.mean(self._mean_vo_variances), global_step=iteration)
 
 
+# ======================================================================================= energy VO
+class EnergyVirtualObservable(BaseVirtualObservable):
+    """Energy-type virtual observable (VirtualObservables.py:672-788): subspace Newton steps on
+    1/2 mu^T A mu - b^T mu with A = diag(prec) + K/T, b = f/T + prec*g,
+        mean <- mean - V (V^T A V)^-1 V^T (A mean - b),   vars = 1 / (prec + diag(K)/T).
+    The reference forms the dense d x d matrix A on the CPU; here K is never formed:
+        A mean - b = prec*(mean - g) + rho(mean)/T      rho = K_ff mean - f_eff   (one residual launch)
+        A V        = prec*V + (K_ff V)/T                K_ff V = residual_T with s = I, shared field
+    and the m x m system is solved on the device.  diag(K) is taken once at construction from the host
+    assembly, like the reference's ``self._querry_point.K.diagonal()`` (:701, setup time)."""
+
+    def __init__(self, querry_point, num_iterations_per_update, stochastic_subspace=None, sampler=None, l=0.1,
+                 dtype=None, device=None):
+        if dtype is None or device is None:
+            raise ValueError('need to provide dtype and device')
+        super().__init__(querry_point, dtype=dtype, device=device)
+        self._stochastic_subspace = stochastic_subspace
+        self._num_iterations_per_update = num_iterations_per_update
+        if sampler is None:
+            if stochastic_subspace is None:
+                raise ValueError
+            sampler = RadialBasisFunctionSampler(self._querry_point, l=l, N_aux=stochastic_subspace)
+        self._sampler = sampler
+        self._temperature = 1
+        self._temperature_schedule = None
+        self._mean = self._vars = None
+        self._forced_temperature = None
+        self._K_diag = _as_f64(self._querry_point.K.diagonal(), self.device)      # setup time (:701)
+        self._plan = VoPlan.cached(self._querry_point.physics, self.device)
+        self._x = _as_f64(self._querry_point.x, self.device)
+        self._g_bc = _as_f64(self._querry_point.dirichlet_values(), self.device)
+        load = self._querry_point.bc.assemble_vanilla_force_vector(self._querry_point.physics.identifier)
+        # the cached plan carries no load vector (zero for both reference factories): keep f_free separately
+        self._load_free = _as_f64(load[self._querry_point.physics.free_dofs], self.device) if np.any(load != 0) else None
+
+    @property
+    def temperature(self):
+        return self._temperature if self._forced_temperature is None else self._forced_temperature
+
+    def force_temperature(self, value):
+        self._forced_temperature = value
+
+    mean = property(lambda self: self._mean)
+    vars = property(lambda self: self._vars)
+    m = property(lambda self: 1)
+
+    def resample(self, ForceResample=False):
+        pass   # nothing to be done (:726-728)
+
+    def set_temperature(self, temperature):
+        assert temperature >= 0
+        self._temperature = temperature
+
+    def set_temperature_schedule(self, type, T_init, T_final, num_steps):
+        assert type.lower() in ['linear', 'exponential']
+        cls = LinearTemperatureSchedule if type.lower() == 'linear' else ExponentialTemperatureSchedule
+        self._temperature_schedule = cls(T_init, T_final, num_steps)
+
+    def set_linear_temperature_schedule(self, T_init=1, T_final=0.0001, num_steps=None):
+        if num_steps is None:
+            raise ValueError
+        self._temperature_schedule = LinearTemperatureSchedule(T_init, T_final, num_steps)
+
+    def update_precision(self, iteration):
+        if self._forced_temperature is not None:
+            return
+        if self._temperature_schedule is None:
+            raise RuntimeError
+        self._temperature = self._temperature_schedule.get_temperature(iteration)
+
+    @torch.no_grad()
+    def update(self, g, prec, iteration, *, ForceUpdate=False):
+        if not ForceUpdate:
+            raise RuntimeError
+        inv_T = 1.0 / self.temperature
+        prec = prec.detach().to(_F64).to(self.device)
+        g = g.detach().to(_F64).to(self.device)
+        self._vars = 1.0 / (prec + inv_T * self._K_diag)
+        if self._mean is None:
+            self._mean = torch.zeros(self.d_y, dtype=_F64, device=self.device)
+        plan, x, gbc = self._plan, self._x, self._g_bc
+        for _ in range(self._num_iterations_per_update):
+            V = _as_f64(self._sampler.sample_V(), self.device)                        # [d, m]
+            m = V.shape[1]
+            eye = torch.eye(m, dtype=_F64, device=self.device)
+            KV = plan.residual_T(x, V, eye)                                            # [m, d], rows (K_ff V e_j)^T
+            M = V.t() @ (prec.unsqueeze(1) * V) + inv_T * (KV @ V)                    # V^T A V (K symmetric)
+            _, rho = plan.residual(x, self._mean.unsqueeze(0), gbc, None)             # rho = K_ff mean - f_eff
+            if self._load_free is not None:
+                rho = rho - self._load_free
+            grad = prec * (self._mean - g) + inv_T * rho[0]                            # A mean - b
+            self._mean = self._mean - V @ torch.linalg.solve(M, V.t() @ grad)
+
+    def __repr__(self):
+        return 'Energy virtual Observable | Current temperature = {}'.format(self._temperature)
+
+
+class EnergyVirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
+    """VirtualObservables.py:1001-1037."""
+
+    def __init__(self, QuerryPointEnsemble, num_iterations_per_update, sampler, dtype, device):
+        vos = [EnergyVirtualObservable(qp, num_iterations_per_update, sampler=sampler, dtype=dtype, device=device)
+               for qp in QuerryPointEnsemble]
+        super().__init__(QuerryPointEnsemble, vos, dtype=dtype, device=device)
+
+    def force_temperature(self, value):
+        for vo in self:
+            vo.force_temperature(value)
+
+    def set_temperature(self, *args, **kwargs):
+        for vo in self:
+            vo.set_temperature(*args, **kwargs)
+
+    def set_temperature_schedule(self, type, **kwargs):
+        for vo in self:
+            vo.set_temperature_schedule(type, **kwargs)
+
+    def set_linear_temperature_schedule(self, *args, **kwargs):
+        for vo in self:
+            vo.set_linear_temperature_schedule(*args, **kwargs)
+
+    def update_vo_precision(self, iteration, writer=None):
+        for vo in self._virtual_observables:
+            vo.update_precision(iteration)
+        if writer is not None:
+            writer.add_scalar('Monitoring/Temperature', self._virtual_observables[0].temperature, global_step=iteration)
+
+
 # ======================================================================================= schedules
 class TemperatureSchedule(object):
     """T(iteration) between T_init and T_final over num_steps (VirtualObservables.py:1040-1091)."""

@@ -132,3 +132,20 @@ class CsrAssembler(object):
                                 shape=self._pattern.shape)
         Kf = K[self._free]
         return Kf[:, self._free], -(Kf[:, self._bc] @ g)
+
+
+def energy_vo_update(K, f, g, prec, mean, V_list, temperature):
+    """EnergyVirtualObservable.update (VirtualObservables.py:769-788), numpy, same order of operations:
+        vars = 1 / (prec + K_diag / T);  A = diag(prec) + K / T;  b = f / T + prec * g
+        for V in V_list:  mean -= V (V^T A V)^-1 V^T (A mean - b)
+    K: scipy sparse [d,d] (free dofs), f, g, prec, mean: [d]; V_list: one [d,m] weighting matrix per iteration.
+    Returns (mean, vars)."""
+    inv_temperature = 1 / temperature
+    vars_ = 1 / (prec + inv_temperature * K.diagonal())
+    A = np.diag(prec) + inv_temperature * K
+    b = inv_temperature * f + prec * g
+    mean = np.array(mean, dtype=np.float64)
+    for V in V_list:
+        M = np.array(V.T @ A @ V)
+        mean = mean - V @ np.linalg.solve(M, V.T @ np.array(A @ mean - b).flatten())
+    return mean, vars_

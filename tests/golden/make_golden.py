@@ -144,16 +144,69 @@ def vo_case(ref, name, nx, refines, N, kind, seed, ell, n_rbf):
     print(name, 'Gamma', out['Gamma'].shape, 'max|r|', np.abs(out['residual']).max())
 
 
+def energy_case(ref, name, nx, refines, N, kind, seed, ell, m_sub, n_it):
+    """EnergyVirtualObservable(sEnsemble) of the reference (VirtualObservables.py:672-788, 1001-1037) run under the
+    shim with a deterministic sampler (a fixed sequence of RBF weighting matrices) and a linear temperature schedule."""
+    VOm = ref['VirtualObservables']
+    P = fem_p1.build_problem(nx, nx, refines)
+    inp = synthetic_inputs(P, N, kind, seed, ell)
+    rng = np.random.RandomState(seed + 200)
+    d = len(P['free_dofs_fom'])
+
+    class BC(object):
+        def __init__(self, g):
+            self.g = g
+
+    def assemble(x, bc):
+        return fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], x, P['bc_dofs_fom'], bc.g,
+                                           P['free_dofs_fom'])
+
+    phys = ref_shim.PhysicsLike(P['bc_dofs_fom'], P['free_dofs_fom'], len(P['cells_fom']), assemble)
+    n_updates = 2
+    V_seq = np.stack([fem_p1.rbf_columns(P['coords_fom'], P['free_dofs_fom'], rng.uniform(size=(m_sub, 2)), 0.25)
+                      for _ in range(n_updates * N * n_it)])            # consumed in call order
+
+    class SequenceSampler(VOm.BaseSampler):
+        calls = 0
+
+        def _sample(self):
+            V = V_seq[SequenceSampler.calls]
+            SequenceSampler.calls += 1
+            return V
+
+    dev = torch.device('cpu')
+    qps = [VOm.QuerryPoint(phys, inp['X_DG'][n], BC(inp['g_fom'][n])) for n in range(N)]
+    qpe = VOm.QuerryPointEnsemble(qps)
+    ens = VOm.EnergyVirtualObservablesEnsemble(qpe, n_it, SequenceSampler(qps[0]), torch.double, dev)
+    ens.set_linear_temperature_schedule(T_init=1.0, T_final=1e-2, num_steps=4)
+    G = rng.normal(size=(n_updates, N, d)) * 0.1 + (P['W'] @ P['coords_rom'][:, 0])[None, None]
+    PREC = rng.uniform(50.0, 200.0, size=(n_updates, N, d))
+    means, varss, temps = [], [], []
+    for it in range(n_updates):
+        ens.update(torch.tensor(G[it]), torch.tensor(PREC[it]), it)
+        means.append(ens.mean.numpy().copy()); varss.append(ens.vars.numpy().copy()); temps.append(ens[0].temperature)
+    np.savez_compressed(os.path.join(OUT, name + '.npz'), nx=nx, refines=refines, kind=kind, n_it=n_it,
+                        in_X_DG=inp['X_DG'], in_g_fom=inp['g_fom'], in_bc_coef=inp['bc_coef'], in_V_seq=V_seq,
+                        in_G=G, in_PREC=PREC, out_mean=np.stack(means), out_vars=np.stack(varss),
+                        out_temperature=np.array(temps))
+    print(name, 'energy VO', np.stack(means).shape, 'T', temps)
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit('reference tree not found; fixtures can only be regenerated in the build container')
     ref = ref_shim.load()
     torch.manual_seed(0)
     np.random.seed(0)
-    rom_case(ref, 'rom_4x4_ndp', 4, 3, 16, 'NDP', 0, 0.15)      # example.ipynb / highres32 shapes
-    rom_case(ref, 'rom_8x8_nd', 8, 2, 8, 'ND', 1, 0.08)         # highres coarse mesh (fine mesh irrelevant here)
-    vo_case(ref, 'vo_4x4_32_ndp', 4, 3, 3, 'NDP', 2, 0.15, n_rbf=5)
-    vo_case(ref, 'vo_2x2_8_nd', 2, 2, 4, 'ND', 3, 0.3, n_rbf=3)
+    only = sys.argv[1] if len(sys.argv) > 1 else None            # regenerate one family: rom | vo | energy
+    if only in (None, 'rom'):
+        rom_case(ref, 'rom_4x4_ndp', 4, 3, 16, 'NDP', 0, 0.15)      # example.ipynb / highres32 shapes
+        rom_case(ref, 'rom_8x8_nd', 8, 2, 8, 'ND', 1, 0.08)         # highres coarse mesh (fine mesh irrelevant here)
+    if only in (None, 'vo'):
+        vo_case(ref, 'vo_4x4_32_ndp', 4, 3, 3, 'NDP', 2, 0.15, n_rbf=5)
+        vo_case(ref, 'vo_2x2_8_nd', 2, 2, 4, 'ND', 3, 0.3, n_rbf=3)
+    if only in (None, 'energy'):
+        energy_case(ref, 'energy_2x2_16_ndp', 2, 3, 3, 'NDP', 5, 0.3, m_sub=6, n_it=3)
 
 
 if __name__ == '__main__':

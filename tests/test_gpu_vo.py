@@ -428,3 +428,34 @@ def test_empty_batch_and_single_sample(dev):
     assert r.shape == (0, 25)
     r1 = plan.residual(T(a[:1]), T(y[:1]), T(g[:1]), V)
     assert rel_err(r1.cpu(), plan.residual(T(a), T(y), T(g), V)[:1].cpu()) == 0.0
+
+
+def test_energy_virtual_observables_against_reference_vectors(dev):
+    """EnergyVirtualObservablesEnsemble mirror (matrix-free subspace Newton on the device) against the reference's
+    own output (tests/golden/energy_2x2_16_ndp.npz): temperature schedule, posterior mean and variances."""
+    from gpde_b200 import VirtualObservables as VO
+    g = load_golden("energy_2x2_16_ndp")
+    ph, bce = _setup(g, dev)
+    fom = ph['fom']
+    N, n_it = g['in_X_DG'].shape[0], int(g['n_it'])
+    qpe = VO.QuerryPointEnsemble.FromArrays(g['in_X_DG'], bce, fom, device=dev)
+
+    class SequenceSampler(VO.BaseSampler):
+        calls = 0
+
+        def _sample(self):
+            V = g['in_V_seq'][SequenceSampler.calls]
+            SequenceSampler.calls += 1
+            return V
+
+    ens = VO.EnergyVirtualObservablesEnsemble(qpe, n_it, SequenceSampler(qpe[0]), torch.double, dev)
+    ens.set_linear_temperature_schedule(T_init=1.0, T_final=1e-2, num_steps=4)
+    with pytest.raises(RuntimeError):
+        ens[0].update(torch.zeros(fom.dim_out), torch.ones(fom.dim_out), 0)          # ForceUpdate is mandatory (:772)
+    for it in range(g['in_G'].shape[0]):
+        ens.update(torch.tensor(g['in_G'][it], device=dev), torch.tensor(g['in_PREC'][it], device=dev), it)
+        assert abs(ens[0].temperature - float(g['out_temperature'][it])) < 1e-15
+        assert rel_err(ens.mean.cpu(), g['out_mean'][it]) < 1e-10
+        assert rel_err(ens.vars.cpu(), g['out_vars'][it]) < 1e-12
+        assert ens.logsigma.shape == (N, fom.dim_out) and ens.m == 1
+    assert SequenceSampler.calls == g['in_V_seq'].shape[0]

@@ -103,3 +103,24 @@ def test_vo_posterior_update_and_precision(name):
     k = np.nonzero(g['in_mask'] < 0)[0]
     for n in range(N):
         assert np.abs(g['out_Gamma'][n][k] @ g['out_mean1'][n] - g['out_alpha'][n][k]).max() < 1e-8
+
+
+def test_energy_vo_restatement_matches_reference():
+    """oracle/vo_ref.energy_vo_update against EnergyVirtualObservablesEnsemble of the reference
+    (tests/golden/energy_2x2_16_ndp.npz, generated by tests/golden/make_golden.py energy)."""
+    from oracle import fem_p1, vo_ref
+    g = load_golden("energy_2x2_16_ndp")
+    P = fem_p1.build_problem(int(g['nx']), int(g['nx']), int(g['refines']))
+    N, n_it = g['in_X_DG'].shape[0], int(g['n_it'])
+    means = [np.zeros(len(P['free_dofs_fom'])) for _ in range(N)]
+    call = 0
+    for it in range(g['in_G'].shape[0]):
+        T = float(g['out_temperature'][it])
+        for n in range(N):
+            K, f = fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], np.exp(g['in_X_DG'][n]), P['bc_dofs_fom'],
+                                               g['in_g_fom'][n], P['free_dofs_fom'])
+            Vs = [g['in_V_seq'][call + i] for i in range(n_it)]
+            call += n_it
+            means[n], vars_ = vo_ref.energy_vo_update(K, f, g['in_G'][it, n], g['in_PREC'][it, n], means[n], Vs, T)
+            assert rel_err(means[n], g['out_mean'][it, n]) < 1e-12
+            assert rel_err(vars_, g['out_vars'][it, n]) < 1e-13
