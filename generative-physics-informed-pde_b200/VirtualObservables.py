@@ -356,8 +356,29 @@ class ConcatenatedSamplers(BaseSampler):
 
 
 class FluxConstrainSampler(BaseSampler):
+    """Wraps a flux-balance constraint object (bottleneck/flux.py:43-158, built with FEniCS facet integrals at
+    setup -- SURVEY.md section 8 row f4, not part of this package): its reduced (Gamma, alpha) are taken as they
+    are, constant, learnable precision (VirtualObservables.py:323-349)."""
+
+    is_constant = True
+
     def __init__(self, qp, FluxConstrain):
-        raise NotImplementedError('flux test functions need FEniCS facet integrals (bottleneck/flux.py)')
+        super().__init__(qp=qp)
+        if not FluxConstrain.initialized:
+            raise RuntimeError('Initialize flux-constrain first')
+        self._Gamma_fc, self._alpha_fc = FluxConstrain.assemble_reduced(np.exp(qp.x), qp.bc)
+
+    m = property(lambda self: int(np.asarray(self._alpha_fc).size))
+    precision_mask = property(lambda self: np.ones(self.m))
+
+    def sample(self):
+        device = self.qp._device
+        if device is None and torch.cuda.is_available():
+            device = torch.device("cuda", torch.cuda.current_device())
+        return _as_f64(self._Gamma_fc, device), _as_f64(self._alpha_fc, device).reshape(-1)
+
+    def _sample(self):
+        raise NotImplementedError
 
 
 # ======================================================================================= linear query

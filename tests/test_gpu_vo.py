@@ -459,3 +459,28 @@ def test_energy_virtual_observables_against_reference_vectors(dev):
         assert rel_err(ens.vars.cpu(), g['out_vars'][it]) < 1e-12
         assert ens.logsigma.shape == (N, fom.dim_out) and ens.m == 1
     assert SequenceSampler.calls == g['in_V_seq'].shape[0]
+
+
+def test_flux_constrain_sampler_wraps_a_setup_time_object(dev):
+    """FluxConstrainSampler (VirtualObservables.py:323-349) takes (Gamma, alpha) from a flux-balance object built at
+    setup; the mirror passes them through as float64 device tensors and concatenates with other samplers' masks."""
+    from gpde_b200 import VirtualObservables as VO
+    plan, fom, a, y, g, rng = _grid_case(8, 8, "NDP", 2, 5, dev)
+    from gpde_b200.physics import BoundaryConditionEnsemble
+    bce = BoundaryConditionEnsemble({'fom': fom, 'rom': fom}, 2, "NDP", rng=rng)
+    qp = VO.QuerryPoint(fom, rng.normal(size=fom.dim_in), bce[0], device=dev)
+
+    class FakeFlux(object):
+        initialized = True
+
+        def assemble_reduced(self, x, bc):
+            assert np.all(x > 0)
+            return rng.normal(size=(3, fom.dim_out)), rng.normal(size=3)
+
+    s = VO.FluxConstrainSampler(qp, FakeFlux())
+    Gam, alp = s.sample()
+    assert s.m == 3 and s.is_constant and np.all(s.precision_mask == 1) and not s.fixed_precision
+    assert Gam.dtype == torch.double and Gam.device.type == "cuda" and Gam.shape == (3, fom.dim_out) and alp.shape == (3,)
+    FakeFlux.initialized = False
+    with pytest.raises(RuntimeError):
+        VO.FluxConstrainSampler(qp, FakeFlux())
