@@ -63,6 +63,16 @@ namespace gpde {
 constexpr int kRomThreads = 128;
 
 __device__ __forceinline__ double ld_as_double(const double *p) { return *p; }
+
+// 1/d for a positive, finite pivot: hardware seed + two Newton steps (<= 1 ulp; the IEEE division sequence is
+// ~4x the instructions and sits on the critical path of every elimination step)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(r, fma(-d, r, 1.0), r);
+    r = fma(r, fma(-d, r, 1.0), r);
+    return r;
+}
 __device__ __forceinline__ double ld_as_double(const float *p) { return (double)*p; }
 
 // ---------------------------------------------------------------------------------------------
@@ -106,7 +116,7 @@ __device__ __forceinline__ int factor_band(const RomDev &P, int gl, double *Ab, 
     for (int k = 0; k < nf; ++k) {
         const double d = Ab[k * bw1];
         if (!(d > 0.0)) bad = GPDE_INFO_NOT_SPD;
-        const double invd = 1.0 / d;
+        const double invd = fast_rcp(d);
         const int wlen = min(hbw, nf - 1 - k);
         const int npairs = (wlen * (wlen + 1)) >> 1;
         for (int q = gl; q < npairs; q += G) {
@@ -229,10 +239,10 @@ rom_forward_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__
         for (int i = gl; i < P.n; i += G) u[b * P.n + i] = (T)Fs[i];
         if (factor) {
             double *fb = factor + b * (long long)P.n_band;
-            for (int p = gl; p < P.n_band; p += G) {
-                const int k = p / P.bw1;
-                fb[p] = (p - k * P.bw1 == 0) ? dinv[k] : Ab[p];
-            }
+            // band entries as they are; the diagonal slots then receive 1/d_k (no index divisions)
+            for (int p = gl; p < P.n_band; p += G) fb[p] = Ab[p];
+            __syncwarp();
+            for (int k = gl; k < P.n_free; k += G) fb[k * P.bw1] = dinv[k];
         }
         if (bad && info) atomicOr(info, bad);
     }
@@ -274,12 +284,8 @@ rom_adjoint_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__
     }
     if (factor) {
         const double *fb = factor + b * (long long)P.n_band;
-        for (int p = gl; p < P.n_band; p += G) {
-            const double v = fb[p];
-            const int k = p / P.bw1;
-            Ab[p] = v;
-            if (p - k * P.bw1 == 0) dinv[k] = v;
-        }
+        for (int p = gl; p < P.n_band; p += G) Ab[p] = fb[p];
+        for (int k = gl; k < P.n_free; k += G) dinv[k] = fb[k * P.bw1];
     }
     __syncwarp();
     if (!factor) {
