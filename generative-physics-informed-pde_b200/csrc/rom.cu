@@ -52,6 +52,7 @@ struct RomDev {
 struct gpde_rom_plan {
     gpde::RomDev dev;
     int device;
+    int tps;                // 1: thread-per-sample kernels (rom_tps.cuh) serve this plan; fixes the factor layout
     int lanes;              // G
     int n_contrib;
     size_t smem_fwd, smem_adj;  // bytes per sample
@@ -319,6 +320,10 @@ rom_adjoint_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__
     }
 }
 
+}  // namespace gpde
+#include "rom_tps.cuh"
+namespace gpde {
+
 // ---------------------------------------------------------------------------------------------
 // GetStiffness: K[n,n,B] (batch last, ROM.py:93), Dirichlet rows -> identity rows (:97-98)
 // ---------------------------------------------------------------------------------------------
@@ -388,6 +393,14 @@ static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     if (!X || !F || !u) return fail(GPDE_ERR_ARG, "rom_forward: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->tps) {
+        auto kern = pl->dev.hbw == 3 ? rom_tps_forward_kernel<T, 15, 3> : rom_tps_forward_kernel<T, 15, 4>;
+        const size_t smem = tps_smem_forward(pl->dev);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, F, u, factor, info, B);
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
     switch (pl->lanes) {
         case 8: return launch_forward<T, 8>(pl, X, x_is_log, F, u, factor, info, B, st);
         case 16: return launch_forward<T, 16>(pl, X, x_is_log, F, u, factor, info, B, st);
@@ -403,6 +416,14 @@ static int rom_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     if (!X || !u || !gbar || !gradX) return fail(GPDE_ERR_ARG, "rom_adjoint: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->tps) {
+        auto kern = pl->dev.hbw == 3 ? rom_tps_adjoint_kernel<T, 15, 3> : rom_tps_adjoint_kernel<T, 15, 4>;
+        const size_t smem = tps_smem_adjoint(pl->dev);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, u, factor, gbar, gradX, gradF, B);
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
     switch (pl->lanes) {
         case 8: return launch_adjoint<T, 8>(pl, X, x_is_log, u, factor, gbar, gradX, gradF, B, st);
         case 16: return launch_adjoint<T, 16>(pl, X, x_is_log, u, factor, gbar, gradX, gradF, B, st);
@@ -583,6 +604,15 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
     const int pairs = D.n_pairs;
     pl->lanes = pairs <= 8 ? 8 : (pairs <= 16 ? 16 : 32);
     pl->n_contrib = (int)band_elem.size();
+    // thread-per-sample kernels (rom_tps.cuh): instantiated for the reference's 4x4 coarse mesh (15 free dofs, half
+    // bandwidth 3 in this package's x-fastest numbering, 4 allowed for other numberings).  MEASURED SLOWER than the
+    // cooperative kernels on B200 (B = 4096: 51 + 39 us vs 18.5 + 15.3 us, only 32 CTAs; B = 131072: 248 M vs
+    // 415 M solves/s, 8 resident warps per SM of serial FP64 chains), so they are opt-in: GPDE_ROM_PATH=tps.
+    // Decided once per plan: it fixes the factor layout.
+    {
+        const char *e = getenv("GPDE_ROM_PATH");
+        pl->tps = (nf == 15 && (hbw == 3 || hbw == 4) && tps_smem_adjoint(D) <= 227 * 1024 && e && strcmp(e, "tps") == 0) ? 1 : 0;
+    }
     pl->smem_fwd = sizeof(double) * (size_t)(E + n + n_band + 3 * nf);
     pl->smem_adj = sizeof(double) * (size_t)(2 * E + 2 * n + n_band + 4 * nf);
     const size_t groups = (kRomThreads / 32) * (32 / pl->lanes);
@@ -606,7 +636,7 @@ int gpde_rom_plan_destroy(gpde_rom_plan *pl) {
 int gpde_rom_plan_info(const gpde_rom_plan *pl, int64_t out[8]) {
     if (!pl || !out) return fail(GPDE_ERR_ARG, "rom_plan_info: null");
     out[0] = pl->dev.n; out[1] = pl->dev.E; out[2] = pl->dev.n_free; out[3] = pl->dev.hbw;
-    out[4] = pl->dev.n_band; out[5] = pl->n_contrib; out[6] = pl->lanes; out[7] = pl->device;
+    out[4] = pl->dev.n_band; out[5] = pl->n_contrib; out[6] = pl->tps ? 1 : pl->lanes; out[7] = pl->device;
     return GPDE_OK;
 }
 

@@ -61,7 +61,7 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M_hos
 int gpde_rom_plan_destroy(gpde_rom_plan *plan);
 
 /* out[0]=n, [1]=E, [2]=n_free, [3]=half bandwidth, [4]=factor doubles per sample,
- * [5]=assembly contributions, [6]=lanes per sample, [7]=device */
+ * [5]=assembly contributions, [6]=lanes per sample (1 = thread-per-sample kernels), [7]=device */
 int gpde_rom_plan_info(const gpde_rom_plan *plan, int64_t out[8]);
 
 /* bytes of factor stash needed for a batch of B samples (always doubles) */

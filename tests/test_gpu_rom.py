@@ -236,3 +236,45 @@ def test_large_batch_config4_shard(dev):
     K = op.rom.GetStiffness(torch.exp(lx.detach()) + 1e-8, DirichletBC=True)          # [n,n,7]
     res = torch.einsum('ijb,bj->bi', K, us.detach()) - F[idx]
     assert res.abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
+@pytest.mark.parametrize("ptype", ["ND", "NDP"])
+def test_thread_per_sample_kernels_match_cooperative_kernels(dtype, ptype, dev, monkeypatch):
+    """4x4 coarse mesh: the opt-in thread-per-sample kernels (rom_tps.cuh, GPDE_ROM_PATH=tps) and the default
+    cooperative kernels on the same inputs: u, dL/dlogX, dL/dF, with and without the stashed factor,
+    conductivity and log-conductivity input, ragged batch (B % 128 != 0)."""
+    from gpde_b200 import ROM as rom_mod
+    from gpde_b200.ROM import ROM
+    from gpde_b200.workloads import Workload
+    w = Workload("cfg1", B=333, seed=9, ptype=ptype)
+    tol = 1e-12 if dtype == torch.float64 else 2e-6
+    X = torch.tensor(w.logX, dtype=dtype, device=dev)
+    F = torch.tensor(w.F, dtype=dtype, device=dev)
+    gbar = torch.tensor(w.gbar_u, dtype=dtype, device=dev)
+    out = {}
+    for path in ("tps", "coop"):
+        if path == "tps":
+            monkeypatch.setenv("GPDE_ROM_PATH", "tps")
+        else:
+            monkeypatch.delenv("GPDE_ROM_PATH", raising=False)
+        rom = ROM.FromPhysics(w.physics['rom'], dtype=dtype, device=dev)
+        plan = rom._get_plan()
+        assert plan.lanes == (1 if path == "tps" else 8) and plan.half_bandwidth == 3 and plan.n_free == 15
+        res = []
+        for x_is_log, Xin in ((True, X), (False, torch.exp(X))):
+            u, factor = rom_mod._launch_forward(plan, Xin, F, x_is_log, want_factor=True, info=rom._info_word(dev))
+            gX, gF = rom_mod._launch_adjoint(plan, Xin, u, factor, gbar, x_is_log, want_gradF=True)
+            gX2, _ = rom_mod._launch_adjoint(plan, Xin, u, None, gbar, x_is_log, want_gradF=False)   # factor recomputed
+            res += [u, gX, gF, gX2]
+        rom.check()
+        out[path] = res
+    monkeypatch.delenv("GPDE_ROM_PATH", raising=False)
+    for a, b in zip(out["tps"], out["coop"]):
+        assert rel_err(a.cpu(), b.cpu()) < tol
+    # error flag: a non-positive conductivity raises like the reference (ROM.py:74-76) on the default path too
+    rom = ROM.FromPhysics(w.physics['rom'], dtype=dtype, device=dev)
+    bad = torch.exp(X).clone()
+    bad[200, 3] = 0.0
+    with pytest.raises(ValueError):
+        rom(bad, F)
