@@ -41,15 +41,31 @@ def is_stale():
 
 
 def build_library(force=False, verbose=False):
+    """Compiles the translation units in parallel (one nvcc -c each), then links the shared library."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
+    obj_dir = os.path.join(HERE, "build")
+    os.makedirs(obj_dir, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+    jobs = []
+    for src in SOURCES:
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + compile_flags + ["-c", "-o", obj, os.path.join(CSRC, src)]
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for cmd, obj, proc in jobs:
+        out, _ = proc.communicate()
+        if verbose or proc.returncode != 0:
+            sys.stderr.write(out)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed (%d): %s" % (proc.returncode, " ".join(cmd)))
+        objs.append(obj)
+    cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
+        raise RuntimeError("nvcc link failed (%d): %s" % (res.returncode, " ".join(cmd)))
     return LIB
 
 

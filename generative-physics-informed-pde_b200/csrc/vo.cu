@@ -377,28 +377,27 @@ static inline int grid_nstrips(int ncol, int cols) {
     return n;
 }
 static inline size_t grid_packed_bytes(const GridDev &G, int NT) {
-    const int per_row = std::max(grid_nstrips(G.ncol, 4) * 4, grid_nstrips(G.ncol, 8) * 8);   // either decomposition
-    return (size_t)(G.ny + 1) * per_row * NT * 32 * 8;
+    return (size_t)(G.ny + 1) * grid_nstrips(G.ncol, 4) * 4 * NT * 32 * 8;
 }
 // rows per stage and ring depth that fit the 227 KB of a CTA: two rows per stage halve the per-row barrier and
 // staging overhead (GPDE_GRID_R forces 1 or 2 for experiments)
-// Decomposition: columns per lane C, warps per CTA W, rows per stage R, ring depth NS.
-//   default     C = 4, W = 16 : 16 warps of 128 registers, one CTA per SM          (cfg 2: 156 us)
-//   GPDE_GRID_W=8 (C = 4)     : 8 warps per CTA, two CTAs per SM, R = 1 only       (cfg 2: 174 us)
-//   GPDE_GRID_C=8 (W = 8)     : 8 fat warps, half the per-step overhead per node   (cfg 2: 176 us)
-// The kernel is latency-bound at 4 warps per scheduler: more resident warps win over less overhead per node
-// (measured on B200, round 1).  R = 2 rows per stage when two stages fit, else 1 (GPDE_GRID_R forces it).
+// Decomposition: columns per lane C, warps per CTA W, rows per stage R, ring depth NS.  The kernel is templated on
+// all of them; measured on B200 at cfg 2 (round 1):
+//     C = 4, W = 16, R = 2 : 156 us   <- instantiated (16 warps of 128 registers, one CTA per SM)
+//     C = 4, W = 16, R = 1 : 186 us   <- instantiated (used when two 2-row stages do not fit)
+//     C = 4, W =  8, R = 1 : 174 us   (8 warps per CTA, two CTAs per SM)
+//     C = 8, W =  8, R = 2 : 176 us   (8 fat warps, half the per-step overhead per node)
+// The kernel is latency-bound at 4 warps per scheduler: more resident warps win over less overhead per node.
+// GPDE_GRID_R=1 forces one row per stage (A/B runs).
 static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t &stage) {
-    const char *e = getenv("GPDE_GRID_R"), *ew = getenv("GPDE_GRID_W"), *ec = getenv("GPDE_GRID_C");
-    int C = (ec && atoi(ec) == 8) ? 8 : 4;
-    if (grid_nstrips(G.ncol, C) > 8) C = 4;
-    W = (C == 8 || (ew && atoi(ew) == 8)) ? 8 : 16;
-    if (grid_nstrips(G.ncol, C) > W) { C = 4; W = 16; }
+    const char *e = getenv("GPDE_GRID_R");
+    const int C = 4;
+    W = 16;
+    if (grid_nstrips(G.ncol, C) > W) return false;
     G.cols = C;
     G.nstrips = grid_nstrips(G.ncol, C);
     G.groups = W / G.nstrips;
-    const bool two_ctas = (W == 8 && C == 4);
-    const size_t budget = (two_ctas ? 112 * 1024 : 225 * 1024) - 512;
+    const size_t budget = 225 * 1024 - 512;
     for (R = (e ? atoi(e) : 2); R >= 1; --R) {
         stage = grid_layout(G, R, NT);
         NS = (int)std::min<size_t>(R == 2 ? 3 : 4, budget / stage);
@@ -456,16 +455,8 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
         else if (NT == 2) GPDE_LAUNCH_GRID(2, RV, WV, CV)                                                        \
         else GPDE_LAUNCH_GRID(4, RV, WV, CV)                                                                     \
     }
-    if (G.cols == 8) {
-        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8, 8)
-        else GPDE_LAUNCH_GRID_NT(1, 8, 8)
-    } else if (W == 16) {
-        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 16, 4)
-        else GPDE_LAUNCH_GRID_NT(1, 16, 4)
-    } else {
-        if (R == 2) GPDE_LAUNCH_GRID_NT(2, 8, 4)
-        else GPDE_LAUNCH_GRID_NT(1, 8, 4)
-    }
+    if (R == 2) GPDE_LAUNCH_GRID_NT(2, 16, 4)
+    else GPDE_LAUNCH_GRID_NT(1, 16, 4)
 #undef GPDE_LAUNCH_GRID_NT
 #undef GPDE_LAUNCH_GRID
     GPDE_CUDA_OK(cudaGetLastError());
@@ -493,13 +484,7 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         kern<<<grid, WV * 32, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, nullptr, pitch, rho, B, NS, (int)stage, 0); \
     }
-    if (G.cols == 8) {
-        if (R == 2) GPDE_LAUNCH_RHO(2, 8, 8) else GPDE_LAUNCH_RHO(1, 8, 8)
-    } else if (W == 16) {
-        if (R == 2) GPDE_LAUNCH_RHO(2, 16, 4) else GPDE_LAUNCH_RHO(1, 16, 4)
-    } else {
-        if (R == 2) GPDE_LAUNCH_RHO(2, 8, 4) else GPDE_LAUNCH_RHO(1, 8, 4)
-    }
+    if (R == 2) GPDE_LAUNCH_RHO(2, 16, 4) else GPDE_LAUNCH_RHO(1, 16, 4)
 #undef GPDE_LAUNCH_RHO
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
