@@ -6,8 +6,12 @@
 // incident cells ("row-cell ELL", slot-major so that consecutive rows read consecutive words):
 //   rho_i = sum_slots a[in] * (c0 * u_i + c1 * u~[j1] + c2 * u~[j2]) - f_i
 //
-// Version 1 (round 1, first measured path): a matvec kernel (one CTA owns S samples, conductivities
-// staged in shared memory with exp() applied once) + a tiled FP64 contraction kernel.
+// Kernel families, chosen per call (gpde_vo_plan_kernel_path):
+//   vo_grid.cuh   structured pixel grid (verified at plan creation), FP64 I/O: marching flux-form kernel with the
+//                 contraction on the FP64 tensor pipe inside the kernel (m <= 32), or producing rho for ...
+//   vo_gemm.cuh   ... the FP64 tensor-core contraction rho[B,d] V[d,m] for many weighting functions (m > 32);
+//   vo_fused.cuh  any P1 diffusion mesh, m <= 32: edge-form matvec + ring-staged tiles + DMMA contraction;
+//   version 1     (below) any mesh, any m, FP32/FP64: row-cell ELL matvec, then vo_gemm.cuh.
 #include "common.cuh"
 
 #include <algorithm>

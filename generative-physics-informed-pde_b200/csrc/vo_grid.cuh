@@ -12,9 +12,9 @@
 //
 // Work decomposition (FP64 pipe and HBM are co-limiting at m = 25):
 //   * a CTA of 16 warps owns S = 8*groups samples and marches over the node rows bottom to top;
-//   * row t of y, pixel row t-1 of a (all S samples) and row t-1 of the fragment-packed V form one
+//   * R node rows of y, R pixel rows of a (all S samples) and R rows of the fragment-packed V form one
 //     pipeline stage, brought into shared memory NS-1 stages ahead: a / y rows by 16-byte cp.async shared
-//     out over all threads, the packed V row by one bulk copy (cp.async.bulk); both complete on the
+//     out over all warps, the packed V rows by one bulk copy (cp.async.bulk); both complete on the
 //     stage's mbarrier.  Every input byte crosses HBM once, nothing waits on a global load;
 //   * warp (group, strip): 8 samples x 16 node columns; lane (s = lane/4, k = lane%4) owns the 4
 //     columns 16*strip + 4k .. +3 of sample s and keeps the row below (u, conductivities, vertical
