@@ -611,6 +611,32 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     if (!a || !V || !s || !q || !workspace) return fail(GPDE_ERR_ARG, "vo_residual_T: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if constexpr (sizeof(T) == 8) {
+        // structured pixel grid: w = s V^T on the FP64 tensor pipe, then q = K_ff w with the marching kernel
+        // (rho of u~ = (w, 0) without the load vector IS K_ff w)
+        if (use_grid(pl) && !((uintptr_t)a & 15) && !(a_stride & 1) && !((uintptr_t)workspace & 15)) {
+            const int d = pl->dev.d, mp = gemm_dp(m), bn = 128, ldb = (d + bn - 1) / bn * bn;
+            double *Sp = (double *)workspace, *Vt = Sp + (size_t)B * mp, *w = Vt + (size_t)mp * ldb;
+            {
+                const long long total = (long long)B * mp;
+                const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 8);
+                vo_gemm_pad_rows_kernel<<<grid, 256, 0, st>>>((const double *)s, (long long)B, m, Sp, mp);
+                vo_gemm_pack_transposed_kernel<<<dim3((unsigned)(ldb / 32), (unsigned)((mp + 31) / 32)), dim3(32, 8), 0, st>>>(
+                    (const double *)V, d, m, Vt, mp, ldb);
+            }
+            {
+                auto kern = vo_gemm_kernel<128, double>;
+                const size_t smem = gemm_smem(bn);
+                GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
+                kern<<<grid, kGemmThreads, smem, st>>>(Sp, mp, Vt, ldb, w, d, (long long)B);
+                GPDE_CUDA_OK(cudaGetLastError());
+            }
+            const int rc = launch_grid_rho(pl, (const double *)a, (long long)a_stride, a_is_log, w, nullptr, 0, (double *)q, d,
+                                           0, (long long)B, st);
+            if (rc != 0) return rc < 0 ? rc : GPDE_OK;
+        }
+    }
     if (use_fused(pl) && sizeof(double) * kFS * (size_t)m <= sizeof(double) * kFS * kRhoPitch) {
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
         const size_t smem = pl->fused_smem;   // the coefficient vectors live in the (unused) rho tile
@@ -743,6 +769,10 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
     // version-1 kernels: K-padded rho [B][dp] + padded V [dp][ldb] (residual), V s [B][d] (residual_T)
     const size_t dp = (size_t)gemm_dp(pl->dev.d);
     size_t need = sizeof(double) * (dp * (size_t)B + dp * (size_t)gemm_ldb(std::max(m, 1)));
+    if (pl->grid.ok && m > 0) {   // residual_T on the grid path: padded s [B][mp], V^T [mp][ldb], w [B][d]
+        const size_t mp = (size_t)gemm_dp(m), ldb = ((size_t)pl->dev.d + 127) / 128 * 128;
+        need = std::max(need, sizeof(double) * ((size_t)B * mp + mp * ldb + (size_t)B * pl->dev.d));
+    }
     if (pl->grid.ok && m > 0 && m <= 32) need = std::max(need, grid_packed_bytes(pl->grid, 4));   // packed V
     return need;
 }

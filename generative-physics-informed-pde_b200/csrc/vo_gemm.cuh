@@ -47,6 +47,33 @@ __global__ void vo_gemm_pack_kernel_t(const T *__restrict__ V, int d, int m, dou
     }
 }
 
+// Operands of the transposed application  w[B,d] = s[B,m] V^T  on the same kernel:
+//   Sp[B][mp] <- s[B][m] (K padded to 16 with zeros),  Vt[mp][ldb] <- V^T (rows k < m, columns n < d, zero padded)
+__global__ void vo_gemm_pad_rows_kernel(const double *__restrict__ s, long long B, int m, double *__restrict__ Sp, int mp) {
+    const long long total = B * mp;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / mp;
+        const int k = (int)(idx - b * mp);
+        Sp[idx] = k < m ? s[b * m + k] : 0.0;
+    }
+}
+__global__ void vo_gemm_pack_transposed_kernel(const double *__restrict__ V, int d, int m, double *__restrict__ Vt, int mp,
+                                               int ldb) {
+    // 32 x 32 tiles through shared memory: coalesced reads of V rows, coalesced writes of Vt rows
+    __shared__ double tile[32][33];
+    const int n0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int n = n0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (n < d && k < m) ? V[(long long)n * m + k] : 0.0;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, n = n0 + threadIdx.x;
+        if (k < mp && n < ldb) Vt[(long long)k * ldb + n] = tile[threadIdx.x][r];
+    }
+}
+
 template <int BN, typename To>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ Vp, int ldb, To *__restrict__ R, int m,

@@ -347,6 +347,18 @@ def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
             r_v1 = plan.residual(aa, yy, gg, V, **kw)
             monkeypatch.delenv("GPDE_VO_PATH", raising=False)
             assert rel_err(r_grid.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
+    # transposed application q = K_ff (V s): tensor-core expansion + marching kernel against the generic kernels
+    for m in (1, 25, 70):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        sv = T(rng.normal(size=(B, m)))
+        for kw in (dict(a=T(a)), dict(a=T(a[0])), dict(a=T(np.exp(a)), a_is_log=False)):
+            aa = kw.pop('a')
+            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            q_grid = plan.residual_T(aa, V, sv, **kw)
+            monkeypatch.setenv("GPDE_VO_PATH", "v1")
+            q_v1 = plan.residual_T(aa, V, sv, **kw)
+            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            assert rel_err(q_grid.cpu(), q_v1.cpu()) < 1e-12, (m, sorted(kw))
     # unaligned views (odd storage offsets) are served by the generic kernels, same numbers
     V = T(rng.normal(size=(fom.dim_out, 25)))
     big = torch.zeros(B * fom.dim_out + 1, dtype=torch.float64, device=dev)
