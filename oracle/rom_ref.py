@@ -5,7 +5,7 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline leg
 import this module.
 
 Pinned against the reference itself: tests/golden/make_golden.py imports
-/root/reference/bottleneck/ROM.py + components.py under stub ``dolfin`` (oracle/ref_shim.py)
+the reference tree's bottleneck/ROM.py + components.py under stub ``dolfin`` (oracle/ref_shim.py)
 and stores its outputs; tests/test_oracle_golden.py checks this restatement against them.
 The constants fed to it (M, W, dof sets) come from oracle/fem_p1.py, whose FEniCS
 boundary is "parity unpinned" (see its header).
