@@ -304,10 +304,20 @@ class RadialBasisFunctionSampler(BaseSampler):
         super().__init__(qp)
         assert l is not None
         self._rows, self._l, self.m = qp.bc.free_dofs('fom'), l, N_aux
+        self._xy_dev = None
 
     def _sample(self):
+        # centres from numpy's global stream, in the reference's order (VirtualObservables.py:184-190) ...
         centres = np.array([[np.random.uniform(), np.random.uniform()] for _ in range(self.m)])
-        return fem.rbf_weighting(self.qp.physics.mesh, self._rows, centres, self._l)
+        device = self.qp._device
+        if device is None or torch.device(device).type != "cuda":
+            return fem.rbf_weighting(self.qp.physics.mesh, self._rows, centres, self._l)
+        # ... evaluated at the fine free nodes on the device (resample() runs at every VO update)
+        if self._xy_dev is None:
+            self._xy_dev = _as_f64(self.qp.physics.mesh.coords[self._rows], device)
+        c = _as_f64(centres, device)
+        d2 = (self._xy_dev[:, None, :] - c[None, :, :]).pow(2).sum(-1)
+        return torch.exp(-d2 / self._l ** 2)
 
 
 class GaussianSketchingSampler(BaseSampler):
@@ -352,7 +362,11 @@ class ConcatenatedSamplers(BaseSampler):
     precision_mask = property(lambda self: np.concatenate([s.precision_mask for s in self._samplers]))
 
     def _sample(self):
-        return np.hstack([s.sample_V() for s in self._samplers])
+        parts = [s.sample_V() for s in self._samplers]
+        if any(isinstance(p, torch.Tensor) for p in parts):
+            dev = next(p.device for p in parts if isinstance(p, torch.Tensor))
+            return torch.cat([_as_f64(p, dev) for p in parts], dim=1)
+        return np.hstack(parts)
 
 
 class FluxConstrainSampler(BaseSampler):

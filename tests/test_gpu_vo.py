@@ -496,3 +496,26 @@ def test_flux_constrain_sampler_wraps_a_setup_time_object(dev):
     FakeFlux.initialized = False
     with pytest.raises(RuntimeError):
         VO.FluxConstrainSampler(qp, FakeFlux())
+
+
+def test_rbf_sampler_on_device_matches_host_evaluation(dev):
+    """RadialBasisFunctionSampler: centres from numpy's stream in the reference's order, evaluation on the device
+    (query points that live on a CUDA device) against the host evaluation (query points without a device)."""
+    from gpde_b200 import VirtualObservables as VO
+    g = load_golden("vo_2x2_8_nd")
+    ph, bce = _setup(g, dev)
+    qp_dev = VO.QuerryPoint(ph['fom'], g['in_X_DG'][0], bce[0], device=dev)
+    qp_host = VO.QuerryPoint(ph['fom'], g['in_X_DG'][0], bce[0])
+    np.random.seed(11)
+    V_dev = VO.RadialBasisFunctionSampler(qp_dev, 0.2, 4).sample_V()
+    np.random.seed(11)
+    V_host = VO.RadialBasisFunctionSampler(qp_host, 0.2, 4).sample_V()
+    assert isinstance(V_dev, torch.Tensor) and V_dev.device.type == "cuda" and isinstance(V_host, np.ndarray)
+    assert rel_err(V_dev.cpu(), V_host) < 1e-14
+    # concatenation with a host-side sampler ends up on the device
+    np.random.seed(3)
+    cat = VO.ConcatenatedSamplers([VO.GaussianSketchingSampler(qp_dev, 2), VO.RadialBasisFunctionSampler(qp_dev, 0.2, 3)])
+    Vc = cat.sample_V()
+    assert isinstance(Vc, torch.Tensor) and Vc.shape == (ph['fom'].dim_out, 5) and cat.m == 5
+    Gam, alp = cat.sample()
+    assert Gam.shape == (5, ph['fom'].dim_out) and alp.shape == (5,)
