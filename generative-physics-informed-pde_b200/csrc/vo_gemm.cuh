@@ -12,6 +12,8 @@
 // CTA tile 128 samples x BN columns, 8 warps as 4 (M) x 2 (N), warp tile 32 x BN/2 => 4 x BN/16 DMMA tiles
 // whose accumulators stay in registers; K in chunks of 16 through a 4-stage cp.async ring.  Shared-memory row
 // pitches are = 4 (mod 16) doubles, which makes both fragment loads conflict-free.
+// (A 112-row tile on 7 warps, tried against the 256-tiles-on-148-SMs tail of config 3, is no faster: the FP64
+// tensor pipe is per scheduler, and 7 warps leave one scheduler with half the work -- measured, round 1.)
 #pragma once
 
 namespace gpde {
