@@ -95,7 +95,9 @@ def run_reference(args):
         return
     import gpde_b200  # noqa: F401
     from gpde_b200.workloads import Workload
-    w = Workload(args.workload, B=args.batch, seed=0)
+    from gpde_b200.workloads import CONFIGS
+    # bounded sample: the CPU arm never builds more than 4096 samples of the workload (cfg4 has 131072)
+    w = Workload(args.workload, B=min(int(args.batch or CONFIGS[args.workload]["B"]), 4096), seed=0)
     sample = 64 if w.d <= 4095 else 8
     ref = CpuReference(w, sample)
     for _ in range(min(args.warmup, 2)):
@@ -215,8 +217,17 @@ def run_b200(args):
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     s = 8 if args.dtype == "f64" else 4
 
-    # per-GPU shard of the sample-sharded batch (weak scaling: every rank owns a full workload batch)
-    w = Workload(args.workload, B=args.batch, seed=rank)
+    # per-GPU shard of the sample-sharded batch.  Default: weak scaling, every rank owns a full workload batch.
+    # cfg4 (BASELINE config 4): ONE batch of 131072 cut into contiguous shards (gpde_b200.sharding), strong scaling.
+    from gpde_b200.sharding import shard_range
+    strong = args.workload == "cfg4"
+    if strong:
+        from gpde_b200.workloads import CONFIGS
+        total = int(args.batch if args.batch is not None else CONFIGS["cfg4"]["B"])
+        lo, hi = shard_range(total, rank, world)
+        w = Workload(args.workload, B=hi - lo, seed=rank)
+    else:
+        w = Workload(args.workload, B=args.batch, seed=rank)
     B = w.B
     op = ReducedOrderModelOperator.FromPhysics(w.physics, dtype=tdt, device=dev)
     rom = op.rom
@@ -405,10 +416,11 @@ def run_b200(args):
     vo_flops = 2.0 * w.d * (11 * 1.25 + 10 + w.m) * B
     fp64_peak = 37.0   # TFLOP/s, DMMA/DFMA rate measured on this pool: profiles/r1_fp64_peak.txt
     line = {
-        "metric": METRIC, "value": world * B / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": METRIC, "value": (total if strong else world * B) / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": dict(w.describe(), per_gpu_batch=B, global_batch=world * B,
+        "config": dict(w.describe(), per_gpu_batch=B, global_batch=(total if strong else world * B),
                        parallelism="sample-sharded x%d, no data-path collective" % world,
                        l2="inputs larger than L2: %.0f MB streamed per step per GPU" % ((vo_bytes + cgm_bytes) / 1e6)),
         "components": {

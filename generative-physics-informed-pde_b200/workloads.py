@@ -15,6 +15,8 @@ CONFIGS = {
                  desc="example.ipynb/highres32: 4x4 CGM, 32x32 FOM, batch 64, V=W (m=25)"),
     "cfg2": dict(nx=4, refines=4, ptype="ND", ell=0.04, B=4096, n_rbf=0,
                  desc="4x4 CGM, 64x64 FOM, batch 4096 log-normal fields, V=W (m=25)"),
+    "cfg4": dict(nx=4, refines=4, ptype="ND", ell=0.04, B=131072, n_rbf=0,
+                 desc="config 2's mesh, batch 131072 sample-sharded over the GPUs (strong scaling), V=W (m=25)"),
     "cfg3": dict(nx=8, refines=4, ptype="ND", ell=0.04, B=16384, n_rbf=175,
                  desc="8x8 CGM, 128x128 FOM, 256 weighting functions (81 CGR + 175 RBF), batch 16384"),
 }
