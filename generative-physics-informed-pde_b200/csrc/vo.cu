@@ -42,6 +42,7 @@ constexpr int kVoThreads = 256;
 
 #include "vo_fused.cuh"
 #include "vo_grid.cuh"
+#include "vo_grid2.cuh"
 #include "vo_gemm.cuh"
 
 struct gpde_vo_plan {
@@ -424,6 +425,71 @@ static bool use_grid(const gpde_vo_plan *pl) {
     return !(e && (strcmp(e, "v1") == 0 || strcmp(e, "fused") == 0));
 }
 
+// Lean structured-grid kernel (vo_grid2.cuh): nx in {16, 32, 64, 128}, even ny, no load vector.  Returns 1 if it
+// served the call, 0 if vo_grid.cuh should.  rho_pitch > 0 selects the rho variant (V, m unused).
+// GPDE_GRID_V=1 keeps it out (A/B runs against the general kernel).
+static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
+                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
+                        int rho_pitch, int sub_f, long long B, cudaStream_t st) {
+    const GridDev &G0 = pl->grid;
+    {
+        const char *e = getenv("GPDE_GRID_V");
+        if (e && atoi(e) == 1) return 0;
+    }
+    const int nx = G0.nx, ny = G0.ny;
+    if (!(nx == 16 || nx == 32 || nx == 64 || nx == 128) || ny < 2 || (ny & 1)) return 0;
+    if (G0.has_load && sub_f) return 0;
+    if (((uintptr_t)a & 15) || (a_stride & 1) || ((uintptr_t)y & 7)) return 0;
+    const bool rho = rho_pitch > 0;
+    int NT = 1, NX = 0;
+    if (!rho) {
+        if (m < 1 || m > 32 || ((uintptr_t)workspace & 15)) return 0;
+        NT = m >> 3; NX = m & 7;
+        if (NX > 1 || NT == 0) { NT += NX ? 1 : 0; NX = 0; }
+    }
+    Grid2Dev G;
+    memset(&G, 0, sizeof(G));
+    G.nx = nx; G.ny = ny; G.ncol = G0.ncol;
+    for (G.lognx = 0; (1 << G.lognx) < nx; ++G.lognx) {}
+    G.nstrips = nx / 16;
+    for (G.lognstrips = 0; (1 << G.lognstrips) < G.nstrips; ++G.lognstrips) {}
+    G.groups = 16 / G.nstrips;
+    G.in0 = G0.in0; G.sy = G0.sy; G.rh = G0.rh; G.scale = G0.scale;
+    const int S = 8 * G.groups;
+    G.a_pitch = 2 * nx + 2;
+    G.y_pitch = 2 * nx + 8;
+    G.y_off = S * G.a_pitch * 8;
+    G.v_off = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
+    G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128);
+    G.stage_bytes = (G.v_off + 2 * G.v_row_bytes + 127) & ~127;
+    const size_t smem = 2 * (size_t)G.stage_bytes + 4 * sizeof(unsigned long long) + 16 * sizeof(double);
+    if (smem > 227 * 1024) return 0;
+    double *Vp = (double *)workspace;
+    if (!rho) {
+        const long long total = (long long)(ny + 1) * G.v_row_bytes / 8;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+        vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
+    }
+    const unsigned grid = (unsigned)((B + S - 1) / S);
+#define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV)                                                                        \
+    {                                                                                                            \
+        auto kern = vo_grid2_kernel<NTV, NXV, RHOV>;                                                             \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<grid, 512, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, rho ? rho_pitch : m, r, B);  \
+    }
+    if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
+    else if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)
+    else if (NT == 1) GPDE_LAUNCH_GRID2(1, 1, false)
+    else if (NT == 2 && NX == 0) GPDE_LAUNCH_GRID2(2, 0, false)
+    else if (NT == 2) GPDE_LAUNCH_GRID2(2, 1, false)
+    else if (NT == 3 && NX == 0) GPDE_LAUNCH_GRID2(3, 0, false)
+    else if (NT == 3) GPDE_LAUNCH_GRID2(3, 1, false)
+    else GPDE_LAUNCH_GRID2(4, 0, false)
+#undef GPDE_LAUNCH_GRID2
+    GPDE_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 // Structured-grid path (FP64 I/O only).  Returns 1 if it served the call, 0 if the caller should use the
 // generic kernels (alignment / size conditions not met), <0 on error.
 static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
@@ -431,6 +497,10 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
                        int sub_f, long long B, cudaStream_t st) {
     GridDev G = pl->grid;
     if (!y || m < 1 || m > 32) return 0;
+    {
+        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, B, st);
+        if (rc2 != 0) return rc2;
+    }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
     int R, NS, W;
@@ -474,6 +544,10 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
                            cudaStream_t st) {
     GridDev G = pl->grid;
     if (!y) return 0;
+    {
+        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, nullptr, 0, rho, nullptr, pitch, sub_f, B, st);
+        if (rc2 != 0) return rc2;
+    }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
     int R, NS, W;
     size_t stage;                                     // no V rows in the stage

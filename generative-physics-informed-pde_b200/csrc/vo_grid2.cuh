@@ -1,0 +1,359 @@
+// Structured-grid virtual-observable residual kernel, lean variant (sm_100a).  Included by vo.cu after vo_grid.cuh.
+//
+//   r[b,:] = V^T (K_fom(a_b) u~_b - f)_free        (VirtualObservables.py:61-69, 662, 990)
+//
+// Same algorithm and work decomposition as vo_grid.cuh (marching over node rows, flux form, the 4 values a lane
+// produces are its A fragments of mma.sync.m8n8k4.f64), specialised for the reference's own meshes so that the
+// inner loop carries no generality:
+//   * nx in {16, 32, 64, 128} pixels per row and an even number of pixel rows, no load vector
+//     (LinearEllipticFactories.py:165-171 is the zero load); anything else stays with vo_grid.cuh;
+//   * exactly one lane per warp row touches the left Dirichlet column and one the right one: two selects per
+//     row instead of per-column category decoding; no column masks; first and last node row peeled;
+//   * a stage = 2 node rows; every thread copies the same 4 + 4 16-byte pieces per stage (one piece position in
+//     4 samples), addresses advance by a constant: ~35 instructions per thread and stage;
+//   * B fragments two at a time (LDS.128 from a pair-packed V row);
+//   * m = 8 NT + NX: the NX (0 or 1) columns past the last full n-tile go through DFMA with one accumulator per
+//     lane (m = 25: 3 DMMA tiles + 1 DFMA column instead of 4 tiles: -12 % FP64-pipe cycles per node row).
+// Shared memory: 2 stages x (a rows | y rows | packed V rows), zero-initialised once so that the few halo reads
+// that fall outside a sample's rows see finite numbers.
+#pragma once
+
+namespace gpde {
+
+struct Grid2Dev {
+    int nx, ny, ncol, lognx;
+    int nstrips, lognstrips, groups;
+    long long in0, sy;       // conductivity entry of pixel (cx, cy) = in0 + cy * sy + cx
+    double rh, scale;
+    int a_pitch, y_pitch;    // doubles per sample inside a stage
+    int y_off, v_off;        // byte offsets inside a stage
+    int stage_bytes, v_row_bytes;
+};
+
+__device__ __forceinline__ void cp_async8_u32(unsigned smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ double2 lds128(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ double lds64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// V[d,m] row-major -> per node row t: [strip q][pair p < 2 NT][lane][2] then [strip q][k][4] (NX = 1 only).
+//   pair p, half h: idx = 2 p + h = jj * NT + tt; lane = 4 n + kk holds V[t*ncol + 16 q + 4 kk + jj][8 tt + n];
+//   extra column: V[t*ncol + 16 q + 4 k + j][8 NT]     (0 outside the matrix)
+__global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, int m, int NT, int NX,
+                                     double *__restrict__ Vp) {
+    const int per_strip = 4 * NT * 32, per_row = G.v_row_bytes / 8, main = G.nstrips * per_strip;
+    const long long total = (long long)(G.ny + 1) * per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / per_row);
+        int rem = (int)(i - (long long)t * per_row);
+        int c, col;
+        if (rem < main) {
+            const int q = rem / per_strip;
+            rem -= q * per_strip;
+            const int h = rem & 1, lane = (rem >> 1) & 31, p = rem >> 6;
+            const int idx = 2 * p + h, jj = idx / NT, tt = idx - jj * NT;
+            c = 16 * q + 4 * (lane & 3) + jj;
+            col = 8 * tt + (lane >> 2);
+        } else {
+            rem -= main;
+            c = rem;             // [q][k][j] = column 16 q + 4 k + j
+            col = 8 * NT;
+        }
+        Vp[i] = (c < G.ncol && col < m && (NX || col < 8 * NT)) ? V[((long long)t * G.ncol + c) * m + col] : 0.0;
+    }
+}
+
+template <int NT, int NX, bool RHO>
+__global__ void __launch_bounds__(512, 1)
+vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, int a_is_log,
+                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
+                const double *__restrict__ Vp, int m, double *__restrict__ r, long long B) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kThreads = 512, kWarps = 16;
+    constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + 2 * (size_t)G.stage_bytes);
+    unsigned long long *empty = full + 2;
+    double *tab = reinterpret_cast<double *>(empty + 2);
+    const unsigned sm0 = smem_u32(smem_raw);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & (G.nstrips - 1), grp = warp >> G.lognstrips;
+    const int s = lane >> 2, k = lane & 3;
+    const int S = 8 * G.groups;
+    const int sl = grp * 8 + s;
+    const long long cta_b0 = (long long)blockIdx.x * S;
+    const bool b_valid = cta_b0 + sl < B;
+    const long long b = b_valid ? cta_b0 + sl : B - 1;
+    const int ncol = G.ncol, nx = G.nx, ny = G.ny;
+    const long long d = (long long)ncol * (ny + 1);
+    const int c0 = 16 * q + 4 * k;
+    const int n_stages = ny >> 1;
+
+    // ---- zero the stages (halo reads past a sample's rows must see finite numbers), barriers, exp table
+    {
+        const int n16 = (2 * G.stage_bytes) >> 4;
+        for (int i = tid; i < n16; i += kThreads)
+            asm volatile("st.shared.v2.f64 [%0], {%1,%1};" ::"r"(sm0 + 16 * i), "d"(0.0) : "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(full + i, kThreads + 1);
+            mbar_init(empty + i, kWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 16) tab[tid] = kExp16Tab[tid];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros are ordered before the bulk copies
+    __syncthreads();
+
+    // ---- staging: thread tid copies piece (tid mod nx) of samples smp0 + i * dsm, i < 4 (those inside the batch)
+    const int piece = tid & (nx - 1), smp0 = tid >> G.lognx, dsm = kThreads >> G.lognx;
+    int nv = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nv += (cta_b0 + smp0 + i * dsm < B) ? 1 : 0;
+    // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx doubles (lowest address first)
+    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece;
+    const long long a_adv = 16 * G.sy, a_smp = (long long)dsm * a_stride * 8;
+    const unsigned a_dst = smp0 * G.a_pitch * 8 + 16 * piece, a_dsmp = dsm * G.a_pitch * 8;
+    // node rows 2 ts + 1, 2 ts + 2: 2 ncol doubles starting on an 8-byte boundary; copied from the enclosing
+    // 16-byte boundary (the phase is the same for all stages and for the 4 samples of a thread: dsm is even)
+    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * d + ncol);
+    const int y_sig = (int)(((unsigned long long)y_row1 >> 3) & 1);
+    const char *y_src = y_row1 - 8 * y_sig + 16 * piece;
+    const long long y_adv = 16 * ncol, y_smp = (long long)dsm * d * 8;
+    const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + 2 * ((smp0 >> 1) & 1) + 2) * 8 + 16 * piece, y_dsmp = dsm * G.y_pitch * 8;
+    const bool y_piece_ok = piece < nx - 1 || y_sig;
+    // the last piece of the batch's last sample would read 8 bytes past the tensor: copied as 8 bytes instead
+    const bool y_tail = y_sig && piece == nx - 1 && nv > 0 && cta_b0 + smp0 + (nv - 1) * dsm == B - 1;
+
+    auto issue_stage = [&](int ts, int slot) {
+        const unsigned sb = sm0 + slot * G.stage_bytes;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nv) cp_async16_u32(sb + a_dst + i * a_dsmp, a_src + i * a_smp);
+        if (y_piece_ok) {
+            const int nvy = nv - ((y_tail && ts == n_stages - 1) ? 1 : 0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp, y_src + i * y_smp);
+            if (nvy != nv) cp_async8_u32(sb + y_dst + (nv - 1) * y_dsmp, y_src + (nv - 1) * y_smp);
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full + slot)) : "memory");
+        if (tid == 0) {
+            if (!RHO) {
+                const unsigned bytes = 2u * G.v_row_bytes;
+                mbar_arrive_expect_tx(full + slot, bytes);
+                bulk_g2s(smem_raw + (size_t)slot * G.stage_bytes + G.v_off,
+                         reinterpret_cast<const char *>(Vp) + (size_t)(2 * ts) * G.v_row_bytes, bytes, full + slot);
+            } else {
+                mbar_arrive(full + slot);
+            }
+        }
+        a_src += a_adv;
+        y_src += y_adv;
+    };
+    issue_stage(0, 0);
+    if (n_stages > 1) issue_stage(1, 1);
+
+    // ---- per-lane constants of the consumer
+    const bool is_left = c0 == 0, is_right = c0 == nx - 4;
+    const double *yb = y + b * d;
+    const double *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
+    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * d + ncol) >> 3) & 1);
+    // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
+    const unsigned y_lane = G.y_off + (sl * G.y_pitch + 2 * ((sl >> 1) & 1) + 2 + sig_b + c0) * 8;
+    const unsigned a_lane0 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? 0 : nx * 8);   // pixel row 2 ts
+    const unsigned a_lane1 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? nx * 8 : 0);   // pixel row 2 ts + 1
+    const unsigned v_lane = G.v_off + (q * NP * 32 + lane) * 16;
+    const unsigned x_lane = G.v_off + G.nstrips * NP * 512 + (q * 4 + k) * 32;
+    const unsigned row_bytes = ncol * 8;
+    const double rh = G.rh;
+
+    double acc[NT][2], accx = 0.0;
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt) acc[tt][0] = acc[tt][1] = 0.0;
+    double uc[4], ulc, urc, ap[5], fvp[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fvp[j] = 0.0;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) ap[j] = 0.0;
+    // node row 0 straight from global memory
+    {
+        const double g0 = gp ? __ldg(gp) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) uc[j] = (c0 + j < ncol) ? __ldg(yb + c0 + j) : 0.0;
+        ulc = is_left ? g0 : __ldg(yb + c0 - 1);
+        urc = (c0 + 4 < ncol) ? __ldg(yb + c0 + 4) : 0.0;
+        if (is_right) uc[3] = g0;
+    }
+    double gn0 = gp ? __ldg(gp + 2) : 0.0, gn1 = gp ? __ldg(gp + 4) : 0.0;   // Dirichlet values of node rows 1, 2
+
+    // one node row: new row (un, an) in, residual of the row below (uc between ap and an) out
+    auto node_row = [&](const double (&un)[4], double unl, double unr, const double (&an)[5], unsigned v_addr,
+                        unsigned x_addr, const double *v_glob, int t_out) {
+        double fh[5];
+        fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) fh[j] = (ap[j] + an[j]) * (uc[j] - uc[j - 1]);
+        fh[4] = (ap[4] + an[4]) * (urc - uc[3]);
+        double Sv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double fv = (an[j] + an[j + 1]) * (un[j] - uc[j]);
+            Sv[j] = fma(rh, fh[j + 1] - fh[j], fv - fvp[j]);
+            fvp[j] = fv;
+        }
+        if (is_right) Sv[3] = 0.0;
+        if constexpr (RHO) {
+            if (b_valid) {
+                double *dst = r + b * (long long)m + (long long)t_out * ncol + c0;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dst[j] = G.scale * Sv[j];
+                if (!is_right) dst[3] = G.scale * Sv[3];
+            }
+        } else {
+            double bf[4 * NT];
+            if (v_glob) {   // last node row: packed V row from global memory
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = __ldg(reinterpret_cast<const double2 *>(v_glob) + (q * NP + p) * 32 + lane);
+                    bf[2 * p] = v.x; bf[2 * p + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                    const double2 v = lds128(v_addr + p * 512);
+                    bf[2 * p] = v.x; bf[2 * p + 1] = v.y;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+                for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj * NT + tt]);
+            if constexpr (NX > 0) {
+                double2 x0, x1;
+                if (v_glob) {
+                    const double2 *xp = reinterpret_cast<const double2 *>(v_glob) + G.nstrips * NP * 32 + (q * 4 + k) * 2;
+                    x0 = __ldg(xp); x1 = __ldg(xp + 1);
+                } else {
+                    x0 = lds128(x_addr); x1 = lds128(x_addr + 16);
+                }
+                accx = fma(Sv[0], x0.x, accx);
+                accx = fma(Sv[1], x0.y, accx);
+                accx = fma(Sv[2], x1.x, accx);
+                accx = fma(Sv[3], x1.y, accx);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) uc[j] = un[j];
+        ulc = unl; urc = unr;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) ap[j] = an[j];
+    };
+
+    for (int ts = 0; ts < n_stages; ++ts) {
+        const int slot = ts & 1;
+        const unsigned par = (ts >> 1) & 1;
+        const unsigned sb = sm0 + slot * G.stage_bytes;
+        const double g0 = gn0, g1 = gn1;
+        if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
+            gn0 = __ldg(gp + 2 * (2 * ts + 3));
+            gn1 = __ldg(gp + 2 * (2 * ts + 4));
+        }
+        mbar_wait(full + slot, par);
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+            const unsigned ya = sb + y_lane + rr * row_bytes;
+            double un[4], unl, unr, an[5];
+            unl = lds64(ya - 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) un[j] = lds64(ya + 8 * j);
+            unr = lds64(ya + 32);
+            const double gv = rr ? g1 : g0;
+            if (is_left) unl = gv;
+            if (is_right) un[3] = gv;
+            const unsigned aa = sb + (rr ? a_lane1 : a_lane0);
+            {
+                const double2 p0 = lds128(aa), p1 = lds128(aa + 16);
+                an[0] = p0.x; an[1] = p0.y; an[2] = p1.x; an[3] = p1.y;
+                an[4] = lds64(aa + 32);
+            }
+            if (a_is_log) {
+                int hmax = exp_arg_hi(an[4]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hmax = max(hmax, exp_arg_hi(an[j]));
+                if (hmax <= kExpHiMax) {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+                }
+            }
+            node_row(un, unl, unr, an, sb + v_lane + rr * G.v_row_bytes, sb + x_lane + rr * G.v_row_bytes, nullptr,
+                     2 * ts + rr);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + slot);
+        if (ts + 2 < n_stages) {
+            mbar_wait(empty + slot, par);
+            issue_stage(ts + 2, slot);
+        }
+    }
+    // ---- last node row (ny): no pixel row above
+    {
+        const double un[4] = {0.0, 0.0, 0.0, 0.0}, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        node_row(un, 0.0, 0.0, an, 0u, 0u,
+                 RHO ? nullptr : reinterpret_cast<const double *>(reinterpret_cast<const char *>(Vp) + (size_t)ny * G.v_row_bytes),
+                 ny);
+    }
+
+    if constexpr (RHO) {
+        const int pad = m - (int)d;   // zero the K padding [d, m) of this CTA's rows
+        for (int idx = tid; idx < S * pad; idx += kThreads) {
+            const int si = idx / pad, c = idx - si * pad;
+            if (cta_b0 + si < B) r[(cta_b0 + si) * (long long)m + d + c] = 0.0;
+        }
+        return;
+    }
+    // ---- sum the strips' partial tiles and store r = cvs * sum   (stage memory is free now)
+    constexpr int NW = NT * 8 + 2 * NX;   // doubles per (sample, strip) record
+    if constexpr (NX > 0) {
+        accx += __shfl_xor_sync(0xffffffffu, accx, 1);
+        accx += __shfl_xor_sync(0xffffffffu, accx, 2);
+    }
+    __syncthreads();
+    double *red = reinterpret_cast<double *>(smem_raw);   // [groups][nstrips][8 samples][NW]
+    {
+        double *dst = red + (((size_t)grp * G.nstrips + q) * 8 + s) * NW;
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt) {
+            dst[tt * 8 + 2 * k] = acc[tt][0];
+            dst[tt * 8 + 2 * k + 1] = acc[tt][1];
+        }
+        if (NX > 0 && k == 0) dst[NT * 8] = accx;
+    }
+    __syncthreads();
+    constexpr int MC = NT * 8 + NX;
+    for (int idx = tid; idx < S * MC; idx += kThreads) {
+        const int si = idx / MC, col = idx - si * MC;
+        const long long bs = cta_b0 + si;
+        if (col < m && bs < B) {
+            const int gi = si >> 3, ss = si & 7;
+            double v = 0.0;
+            for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * NW + col];
+            r[bs * m + col] = G.scale * v;
+        }
+    }
+}
+
+}  // namespace gpde

@@ -367,6 +367,57 @@ def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
     assert rel_err(plan.residual(T(a), yv, T(g), V).cpu(), plan.residual(T(a), T(y), T(g), V).cpu()) < 1e-12
 
 
+@pytest.mark.parametrize("nx,ny,B", [(64, 64, 37), (32, 32, 64), (16, 2, 130), (16, 6, 3), (128, 4, 19), (64, 2, 1),
+                                     (32, 8, 129)])
+def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, monkeypatch):
+    """vo_grid2.cuh (nx in {16,32,64,128}, even ny, no load) against the general grid kernel (GPDE_GRID_V=1) and the
+    version-1 kernels: every (n-tiles, DFMA column) split of m, ragged batches (incl. batches smaller than a
+    CTA), y views starting off a 16-byte boundary (both phases), shared field / Dirichlet rows, no Dirichlet data,
+    conductivity input, the rho variant behind residual_T and m > 32."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 77 + ny, dev, load=False)
+    T = lambda t: torch.tensor(t, device=dev)
+    big = torch.zeros(B * fom.dim_out + 1, dtype=torch.float64, device=dev)
+    y_odd = big[1:].view(B, fom.dim_out)
+    y_odd.copy_(T(y))
+    for m in (1, 8, 9, 16, 17, 24, 25, 32, 40):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        variants = [
+            dict(a=T(a), y=T(y), g=T(g)),
+            dict(a=T(a), y=y_odd, g=T(g)),
+            dict(a=T(a[0]), y=T(y), g=T(g[0])),
+            dict(a=T(np.exp(a)), y=T(y), g=None, a_is_log=False),
+        ]
+        for kw in variants:
+            aa, yy, gg = kw.pop('a'), kw.pop('y'), kw.pop('g')
+            r_lean = plan.residual(aa, yy, gg, V, **kw)
+            monkeypatch.setenv("GPDE_GRID_V", "1")
+            r_gen = plan.residual(aa, yy.contiguous().clone(), gg, V, **kw)
+            monkeypatch.delenv("GPDE_GRID_V", raising=False)
+            monkeypatch.setenv("GPDE_VO_PATH", "v1")
+            r_v1 = plan.residual(aa, yy, gg, V, **kw)
+            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            assert rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
+            assert rel_err(r_lean.cpu(), r_gen.cpu()) < 1e-12, (m, sorted(kw))
+    for m in (5, 25):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        sv = T(rng.normal(size=(B, m)))
+        q_lean = plan.residual_T(T(a), V, sv)
+        monkeypatch.setenv("GPDE_VO_PATH", "v1")
+        q_v1 = plan.residual_T(T(a), V, sv)
+        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        assert rel_err(q_lean.cpu(), q_v1.cpu()) < 1e-12, m
+    # extreme log-conductivities take the libm exp() branch: same numbers as the generic kernels
+    a2 = a.copy()
+    a2[:, ::7] = -705.0
+    a2[:, 3::11] = -750.0
+    V = T(rng.normal(size=(fom.dim_out, 25)))
+    r_lean = plan.residual(T(a2), T(y), T(g), V)
+    monkeypatch.setenv("GPDE_VO_PATH", "v1")
+    r_v1 = plan.residual(T(a2), T(y), T(g), V)
+    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+    assert torch.isfinite(r_v1).all() and rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12
+
+
 def test_grid_kernel_against_oracle(dev):
     """Grid kernel against the CPU oracle (restated FEniCS assembly + reference VO arithmetic), 1e-10."""
     from oracle import fem_p1, vo_ref
