@@ -429,13 +429,13 @@ def run_b200(args):
             "launch_mode": mode + ("" if args.no_overlap else " + ROM/VO on two streams"), "ms_per_step_eager": eager_ms, "ms_host_enqueue_per_step": host_enqueue_ms,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
         },
-        "roofline": ({"kernel": "vo_grid_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
+        "roofline": ({"kernel": "vo_grid2_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
                       "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                       "frac": vo_flops / (t_vo * 1e-3) / 1e12 / fp64_peak, "traffic": recorded_traffic(args.workload, args.dtype),
                       "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
                       "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
                      if path in (0, 3) and w.m > 32 else
-                     {"kernel": {2: "vo_grid_kernel (+ vo_grid_pack_kernel)", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
+                     {"kernel": {2: "vo_grid2_kernel (+ vo_grid2_pack_kernel)", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
                       "bound": "hbm", "achieved": achieved, "peak": peak,
                       "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes,
