@@ -459,11 +459,19 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     G.a_pitch = 2 * nx + 2;
     G.y_pitch = 2 * nx + 8;
     G.y_off = S * G.a_pitch * 8;
-    G.v_off = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
+    G.v_off = 0;
     G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128);
-    G.stage_bytes = (G.v_off + 2 * G.v_row_bytes + 127) & ~127;
-    const size_t smem = 2 * (size_t)G.stage_bytes + 4 * sizeof(unsigned long long) + 16 * sizeof(double);
+    G.stage_bytes = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
+    const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 16 * sizeof(double);
+    // V ring: three 2-row stages when they fit (the sample groups of a CTA may then drift a stage apart), else two
+    G.nvs = rho ? 0 : ((fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2);
+    {
+        const char *e = getenv("GPDE_GRID2_NVS");
+        if (e && !rho && (atoi(e) == 2 || atoi(e) == 3)) G.nvs = atoi(e);
+    }
+    const size_t smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
     if (smem > 227 * 1024) return 0;
+    G.flags = getenv("GPDE_GRID2_FLAGS") ? atoi(getenv("GPDE_GRID2_FLAGS")) : 0;
     double *Vp = (double *)workspace;
     if (!rho) {
         const long long total = (long long)(ny + 1) * G.v_row_bytes / 8;
@@ -471,11 +479,31 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
         vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
     }
     const unsigned grid = (unsigned)((B + S - 1) / S);
+    // the residual kernel is launched as a programmatic dependent of the packing kernel (its prologue and first
+    // a / y stages overlap the packing); GPDE_GRID2_PDL=0 keeps the plain stream order
+    bool pdl = !rho;
+    {
+        const char *e = getenv("GPDE_GRID2_PDL");
+        if (e && atoi(e) == 0) pdl = false;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(512);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const int m_arg = rho ? rho_pitch : m;
 #define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV)                                                                        \
     {                                                                                                            \
         auto kern = vo_grid2_kernel<NTV, NXV, RHOV>;                                                             \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        kern<<<grid, 512, smem, st>>>(G, a, a_stride, a_is_log, y, g, g_stride, Vp, rho ? rho_pitch : m, r, B);  \
+        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, g, g_stride,                   \
+                                        (const double *)Vp, m_arg, r, B));                                       \
     }
     if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
     else if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)

@@ -27,11 +27,38 @@ struct Grid2Dev {
     double rh, scale;
     int a_pitch, y_pitch;    // doubles per sample inside a stage
     int y_off, v_off;        // byte offsets inside a stage
-    int stage_bytes, v_row_bytes;
+    int stage_bytes, v_row_bytes;   // one a/y stage (all samples of the CTA); one packed V row
+    int nvs;                        // V stages in the ring (2 or 3)
+    int flags;                      // experiment switches (GPDE_GRID2_FLAGS): 1 = poll barriers without nanosleep
 };
 
 __device__ __forceinline__ void cp_async8_u32(unsigned smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// mbar_wait without the back-off between polls
+__device__ __forceinline__ void mbar_spin(unsigned long long *bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
 }
 __device__ __forceinline__ double2 lds128(unsigned addr) {
     double2 v;
@@ -49,6 +76,9 @@ __device__ __forceinline__ double lds64(unsigned addr) {
 //   extra column: V[t*ncol + 16 q + 4 k + j][8 NT]     (0 outside the matrix)
 __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, int m, int NT, int NX,
                                      double *__restrict__ Vp) {
+    // programmatic dependent launch: the residual kernel may start its prologue (shared-memory setup, first a / y
+    // stages) now; it waits for this grid (griddepcontrol.wait) before it touches the packed rows
+    asm volatile("griddepcontrol.launch_dependents;");
     const int per_strip = 4 * NT * 32, per_row = G.v_row_bytes / 8, main = G.nstrips * per_strip;
     const long long total = (long long)(G.ny + 1) * per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -80,9 +110,14 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + 2 * (size_t)G.stage_bytes);
-    unsigned long long *empty = full + 2;
-    double *tab = reinterpret_cast<double *>(empty + 2);
+    // shared memory: 2 a/y stages | nvs V stages | barriers | exp table
+    const int v_bytes = 2 * G.v_row_bytes;          // one V stage = 2 packed rows
+    unsigned char *v_base = smem_raw + 2 * (size_t)G.stage_bytes;
+    unsigned long long *full_ay = reinterpret_cast<unsigned long long *>(v_base + (size_t)G.nvs * v_bytes);   // [group][2]
+    unsigned long long *empty_ay = full_ay + 2 * kWarps;
+    unsigned long long *full_v = empty_ay + 2 * kWarps;                                                         // [nvs <= 4]
+    unsigned long long *empty_v = full_v + 4;
+    double *tab = reinterpret_cast<double *>(empty_v + 4);
     const unsigned sm0 = smem_u32(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -97,43 +132,54 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     const long long d = (long long)ncol * (ny + 1);
     const int c0 = 16 * q + 4 * k;
     const int n_stages = ny >> 1;
+    const int gthreads = 32 * G.nstrips;            // threads of one sample group (= 2 nx)
 
     // ---- zero the stages (halo reads past a sample's rows must see finite numbers), barriers, exp table
     {
-        const int n16 = (2 * G.stage_bytes) >> 4;
+        const int n16 = (2 * G.stage_bytes) >> 4;   // a / y stages only: every byte of a V stage is overwritten
         for (int i = tid; i < n16; i += kThreads)
             asm volatile("st.shared.v2.f64 [%0], {%1,%1};" ::"r"(sm0 + 16 * i), "d"(0.0) : "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(full + i, kThreads + 1);
-            mbar_init(empty + i, kWarps);
+        for (int i = 0; i < 2 * G.groups; ++i) {
+            mbar_init(full_ay + i, gthreads);
+            mbar_init(empty_ay + i, G.nstrips);
+        }
+        for (int i = 0; i < G.nvs; ++i) {
+            mbar_init(full_v + i, 1);
+            mbar_init(empty_v + i, kWarps);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 16) tab[tid] = kExp16Tab[tid];
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zeros are ordered before the bulk copies
     __syncthreads();
 
-    // ---- staging: thread tid copies piece (tid mod nx) of samples smp0 + i * dsm, i < 4 (those inside the batch)
-    const int piece = tid & (nx - 1), smp0 = tid >> G.lognx, dsm = kThreads >> G.lognx;
+    // ---- staging.  Every sample group (8 samples, nstrips warps) runs its OWN two-stage ring of a / y rows with its
+    // own barriers, so the groups drift apart and the four warps of a scheduler (one per group) sit in different
+    // phases of the row (exp / fluxes / DMMA / waiting); only the packed V rows are shared by the CTA (ring of nvs
+    // stages, copied by thread 0).  Thread tg of a group copies piece (tg mod nx) of samples (tg / nx) + 2 i, i < 4.
+    const int tg = tid & (gthreads - 1);
+    const int piece = tg & (nx - 1), smp0 = 8 * grp + (tg >> G.lognx);
     int nv = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) nv += (cta_b0 + smp0 + i * dsm < B) ? 1 : 0;
+    for (int i = 0; i < 4; ++i) nv += (cta_b0 + smp0 + 2 * i < B) ? 1 : 0;
     // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx doubles (lowest address first)
     const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece;
-    const long long a_adv = 16 * G.sy, a_smp = (long long)dsm * a_stride * 8;
-    const unsigned a_dst = smp0 * G.a_pitch * 8 + 16 * piece, a_dsmp = dsm * G.a_pitch * 8;
+    const long long a_adv = 16 * G.sy, a_smp = 2 * a_stride * 8;
+    const unsigned a_dst = smp0 * G.a_pitch * 8 + 16 * piece, a_dsmp = 2 * G.a_pitch * 8;
     // node rows 2 ts + 1, 2 ts + 2: 2 ncol doubles starting on an 8-byte boundary; copied from the enclosing
-    // 16-byte boundary (the phase is the same for all stages and for the 4 samples of a thread: dsm is even)
+    // 16-byte boundary (the phase is the same for all stages and for the 4 samples of a thread: d is odd, the
+    // samples are 2 apart)
     const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * d + ncol);
     const int y_sig = (int)(((unsigned long long)y_row1 >> 3) & 1);
     const char *y_src = y_row1 - 8 * y_sig + 16 * piece;
-    const long long y_adv = 16 * ncol, y_smp = (long long)dsm * d * 8;
-    const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + 2 * ((smp0 >> 1) & 1) + 2) * 8 + 16 * piece, y_dsmp = dsm * G.y_pitch * 8;
+    const long long y_adv = 16 * ncol, y_smp = 2 * d * 8;
+    // slot of sample sl starts at (sl * y_pitch + 2 * ((sl >> 1) & 1) + 2) doubles; (smp0 + 2 i) >> 1 has the parity of i
+    const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + 2) * 8 + 16 * piece, y_dsmp = 2 * G.y_pitch * 8;
     const bool y_piece_ok = piece < nx - 1 || y_sig;
     // the last piece of the batch's last sample would read 8 bytes past the tensor: copied as 8 bytes instead
-    const bool y_tail = y_sig && piece == nx - 1 && nv > 0 && cta_b0 + smp0 + (nv - 1) * dsm == B - 1;
+    const bool y_tail = y_sig && piece == nx - 1 && nv > 0 && cta_b0 + smp0 + 2 * (nv - 1) == B - 1;
+    unsigned long long *my_full = full_ay + 2 * grp, *my_empty = empty_ay + 2 * grp;
 
     auto issue_stage = [&](int ts, int slot) {
         const unsigned sb = sm0 + slot * G.stage_bytes;
@@ -144,25 +190,31 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
             const int nvy = nv - ((y_tail && ts == n_stages - 1) ? 1 : 0);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp, y_src + i * y_smp);
-            if (nvy != nv) cp_async8_u32(sb + y_dst + (nv - 1) * y_dsmp, y_src + (nv - 1) * y_smp);
+                if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp + 16 * (i & 1), y_src + i * y_smp);
+            if (nvy != nv) cp_async8_u32(sb + y_dst + (nv - 1) * y_dsmp + 16 * ((nv - 1) & 1), y_src + (nv - 1) * y_smp);
         }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(full + slot)) : "memory");
-        if (tid == 0) {
-            if (!RHO) {
-                const unsigned bytes = 2u * G.v_row_bytes;
-                mbar_arrive_expect_tx(full + slot, bytes);
-                bulk_g2s(smem_raw + (size_t)slot * G.stage_bytes + G.v_off,
-                         reinterpret_cast<const char *>(Vp) + (size_t)(2 * ts) * G.v_row_bytes, bytes, full + slot);
-            } else {
-                mbar_arrive(full + slot);
-            }
-        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(my_full + slot)) : "memory");
         a_src += a_adv;
         y_src += y_adv;
     };
     issue_stage(0, 0);
     if (n_stages > 1) issue_stage(1, 1);
+
+    // packed V rows 2 ts, 2 ts + 1 -> V stage (thread 0 only; v_next = next stage to copy, into slot v_islot)
+    int v_next = 0, v_islot = 0;
+    unsigned v_ipar = 0;             // parity of the next wait on empty_v[v_islot]
+    auto issue_v = [&]() {
+        const unsigned bytes = (unsigned)v_bytes;
+        mbar_arrive_expect_tx(full_v + v_islot, bytes);
+        bulk_g2s(v_base + (size_t)v_islot * v_bytes, reinterpret_cast<const char *>(Vp) + (size_t)(2 * v_next) * G.v_row_bytes,
+                 bytes, full_v + v_islot);
+        ++v_next;
+        if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) v_ipar ^= 1; }
+    };
+    if (!RHO && tid == 0) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");   // the packing kernel's rows (no-op without a dependent launch)
+        while (v_next < G.nvs && v_next < n_stages) issue_v();
+    }
 
     // ---- per-lane constants of the consumer
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
@@ -173,8 +225,8 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     const unsigned y_lane = G.y_off + (sl * G.y_pitch + 2 * ((sl >> 1) & 1) + 2 + sig_b + c0) * 8;
     const unsigned a_lane0 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? 0 : nx * 8);   // pixel row 2 ts
     const unsigned a_lane1 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? nx * 8 : 0);   // pixel row 2 ts + 1
-    const unsigned v_lane = G.v_off + (q * NP * 32 + lane) * 16;
-    const unsigned x_lane = G.v_off + G.nstrips * NP * 512 + (q * 4 + k) * 32;
+    const unsigned v_lane = (q * NP * 32 + lane) * 16;                       // inside a V stage
+    const unsigned x_lane = G.nstrips * NP * 512 + (q * 4 + k) * 32;
     const unsigned row_bytes = ncol * 8;
     const double rh = G.rh;
 
@@ -260,16 +312,35 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
         for (int j = 0; j < 5; ++j) ap[j] = an[j];
     };
 
+    int v_slot = 0;                  // V stage being consumed and the parity of its full barrier
+    unsigned v_par = 0;
     for (int ts = 0; ts < n_stages; ++ts) {
         const int slot = ts & 1;
         const unsigned par = (ts >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
+        const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
         const double g0 = gn0, g1 = gn1;
         if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
             gn0 = __ldg(gp + 2 * (2 * ts + 3));
             gn1 = __ldg(gp + 2 * (2 * ts + 4));
         }
-        mbar_wait(full + slot, par);
+        if (!RHO && tid == 0) {
+            // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
+            while (v_next < n_stages && v_next < ts + G.nvs) {
+                if (!mbar_test(empty_v + v_islot, v_ipar)) {
+                    if (v_next > ts) break;
+                    mbar_wait(empty_v + v_islot, v_ipar);
+                }
+                issue_v();
+            }
+        }
+        if (G.flags & 1) {
+            mbar_spin(my_full + slot, par);
+            if (!RHO) mbar_spin(full_v + v_slot, v_par);
+        } else {
+            mbar_wait(my_full + slot, par);
+            if (!RHO) mbar_wait(full_v + v_slot, v_par);
+        }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const unsigned ya = sb + y_lane + rr * row_bytes;
@@ -299,18 +370,24 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                     for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
                 }
             }
-            node_row(un, unl, unr, an, sb + v_lane + rr * G.v_row_bytes, sb + x_lane + rr * G.v_row_bytes, nullptr,
+            node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, nullptr,
                      2 * ts + rr);
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(empty + slot);
+        if (lane == 0) {
+            mbar_arrive(my_empty + slot);
+            if (!RHO) mbar_arrive(empty_v + v_slot);
+        }
+        if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
         if (ts + 2 < n_stages) {
-            mbar_wait(empty + slot, par);
+            if (G.flags & 1) mbar_spin(my_empty + slot, par);
+            else mbar_wait(my_empty + slot, par);
             issue_stage(ts + 2, slot);
         }
     }
     // ---- last node row (ny): no pixel row above
     {
+        if (!RHO) asm volatile("griddepcontrol.wait;" ::: "memory");   // packed row ny is read with plain loads
         const double un[4] = {0.0, 0.0, 0.0, 0.0}, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         node_row(un, 0.0, 0.0, an, 0u, 0u,
                  RHO ? nullptr : reinterpret_cast<const double *>(reinterpret_cast<const char *>(Vp) + (size_t)ny * G.v_row_bytes),
