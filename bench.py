@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-overlap", action="store_true", help="keep the ROM and VO kernels on one stream")
+    ap.add_argument("--no-split-pack", action="store_true",
+                    help="let the VO residual call pack V itself (no ordering of the ROM kernels behind the packing)")
     return ap.parse_args()
 
 
@@ -242,6 +244,8 @@ def run_b200(args):
     torch.cuda.synchronize()
 
     vo_stream = torch.cuda.Stream(device=dev)
+    split_pack = not args.no_split_pack and vplan.kernel_path(w.m, tdt) == 2 and tdt == torch.float64
+    packed, ev_packed = [None], torch.cuda.Event()
 
     def step_resident(overlap=False):
         """One pass of the physics layer.  The coarse-grained model (forward -> adjoint) and the VO residual are
@@ -251,7 +255,18 @@ def run_b200(args):
         if overlap:
             vo_stream.wait_stream(cur)
             with torch.cuda.stream(vo_stream):
-                r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
+                if split_pack:
+                    # V packed by its own call; the ROM kernels are held back until the packing has run, so that
+                    # the VO kernel's CTAs (one whole SM each) are placed first and the ROM CTAs take the SMs left
+                    pw = vplan.pack_weights(d["V"], B, out=packed[0])
+                    if packed[0] is None and hasattr(pw, "buf"):
+                        packed[0] = pw
+                    ev_packed.record(vo_stream)
+                    r = vplan.residual(d["a"], d["y"], d["g"], pw)
+                else:
+                    r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
+            if split_pack:
+                cur.wait_event(ev_packed)
         u, factor = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
         gX, _ = rom_mod._launch_adjoint(plan, d["logX"], u, factor, d["gbar"], True, want_gradF=False)
         if overlap:

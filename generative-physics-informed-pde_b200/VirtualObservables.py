@@ -101,6 +101,25 @@ class VoPlan(object):
             self._scratch = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._scratch
 
+    def pack_weights(self, V, B, *, ignore_load=False, out=None):
+        """Packs V [d,m] once for many residual() calls with the same weighting functions (V = W of the
+        coarse-grained-residual sampler only changes at resample()).  Returns a PackedWeights to pass as ``V``,
+        or V itself when this plan / m has no packed layout.  B = the largest batch it will be used with;
+        ``out`` = an earlier PackedWeights whose buffer is reused."""
+        Vc = V.to(torch.float64).contiguous()
+        m = int(Vc.shape[1])
+        need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, int(B), m)))
+        if out is not None and out.buf.numel() >= need:
+            buf = out.buf
+        else:
+            buf = torch.empty(need, dtype=torch.uint8, device=self.device)
+        rc = self._lib.gpde_vo_pack_weights_f64(self.handle, _lib.ptr(Vc), m, 1 if ignore_load else 0, _lib.ptr(buf),
+                                                _lib.stream_of(Vc.device))
+        if rc == 1:
+            return Vc
+        _lib.check(rc, "gpde_vo_pack_weights_f64")
+        return PackedWeights(Vc, buf, int(B), bool(ignore_load))
+
     def residual(self, a, y, g, V, *, a_is_log=True, want_rho=False, ignore_load=False):
         """r[B,m] = V^T (K(a_b) u~_b - f)_free with u~ = (y on free dofs, g on Dirichlet dofs).
 
@@ -111,6 +130,13 @@ class VoPlan(object):
         sfx = _lib.suffix(dt)
         B = y.shape[0] if y is not None else (a.shape[0] if a.dim() == 2 else 1)
         a = a.contiguous()
+        packed = None
+        if isinstance(V, PackedWeights):
+            # usable as packed only for the kind of call it was packed for; otherwise the plain matrix is used
+            if (dt == torch.float64 and y is not None and not want_rho and B <= V.B and V.ignore_load == bool(ignore_load)
+                    and a.data_ptr() % 16 == 0):
+                packed = V
+            V = V.V
         y = None if y is None else y.to(dt).contiguous()
         g = None if g is None else g.to(dt).contiguous()
         m = 0 if V is None else int(V.shape[1])
@@ -118,10 +144,11 @@ class VoPlan(object):
         r = a.new_empty((B, m)) if m else None
         rho = a.new_empty((B, self.d)) if (want_rho or not m) else None
         fn = getattr(self._lib, "gpde_vo_residual_" + sfx)
+        ws = packed.buf if packed is not None else (self._workspace(B, m) if m else None)
         rc = fn(self.handle, _lib.ptr(a), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(y),
                 _lib.ptr(g), (self.n_bc if g.dim() == 2 else 0) if g is not None else 0, _lib.ptr(Vc), m,
-                _lib.ptr(r), _lib.ptr(rho), _lib.ptr(self._workspace(B, m)) if m else None,
-                1 if ignore_load else 0, B, _lib.stream_of(a.device))
+                _lib.ptr(r), _lib.ptr(rho), _lib.ptr(ws) if m else None,
+                (1 if ignore_load else 0) | (2 if packed is not None else 0), B, _lib.stream_of(a.device))
         _lib.check(rc, "gpde_vo_residual_" + sfx)
         return (r, rho) if rho is not None else r
 
@@ -137,6 +164,17 @@ class VoPlan(object):
                 _lib.ptr(s), _lib.ptr(q), _lib.ptr(self._workspace(B, m)), B, _lib.stream_of(a.device))
         _lib.check(rc, "gpde_vo_residual_T_" + sfx)
         return q
+
+
+class PackedWeights(object):
+    """V [d,m] together with its fragment-packed copy (VoPlan.pack_weights); accepted wherever residual() takes V."""
+
+    def __init__(self, V, buf, B, ignore_load):
+        self.V, self.buf, self.B, self.ignore_load = V, buf, B, ignore_load
+
+    @property
+    def shape(self):
+        return self.V.shape
 
 
 class VoResidualFn(torch.autograd.Function):

@@ -428,26 +428,22 @@ static bool use_grid(const gpde_vo_plan *pl) {
 // Lean structured-grid kernel (vo_grid2.cuh): nx in {16, 32, 64, 128}, even ny, no load vector.  Returns 1 if it
 // served the call, 0 if vo_grid.cuh should.  rho_pitch > 0 selects the rho variant (V, m unused).
 // GPDE_GRID_V=1 keeps it out (A/B runs against the general kernel).
-static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
-                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
-                        int rho_pitch, int sub_f, long long B, cudaStream_t st) {
+// mesh-side conditions and the decomposition of the lean kernel for m weighting functions (rho: no V inside)
+static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid2Dev &G, int &NT, int &NX, size_t &smem) {
     const GridDev &G0 = pl->grid;
     {
         const char *e = getenv("GPDE_GRID_V");
-        if (e && atoi(e) == 1) return 0;
+        if (e && atoi(e) == 1) return false;
     }
     const int nx = G0.nx, ny = G0.ny;
-    if (!(nx == 16 || nx == 32 || nx == 64 || nx == 128) || ny < 2 || (ny & 1)) return 0;
-    if (G0.has_load && sub_f) return 0;
-    if (((uintptr_t)a & 15) || (a_stride & 1) || ((uintptr_t)y & 7)) return 0;
-    const bool rho = rho_pitch > 0;
-    int NT = 1, NX = 0;
+    if (!G0.ok || !(nx == 16 || nx == 32 || nx == 64 || nx == 128) || ny < 2 || (ny & 1)) return false;
+    if (G0.has_load && sub_f) return false;
+    NT = 1; NX = 0;
     if (!rho) {
-        if (m < 1 || m > 32 || ((uintptr_t)workspace & 15)) return 0;
+        if (m < 1 || m > 32) return false;
         NT = m >> 3; NX = m & 7;
         if (NX > 1 || NT == 0) { NT += NX ? 1 : 0; NX = 0; }
     }
-    Grid2Dev G;
     memset(&G, 0, sizeof(G));
     G.nx = nx; G.ny = ny; G.ncol = G0.ncol;
     for (G.lognx = 0; (1 << G.lognx) < nx; ++G.lognx) {}
@@ -469,19 +465,35 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
         const char *e = getenv("GPDE_GRID2_NVS");
         if (e && !rho && (atoi(e) == 2 || atoi(e) == 3)) G.nvs = atoi(e);
     }
-    const size_t smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
-    if (smem > 227 * 1024) return 0;
+    smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
+    if (smem > 227 * 1024) return false;
     G.flags = getenv("GPDE_GRID2_FLAGS") ? atoi(getenv("GPDE_GRID2_FLAGS")) : 0;
+    return true;
+}
+
+static void grid2_pack(const Grid2Dev &G, const double *V, int m, int NT, int NX, double *Vp, cudaStream_t st) {
+    const long long total = (long long)(G.ny + 1) * G.v_row_bytes / 8;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+    vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
+}
+
+static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
+                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
+                        int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st) {
+    const bool rho = rho_pitch > 0;
+    Grid2Dev G;
+    int NT, NX;
+    size_t smem;
+    if (!grid2_setup(pl, m, rho, sub_f, G, NT, NX, smem)) return 0;
+    if (((uintptr_t)a & 15) || (a_stride & 1) || ((uintptr_t)y & 7)) return 0;
+    if (!rho && ((uintptr_t)workspace & 15)) return 0;
+    const int S = 8 * G.groups;
     double *Vp = (double *)workspace;
-    if (!rho) {
-        const long long total = (long long)(ny + 1) * G.v_row_bytes / 8;
-        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
-        vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
-    }
+    if (!rho && !prepacked) grid2_pack(G, V, m, NT, NX, Vp, st);
     const unsigned grid = (unsigned)((B + S - 1) / S);
     // the residual kernel is launched as a programmatic dependent of the packing kernel (its prologue and first
     // a / y stages overlap the packing); GPDE_GRID2_PDL=0 keeps the plain stream order
-    bool pdl = !rho;
+    bool pdl = !rho && !prepacked;
     {
         const char *e = getenv("GPDE_GRID2_PDL");
         if (e && atoi(e) == 0) pdl = false;
@@ -522,12 +534,15 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
 // generic kernels (alignment / size conditions not met), <0 on error.
 static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
-                       int sub_f, long long B, cudaStream_t st) {
+                       int sub_f, bool prepacked, long long B, cudaStream_t st) {
     GridDev G = pl->grid;
     if (!y || m < 1 || m > 32) return 0;
     {
-        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, B, st);
+        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, prepacked, B, st);
         if (rc2 != 0) return rc2;
+        if (prepacked)
+            return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) need the lean structured-grid kernel for this call "
+                                      "(16-byte aligned a, even a_stride, y given, no load vector)");
     }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
@@ -573,7 +588,7 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
     GridDev G = pl->grid;
     if (!y) return 0;
     {
-        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, nullptr, 0, rho, nullptr, pitch, sub_f, B, st);
+        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, nullptr, 0, rho, nullptr, pitch, sub_f, false, B, st);
         if (rc2 != 0) return rc2;
     }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
@@ -643,10 +658,11 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
         if (m > 0 && !rho && use_grid(pl)) {
             const int rc = launch_grid(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y,
                                        (const double *)g, (long long)g_stride, (const double *)V, m, (double *)r,
-                                       workspace, (flags & 1) ? 0 : 1, (long long)B, st);
+                                       workspace, (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
             if (rc != 0) return rc < 0 ? rc : GPDE_OK;
         }
     }
+    if (flags & 2) return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) are not usable for this call");
     if (m > 0 && m <= 32 && use_fused(pl)) {
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
         const int sub_f = (flags & 1) ? 0 : 1;
@@ -877,6 +893,20 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
     }
     if (pl->grid.ok && m > 0 && m <= 32) need = std::max(need, grid_packed_bytes(pl->grid, 4));   // packed V
     return need;
+}
+
+int gpde_vo_pack_weights_f64(const gpde_vo_plan *pl, const double *V, int m, int flags, void *workspace,
+                             gpde_stream_t stream) {
+    if (!pl || !V || !workspace) return fail(GPDE_ERR_ARG, "vo_pack_weights: null argument");
+    if ((uintptr_t)workspace & 15) return fail(GPDE_ERR_ARG, "vo_pack_weights: workspace must be 16-byte aligned");
+    Grid2Dev G;
+    int NT, NX;
+    size_t smem;
+    if (!use_grid(pl) || !grid2_setup(pl, m, false, (flags & 1) ? 0 : 1, G, NT, NX, smem)) return 1;
+    DeviceGuard guard(pl->device);
+    grid2_pack(G, V, m, NT, NX, (double *)workspace, (cudaStream_t)stream);
+    GPDE_CUDA_OK(cudaGetLastError());
+    return GPDE_OK;
 }
 
 int gpde_vo_residual_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, int a_is_log, const double *y,

@@ -143,7 +143,10 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *plan, int64_t B, int m);
  *   y   [B,d]   (NULL = zeros);  g [B or 1, n_bc] with g_stride = n_bc or 0 (NULL = zeros)
  *   V   [d,m] row-major weighting matrix (NULL with m=0: only rho is produced)
  *   rho [B,d] optional output of the fine residual itself (may be NULL)
- *   flags: bit0 = ignore the load vector f                                                  */
+ *   flags: bit0 = ignore the load vector f
+ *          bit1 = `workspace` already holds V packed by gpde_vo_pack_weights_f64 (same plan, m, bit0):
+ *                 the call skips its packing launch; it fails with GPDE_ERR_ARG instead of falling
+ *                 back when the lean structured-grid kernel cannot serve it (V must still be passed)  */
 int gpde_vo_residual_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,
                          const double *y, const double *g, int64_t g_stride, const double *V, int m,
                          double *r, double *rho, void *workspace, int flags, int64_t B,
@@ -152,6 +155,14 @@ int gpde_vo_residual_f32(const gpde_vo_plan *plan, const float *a, int64_t a_str
                          const float *y, const float *g, int64_t g_stride, const float *V, int m,
                          float *r, float *rho, void *workspace, int flags, int64_t B,
                          gpde_stream_t stream);
+
+/* Packs V[d,m] once into `workspace` (>= gpde_vo_workspace_bytes(plan, B, m), 16-byte aligned) in the
+ * fragment order of the structured-grid residual kernel, for callers whose weighting functions stay fixed
+ * over many residual calls (the CoarseGrainedResidual sampler's V = W, VirtualObservables.py:297-321, changes
+ * only at resample()).  Returns 0 when packed (pass flags bit1 to gpde_vo_residual_f64 with that workspace),
+ * 1 when this plan / m has no packed layout (call residual without bit1), < 0 on error. */
+int gpde_vo_pack_weights_f64(const gpde_vo_plan *plan, const double *V, int m, int flags, void *workspace,
+                             gpde_stream_t stream);
 
 /* q[B,d] = K_ff(a_b) (V s_b) = Gamma_b^T s_b  (VirtualObservables.py:663; with s = P r it is the
  * gradient of 1/2 r^T P r w.r.t. y).  With B = m, s = I and a_stride = 0 it yields Gamma itself. */

@@ -418,6 +418,31 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
     assert torch.isfinite(r_v1).all() and rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12
 
 
+def test_packed_weights_give_the_same_residual(dev):
+    """gpde_vo_pack_weights_f64 + flags bit1: V packed once, many residual calls; bitwise equal to the call that packs
+    V itself; meshes without a packed layout hand the matrix back."""
+    from gpde_b200.VirtualObservables import PackedWeights
+    plan, fom, a, y, g, rng = _grid_case(32, 8, "NDP", 21, 5, dev, load=False)
+    T = lambda t: torch.tensor(t, device=dev)
+    for m in (7, 25, 32):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        pw = plan.pack_weights(V, 21)
+        assert isinstance(pw, PackedWeights)
+        r0 = plan.residual(T(a), T(y), T(g), V)
+        for _ in range(2):
+            assert torch.equal(plan.residual(T(a), T(y), T(g), pw), r0)
+        assert torch.equal(plan.residual(T(a[:5]), T(y[:5]), T(g[:5]), pw), r0[:5])          # smaller batch
+        r1, rho1 = plan.residual(T(a), T(y), T(g), pw, want_rho=True)                         # not a packed call: plain V
+        assert rel_err(r1.cpu(), r0.cpu()) < 1e-12 and rel_err((rho1 @ V).cpu(), r0.cpu()) < 1e-12
+        pw2 = plan.pack_weights(2.0 * V, 21, out=pw)                                          # buffer reuse
+        assert pw2.buf.data_ptr() == pw.buf.data_ptr()
+        assert rel_err(plan.residual(T(a), T(y), T(g), pw2).cpu(), 2.0 * r0.cpu()) < 1e-13
+    assert torch.is_tensor(plan.pack_weights(T(rng.normal(size=(fom.dim_out, 40))), 21))      # m > 32
+    plan2, fom2, a2, y2, g2, _ = _grid_case(18, 5, "NDP", 4, 6, dev, load=False)              # general grid kernel only
+    V2 = T(rng.normal(size=(fom2.dim_out, 25)))
+    assert torch.is_tensor(plan2.pack_weights(V2, 4))
+
+
 def test_grid_kernel_against_oracle(dev):
     """Grid kernel against the CPU oracle (restated FEniCS assembly + reference VO arithmetic), 1e-10."""
     from oracle import fem_p1, vo_ref
