@@ -362,12 +362,12 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                 int hmax = exp_arg_hi(an[4]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hmax = max(hmax, exp_arg_hi(an[j]));
-                if (hmax <= kExpHiMax) {
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
-                } else {
+                for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                if (hmax > kExpHiMax) {   // |x| > 700, inf or NaN somewhere in the warp's row (rare): libm exp() on the
+                                          // values re-read from shared memory, so the common path keeps no copies
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = exp(an[j]);
+                    for (int j = 0; j < 5; ++j) an[j] = exp(lds64(aa + 8 * j));
                 }
             }
             node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, nullptr,
