@@ -43,6 +43,7 @@ constexpr int kVoThreads = 256;
 #include "vo_fused.cuh"
 #include "vo_grid.cuh"
 #include "vo_grid2.cuh"
+#include "vo_expand.cuh"
 #include "vo_gemm.cuh"
 
 struct gpde_vo_plan {
@@ -479,7 +480,8 @@ static void grid2_pack(const Grid2Dev &G, const double *V, int m, int NT, int NX
 
 static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
                         const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
-                        int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st) {
+                        int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st, long long y_stride = 0) {
+    if (y_stride == 0) y_stride = pl->dev.d;
     const bool rho = rho_pitch > 0;
     Grid2Dev G;
     int NT, NX;
@@ -514,7 +516,7 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     {                                                                                                            \
         auto kern = vo_grid2_kernel<NTV, NXV, RHOV>;                                                             \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, g, g_stride,                   \
+        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
                                         (const double *)Vp, m_arg, r, B));                                       \
     }
     if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
@@ -735,6 +737,41 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
         if (use_grid(pl) && !((uintptr_t)a & 15) && !(a_stride & 1) && !((uintptr_t)workspace & 15)) {
             const int d = pl->dev.d, mp = gemm_dp(m), bn = 128, ldb = (d + bn - 1) / bn * bn;
             double *Sp = (double *)workspace, *Vt = Sp + (size_t)B * mp, *w = Vt + (size_t)mp * ldb;
+            const char *ev = getenv("GPDE_VO_EXPAND");   // GPDE_VO_EXPAND=gemm: the general GEMM also for m <= 32 (A/B runs)
+            if (m <= 32 && !(ev && strcmp(ev, "gemm") == 0)) {
+                // contraction length m <= 32: one launch, operands read in place (vo_expand.cuh)
+                w = (double *)workspace;
+                Grid2Dev G2;
+                int nt2, nx2;
+                size_t smem2;
+                const bool lean = grid2_setup(pl, 0, true, 0, G2, nt2, nx2, smem2);
+                const long long ldw = lean ? (((long long)d + 3) & ~3ll) : d;   // the general grid kernel wants y contiguous
+                const int n_tiles = (d + 7) / 8;
+                const unsigned gx = (unsigned)((B + 8 * kExpandMT * kExpandWarps - 1) / (8 * kExpandMT * kExpandWarps));
+                const int nch = std::max(1, std::min(n_tiles, (int)(4 * sm_count(pl->device) / gx)));
+                const int tpc = std::min((n_tiles + nch - 1) / nch, 64);         // <= 64 n-tiles of V per CTA in shared memory
+                const dim3 grid(gx, (unsigned)((n_tiles + tpc - 1) / tpc));
+                const size_t smem = (size_t)tpc * 8 * kExpandVPitch * sizeof(double);
+                const double *sd = (const double *)s, *Vd = (const double *)V;
+#define GPDE_LAUNCH_EXPAND(KSV)                                                                                     \
+    {                                                                                                               \
+        auto kern = vo_expand_dmma_kernel<KSV>;                                                                     \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        kern<<<grid, kExpandWarps * 32, smem, st>>>(sd, Vd, w, ldw, (long long)B, d, m, tpc);                       \
+    }
+                if (m <= 8) GPDE_LAUNCH_EXPAND(2)
+                else if (m <= 16) GPDE_LAUNCH_EXPAND(4)
+                else if (m <= 28) GPDE_LAUNCH_EXPAND(7)
+                else GPDE_LAUNCH_EXPAND(8)
+#undef GPDE_LAUNCH_EXPAND
+                GPDE_CUDA_OK(cudaGetLastError());
+                if (lean) {
+                    const int rc2 = launch_grid2(pl, (const double *)a, (long long)a_stride, a_is_log, w, nullptr, 0, nullptr, 0,
+                                                 (double *)q, nullptr, d, 0, false, (long long)B, st, ldw);
+                    if (rc2 != 0) return rc2 < 0 ? rc2 : GPDE_OK;
+                    return fail(GPDE_ERR_ARG, "vo_residual_T: lean grid kernel declined after setup");
+                }
+            } else {
             {
                 const long long total = (long long)B * mp;
                 const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 8);
@@ -749,6 +786,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
                 dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
                 kern<<<grid, kGemmThreads, smem, st>>>(Sp, mp, Vt, ldb, w, d, (long long)B);
                 GPDE_CUDA_OK(cudaGetLastError());
+            }
             }
             const int rc = launch_grid_rho(pl, (const double *)a, (long long)a_stride, a_is_log, w, nullptr, 0, (double *)q, d,
                                            0, (long long)B, st);

@@ -105,8 +105,10 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
 template <int NT, int NX, bool RHO>
 __global__ void __launch_bounds__(512, 1)
 vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, int a_is_log,
-                const double *__restrict__ y, const double *__restrict__ g, long long g_stride,
+                const double *__restrict__ y, long long y_stride, const double *__restrict__ g, long long g_stride,
                 const double *__restrict__ Vp, int m, double *__restrict__ r, long long B) {
+    // y_stride = doubles between the rows of consecutive samples in y (d for a contiguous [B,d]; the expansion kernel
+    // of residual_T pads it to a multiple of 4)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
@@ -170,10 +172,10 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     // node rows 2 ts + 1, 2 ts + 2: 2 ncol doubles starting on an 8-byte boundary; copied from the enclosing
     // 16-byte boundary (the phase is the same for all stages and for the 4 samples of a thread: d is odd, the
     // samples are 2 apart)
-    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * d + ncol);
+    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * y_stride + ncol);
     const int y_sig = (int)(((unsigned long long)y_row1 >> 3) & 1);
     const char *y_src = y_row1 - 8 * y_sig + 16 * piece;
-    const long long y_adv = 16 * ncol, y_smp = 2 * d * 8;
+    const long long y_adv = 16 * ncol, y_smp = 2 * y_stride * 8;
     // slot of sample sl starts at (sl * y_pitch + 2 * ((sl >> 1) & 1) + 2) doubles; (smp0 + 2 i) >> 1 has the parity of i
     const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + 2) * 8 + 16 * piece, y_dsmp = 2 * G.y_pitch * 8;
     const bool y_piece_ok = piece < nx - 1 || y_sig;
@@ -218,9 +220,9 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 
     // ---- per-lane constants of the consumer
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
-    const double *yb = y + b * d;
+    const double *yb = y + b * y_stride;
     const double *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
-    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * d + ncol) >> 3) & 1);
+    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * y_stride + ncol) >> 3) & 1);
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
     const unsigned y_lane = G.y_off + (sl * G.y_pitch + 2 * ((sl >> 1) & 1) + 2 + sig_b + c0) * 8;
     const unsigned a_lane0 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? 0 : nx * 8);   // pixel row 2 ts

@@ -16,14 +16,37 @@ V = torch.tensor(w.V, device=dev)
 y = torch.tensor(w.y, device=dev)
 g = torch.tensor(w.g_fom[0] if w.ptype == "ND" else w.g_fom, device=dev)
 s = torch.randn(w.B, w.m, dtype=torch.float64, device=dev)
-for fn, label in ((lambda: plan.residual_T(a, V, s), "residual_T"), (lambda: plan.residual(a, y, g, V), "residual")):
+def timed(fn, n=20):
+    """device time per call from CUDA-graph replays (no host launch gaps); eager time beside it"""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(20):
-        out = fn()
+    for _ in range(n):
+        fn()
     e1.record()
     torch.cuda.synchronize()
-    print("%s %s B=%d m=%d d=%d: %.3f ms" % (name, label, w.B, w.m, w.d, e0.elapsed_time(e1) / 20))
+    eager = e0.elapsed_time(e1) / n
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        keep = fn()
+    gr.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n, eager
+
+
+for fn, label in ((lambda: plan.residual_T(a, V, s), "residual_T"), (lambda: plan.residual(a, y, g, V), "residual")):
+    tg, te = timed(fn)
+    print("%s %s B=%d m=%d d=%d: %.3f ms (graph replay), %.3f ms (eager launches)" % (name, label, w.B, w.m, w.d, tg, te))

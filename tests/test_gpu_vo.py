@@ -398,7 +398,7 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
             monkeypatch.delenv("GPDE_VO_PATH", raising=False)
             assert rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
             assert rel_err(r_lean.cpu(), r_gen.cpu()) < 1e-12, (m, sorted(kw))
-    for m in (5, 25):
+    for m in (1, 5, 8, 9, 16, 25, 28, 29, 32, 40):   # every k-step count of the expansion kernel (vo_expand.cuh), and m > 32
         V = T(rng.normal(size=(fom.dim_out, m)))
         sv = T(rng.normal(size=(B, m)))
         q_lean = plan.residual_T(T(a), V, sv)
