@@ -613,8 +613,17 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
         const char *e = getenv("GPDE_ROM_PATH");
         pl->tps = (nf == 15 && (hbw == 3 || hbw == 4) && tps_smem_adjoint(D) <= 227 * 1024 && e && strcmp(e, "tps") == 0) ? 1 : 0;
     }
-    pl->smem_fwd = sizeof(double) * (size_t)(E + n + n_band + 3 * nf);
-    pl->smem_adj = sizeof(double) * (size_t)(2 * E + 2 * n + n_band + 4 * nf);
+    // per-sample scratch; with 8 lanes per sample a 64-bit shared-memory wavefront serves two samples, so the pitch is
+    // padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint halves of the banks
+    // (GPDE_ROM_PAD=0 keeps the unpadded pitch for A/B runs)
+    auto pad_pitch = [&](size_t doubles) {
+        const char *e = getenv("GPDE_ROM_PAD");
+        if (pl->lanes != 8 || (e && atoi(e) == 0)) return doubles;
+        while (doubles % 16 != 8) ++doubles;
+        return doubles;
+    };
+    pl->smem_fwd = sizeof(double) * pad_pitch((size_t)(E + n + n_band + 3 * nf));
+    pl->smem_adj = sizeof(double) * pad_pitch((size_t)(2 * E + 2 * n + n_band + 4 * nf));
     const size_t groups = (kRomThreads / 32) * (32 / pl->lanes);
     if (groups * pl->smem_adj + arena.size() > 227 * 1024) {
         gpde_rom_plan_destroy(pl);
