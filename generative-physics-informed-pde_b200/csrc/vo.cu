@@ -482,6 +482,7 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
                         const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
                         int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st, long long y_stride = 0) {
     if (y_stride == 0) y_stride = pl->dev.d;
+    if (y_stride != pl->dev.d && rho_pitch <= 0) return 0;   // only the rho variant is built for strided y
     const bool rho = rho_pitch > 0;
     Grid2Dev G;
     int NT, NX;
@@ -519,7 +520,12 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
         GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
                                         (const double *)Vp, m_arg, r, B));                                       \
     }
-    if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
+    if (rho && y_stride != pl->dev.d) {
+        auto kern = vo_grid2_kernel<1, 0, true, true>;
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride, (const double *)Vp, m_arg, r, B));
+    }
+    else if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
     else if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)
     else if (NT == 1) GPDE_LAUNCH_GRID2(1, 1, false)
     else if (NT == 2 && NX == 0) GPDE_LAUNCH_GRID2(2, 0, false)

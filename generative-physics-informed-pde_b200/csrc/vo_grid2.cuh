@@ -102,13 +102,14 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
     }
 }
 
-template <int NT, int NX, bool RHO>
+template <int NT, int NX, bool RHO, bool YS = false>
 __global__ void __launch_bounds__(512, 1)
 vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                 const double *__restrict__ y, long long y_stride_arg, const double *__restrict__ g, long long g_stride,
                 const double *__restrict__ Vp, int m, double *__restrict__ r, long long B) {
-    // y_stride = doubles between the rows of consecutive samples in y: d for a contiguous [B,d]; only the rho variant
-    // takes it from its argument (the expansion kernel of residual_T pads the rows of w to a multiple of 4 doubles)
+    // y_stride = doubles between the rows of consecutive samples in y: d for a contiguous [B,d]; only the YS variant
+    // takes it from its argument (the expansion kernel of residual_T pads the rows of w to a multiple of 4 doubles):
+    // one more live value shifts the register allocation of the other variants by ~3 % (measured A/B on one box)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
@@ -132,7 +133,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     const long long b = b_valid ? cta_b0 + sl : B - 1;
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
     const long long d = (long long)ncol * (ny + 1);
-    const long long y_stride = RHO ? y_stride_arg : d;
+    const long long y_stride = YS ? y_stride_arg : d;
     const int c0 = 16 * q + 4 * k;
     const int n_stages = ny >> 1;
     const int gthreads = 32 * G.nstrips;            // threads of one sample group (= 2 nx)
