@@ -71,6 +71,28 @@ __device__ __forceinline__ double lds64(unsigned addr) {
     return v;
 }
 
+// exp_tab16 (vo_grid.cuh) with its nine 64-bit constants read as constant-bank operands of the FP64 instructions instead
+// of being re-materialised into registers (two moves each) for every row
+__constant__ double kExpK[9] = {23.083120654223414, -0.04332169877307024, -1.1926343307941173e-11,
+                                1.38888888888888888889e-03, 8.33333333333333333333e-03, 4.16666666666666666667e-02,
+                                1.66666666666666666667e-01, 0.5, 1.0};
+__device__ __forceinline__ double exp_tab16c(double x, unsigned tab) {   // tab = shared-memory address of the 2^(j/16) table
+    const double t = fma(x, kExpK[0], 6755399441055744.0);   // 1.5*2^52: low word = rint(16 x / ln2)
+    const int ki = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, kExpK[1], x);
+    r = fma(kd, kExpK[2], r);
+    double p = kExpK[3];
+    p = fma(p, r, kExpK[4]);
+    p = fma(p, r, kExpK[5]);
+    p = fma(p, r, kExpK[6]);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const double v = p * lds64(tab + ((ki << 3) & 0x78));
+    return __hiloint2double(__double2hiint(v) + ((ki << 16) & 0xfff00000), __double2loint(v));
+}
+
 // V[d,m] row-major -> per node row t: [strip q][pair p < 2 NT][lane][2] then [strip q][k][4] (NX = 1 only).
 //   pair p, half h: idx = 2 p + h = jj * NT + tt; lane = 4 n + kk holds V[t*ncol + 16 q + 4 kk + jj][8 tt + n];
 //   extra column: V[t*ncol + 16 q + 4 k + j][8 NT]     (0 outside the matrix)
@@ -122,6 +144,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     unsigned long long *empty_v = full_v + 4;
     double *tab = reinterpret_cast<double *>(empty_v + 4);
     const unsigned sm0 = smem_u32(smem_raw);
+    const unsigned tab32 = smem_u32(tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = warp & (G.nstrips - 1), grp = warp >> G.lognstrips;
@@ -367,7 +390,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hmax = max(hmax, exp_arg_hi(an[j]));
 #pragma unroll
-                for (int j = 0; j < 5; ++j) an[j] = exp_tab16(an[j], tab);
+                for (int j = 0; j < 5; ++j) an[j] = exp_tab16c(an[j], tab32);
                 if (hmax > kExpHiMax) {   // |x| > 700, inf or NaN somewhere in the warp's row (rare): libm exp() on the
                                           // values re-read from shared memory, so the common path keeps no copies
 #pragma unroll
