@@ -459,7 +459,7 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     G.v_off = 0;
     G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128);
     G.stage_bytes = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
-    const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 16 * sizeof(double);
+    const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 18 * sizeof(double);
     // V ring: three 2-row stages when they fit (the sample groups of a CTA may then drift a stage apart), else two
     G.nvs = rho ? 0 : ((fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2);
     {
@@ -513,18 +513,17 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     const int m_arg = rho ? rho_pitch : m;
-#define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV)                                                                        \
+    // a_is_log is a template parameter: with the exp() path compiled in or out, each variant gets its own register
+    // allocation (as a run-time branch the two paths cost each other 4-8 %, measured A/B)
+#define GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, YSV)                                                                \
     {                                                                                                            \
-        auto kern = vo_grid2_kernel<NTV, NXV, RHOV>;                                                             \
+        auto kern = a_is_log ? vo_grid2_kernel<NTV, NXV, RHOV, YSV, true> : vo_grid2_kernel<NTV, NXV, RHOV, YSV, false>; \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
                                         (const double *)Vp, m_arg, r, B));                                       \
     }
-    if (rho && y_stride != pl->dev.d) {
-        auto kern = vo_grid2_kernel<1, 0, true, true>;
-        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride, (const double *)Vp, m_arg, r, B));
-    }
+#define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV) GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, false)
+    if (rho && y_stride != pl->dev.d) GPDE_LAUNCH_GRID2_YS(1, 0, true, true)
     else if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
     else if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)
     else if (NT == 1) GPDE_LAUNCH_GRID2(1, 1, false)
@@ -534,6 +533,7 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     else if (NT == 3) GPDE_LAUNCH_GRID2(3, 1, false)
     else GPDE_LAUNCH_GRID2(4, 0, false)
 #undef GPDE_LAUNCH_GRID2
+#undef GPDE_LAUNCH_GRID2_YS
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
 }

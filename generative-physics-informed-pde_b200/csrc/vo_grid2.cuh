@@ -124,7 +124,7 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
     }
 }
 
-template <int NT, int NX, bool RHO, bool YS = false>
+template <int NT, int NX, bool RHO, bool YS, bool ALOG>
 __global__ void __launch_bounds__(512, 1)
 vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, int a_is_log,
                 const double *__restrict__ y, long long y_stride_arg, const double *__restrict__ g, long long g_stride,
@@ -228,19 +228,22 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     if (n_stages > 1) issue_stage(1, 1);
 
     // packed V rows 2 ts, 2 ts + 1 -> V stage (thread 0 only; v_next = next stage to copy, into slot v_islot)
-    int v_next = 0, v_islot = 0;
-    unsigned v_ipar = 0;             // parity of the next wait on empty_v[v_islot]
+    // (thread 0's bookkeeping lives in shared memory: three registers less for every thread of the kernel)
+    volatile int *vst = reinterpret_cast<volatile int *>(tab + 16);   // [0] v_next, [1] v_islot, [2] v_ipar
+    if (tid == 0) vst[0] = vst[1] = vst[2] = 0;
     auto issue_v = [&]() {
         const unsigned bytes = (unsigned)v_bytes;
+        int v_next = vst[0], v_islot = vst[1];
         mbar_arrive_expect_tx(full_v + v_islot, bytes);
         bulk_g2s(v_base + (size_t)v_islot * v_bytes, reinterpret_cast<const char *>(Vp) + (size_t)(2 * v_next) * G.v_row_bytes,
                  bytes, full_v + v_islot);
         ++v_next;
-        if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) v_ipar ^= 1; }
+        if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) vst[2] = vst[2] ^ 1; }
+        vst[0] = v_next; vst[1] = v_islot;
     };
     if (!RHO && tid == 0) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // the packing kernel's rows (no-op without a dependent launch)
-        while (v_next < G.nvs && v_next < n_stages) issue_v();
+        while (vst[0] < G.nvs && vst[0] < n_stages) issue_v();
     }
 
     // ---- per-lane constants of the consumer
@@ -346,17 +349,12 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
         const unsigned par = (ts >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
         const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
-        const double g0 = gn0, g1 = gn1;
-        if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
-            gn0 = __ldg(gp + 2 * (2 * ts + 3));
-            gn1 = __ldg(gp + 2 * (2 * ts + 4));
-        }
         if (!RHO && tid == 0) {
             // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
-            while (v_next < n_stages && v_next < ts + G.nvs) {
-                if (!mbar_test(empty_v + v_islot, v_ipar)) {
-                    if (v_next > ts) break;
-                    mbar_wait(empty_v + v_islot, v_ipar);
+            while (vst[0] < n_stages && vst[0] < ts + G.nvs) {
+                if (!mbar_test(empty_v + vst[1], (unsigned)vst[2])) {
+                    if (vst[0] > ts) break;
+                    mbar_wait(empty_v + vst[1], (unsigned)vst[2]);
                 }
                 issue_v();
             }
@@ -376,7 +374,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 #pragma unroll
             for (int j = 0; j < 4; ++j) un[j] = lds64(ya + 8 * j);
             unr = lds64(ya + 32);
-            const double gv = rr ? g1 : g0;
+            const double gv = rr ? gn1 : gn0;
             if (is_left) unl = gv;
             if (is_right) un[3] = gv;
             const unsigned aa = sb + (rr ? a_lane1 : a_lane0);
@@ -385,7 +383,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                 an[0] = p0.x; an[1] = p0.y; an[2] = p1.x; an[3] = p1.y;
                 an[4] = lds64(aa + 32);
             }
-            if (a_is_log) {
+            if constexpr (ALOG) {
                 int hmax = exp_arg_hi(an[4]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) hmax = max(hmax, exp_arg_hi(an[j]));
@@ -399,6 +397,10 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
             }
             node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, nullptr,
                      2 * ts + rr);
+        }
+        if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
+            gn0 = __ldg(gp + 2 * (2 * ts + 3));
+            gn1 = __ldg(gp + 2 * (2 * ts + 4));
         }
         __syncwarp();
         if (lane == 0) {
