@@ -459,7 +459,7 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     G.v_off = 0;
     G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128);
     G.stage_bytes = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
-    const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 18 * sizeof(double);
+    const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 258 * sizeof(double);
     // V ring: three 2-row stages when they fit (the sample groups of a CTA may then drift a stage apart), else two
     G.nvs = rho ? 0 : ((fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2);
     {
