@@ -14,8 +14,12 @@
 //   * B fragments two at a time (LDS.128 from a pair-packed V row);
 //   * m = 8 NT + NX: the NX (0 or 1) columns past the last full n-tile go through DFMA with one accumulator per
 //     lane (m = 25: 3 DMMA tiles + 1 DFMA column instead of 4 tiles: -12 % FP64-pipe cycles per node row).
-// Shared memory: 2 stages x (a rows | y rows | packed V rows), zero-initialised once so that the few halo reads
-// that fall outside a sample's rows see finite numbers.
+//   * one a / y ring per sample group (own mbarriers), the packed V rows in a ring of their own; exp() by a 256-entry
+//     2^(j/256) table + degree-4 polynomial with constant-bank coefficients; a_is_log, the rho output and a strided y
+//     are template parameters (the kernel's time follows its instruction count and is sensitive to the register
+//     allocation: every variant gets its own).
+// Shared memory: 2 a/y stages | 2-3 V stages | barriers | exp table; the a/y stages are zero-initialised once so that the
+// few halo reads that fall outside a sample's rows see finite numbers.
 #pragma once
 
 namespace gpde {
