@@ -394,7 +394,7 @@ static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (pl->tps) {
-        auto kern = pl->dev.hbw == 3 ? rom_tps_forward_kernel<T, 15, 3> : rom_tps_forward_kernel<T, 15, 4>;
+        auto kern = rom_tps_forward_kernel<T, 15, 3>;
         const size_t smem = tps_smem_forward(pl->dev);
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, F, u, factor, info, B);
@@ -417,7 +417,7 @@ static int rom_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (pl->tps) {
-        auto kern = pl->dev.hbw == 3 ? rom_tps_adjoint_kernel<T, 15, 3> : rom_tps_adjoint_kernel<T, 15, 4>;
+        auto kern = rom_tps_adjoint_kernel<T, 15, 3>;
         const size_t smem = tps_smem_adjoint(pl->dev);
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, u, factor, gbar, gradX, gradF, B);
@@ -605,13 +605,14 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
     pl->lanes = pairs <= 8 ? 8 : (pairs <= 16 ? 16 : 32);
     pl->n_contrib = (int)band_elem.size();
     // thread-per-sample kernels (rom_tps.cuh): instantiated for the reference's 4x4 coarse mesh (15 free dofs, half
-    // bandwidth 3 in this package's x-fastest numbering, 4 allowed for other numberings).  MEASURED SLOWER than the
+    // bandwidth 3 in this package's x-fastest numbering; the half-bandwidth-4 instantiations were dropped: they doubled this
+    // file's compile time for a path that is opt-in and slower).  MEASURED SLOWER than the
     // cooperative kernels on B200 (B = 4096: 51 + 39 us vs 18.5 + 15.3 us, only 32 CTAs; B = 131072: 248 M vs
     // 415 M solves/s, 8 resident warps per SM of serial FP64 chains), so they are opt-in: GPDE_ROM_PATH=tps.
     // Decided once per plan: it fixes the factor layout.
     {
         const char *e = getenv("GPDE_ROM_PATH");
-        pl->tps = (nf == 15 && (hbw == 3 || hbw == 4) && tps_smem_adjoint(D) <= 227 * 1024 && e && strcmp(e, "tps") == 0) ? 1 : 0;
+        pl->tps = (nf == 15 && hbw == 3 && tps_smem_adjoint(D) <= 227 * 1024 && e && strcmp(e, "tps") == 0) ? 1 : 0;
     }
     // per-sample scratch; with 8 lanes per sample a 64-bit shared-memory wavefront serves two samples, so the pitch is
     // padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint halves of the banks
