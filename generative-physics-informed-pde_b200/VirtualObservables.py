@@ -675,7 +675,15 @@ class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
         """r[N,m] = V^T (K_fom(x_n) y~_n - f) for all data points in ONE launch; V [d,m] is a weighting
         matrix shared by the ensemble (e.g. V = W of the coarse-grained-residual sampler)."""
         plan, X, G = self._inputs()
-        return plan.residual(X, Y.to(_F64), G, _as_f64(V, self.device))
+        Vd = _as_f64(V, self.device)
+        # the weighting matrix of a sampler stays the same tensor between resample() calls (V = W of the
+        # coarse-grained-residual sampler, VirtualObservables.py:297-321): pack it once, keyed by storage and version
+        key = (Vd.data_ptr(), Vd._version, tuple(Vd.shape), int(Y.shape[0]))
+        cached = getattr(self, "_packed_weights", None)
+        if cached is None or cached[0] != key:
+            cached = (key, plan.pack_weights(Vd, int(Y.shape[0])))
+            self._packed_weights = cached
+        return plan.residual(X, Y.to(_F64), G, cached[1])
 
     def residual_gradients(self, S, V):
         """q[N,d] = K_ff(x_n) V s_n for all data points in one launch (S [N,m])."""

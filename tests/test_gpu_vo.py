@@ -119,6 +119,12 @@ def test_gamma_alpha_and_posterior_update_against_reference_vectors(name, dev):
     # all residuals of the ensemble in one launch
     r = ens.residuals(torch.tensor(g['in_Y'], device=dev), V)
     assert rel_err(r.cpu(), g['out_residual']) < 1e-10
+    # the ensemble keeps V packed between calls (same tensor, same version) and repacks after an in-place change
+    assert torch.equal(ens.residuals(torch.tensor(g['in_Y'], device=dev), V), r)
+    if torch.is_tensor(V) and V.dtype == torch.float64 and V.is_cuda:
+        V.mul_(2.0)
+        assert rel_err(ens.residuals(torch.tensor(g['in_Y'], device=dev), V).cpu(), 2.0 * g['out_residual']) < 1e-10
+        V.mul_(0.5)
 
 
 def test_reference_style_construction_and_samplers(dev):
