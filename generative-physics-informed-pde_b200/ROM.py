@@ -52,8 +52,9 @@ def _launch_forward(plan, X, F, x_is_log, want_factor=True, info=None):
     u = torch.empty((B, plan.n), dtype=X.dtype, device=X.device)
     factor = torch.empty((B, plan.factor_doubles), dtype=torch.float64, device=X.device) if want_factor else None
     fn = getattr(lib, "gpde_rom_forward_" + sfx)
-    rc = fn(plan.handle, _lib.ptr(X), int(bool(x_is_log)), _lib.ptr(F), _lib.ptr(u), _lib.ptr(factor),
-            _lib.ptr(info), B, _lib.stream_of(X.device))
+    dev = plan.device
+    rc = fn(plan.handle, _lib.ptr(X, dev), int(bool(x_is_log)), _lib.ptr(F, dev), _lib.ptr(u, dev), _lib.ptr(factor, dev),
+            _lib.ptr(info, dev), B, _lib.stream_of(dev))
     _lib.check(rc, "gpde_rom_forward_" + sfx)
     return u, factor
 
@@ -64,8 +65,9 @@ def _launch_adjoint(plan, X, u, factor, gbar, x_is_log, want_gradF=True):
     gX = torch.empty_like(X)
     gF = torch.empty((B, plan.n), dtype=X.dtype, device=X.device) if want_gradF else None
     fn = getattr(lib, "gpde_rom_adjoint_" + sfx)
-    rc = fn(plan.handle, _lib.ptr(X), int(bool(x_is_log)), _lib.ptr(u), _lib.ptr(factor), _lib.ptr(gbar),
-            _lib.ptr(gX), _lib.ptr(gF), B, _lib.stream_of(X.device))
+    dev = plan.device
+    rc = fn(plan.handle, _lib.ptr(X, dev), int(bool(x_is_log)), _lib.ptr(u, dev), _lib.ptr(factor, dev), _lib.ptr(gbar, dev),
+            _lib.ptr(gX, dev), _lib.ptr(gF, dev), B, _lib.stream_of(dev))
     _lib.check(rc, "gpde_rom_adjoint_" + sfx)
     return gX, gF
 
@@ -214,8 +216,8 @@ class ROM(object):
             x64 = x64.unsqueeze(0)
         B = x64.shape[0]
         K = torch.empty((plan.n, plan.n, B), dtype=torch.float64, device=x64.device)
-        rc = plan._lib.gpde_rom_stiffness_f64(plan.handle, _lib.ptr(x64), _lib.ptr(K), int(bool(DirichletBC)), B,
-                                              _lib.stream_of(x64.device))
+        rc = plan._lib.gpde_rom_stiffness_f64(plan.handle, _lib.ptr(x64, plan.device), _lib.ptr(K, plan.device),
+                                              int(bool(DirichletBC)), B, _lib.stream_of(plan.device))
         _lib.check(rc, "gpde_rom_stiffness_f64")
         return K.to(x.dtype)
 

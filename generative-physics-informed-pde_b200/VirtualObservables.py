@@ -19,6 +19,7 @@ VirtualObservablesEnsemble(.update/.mean/.vars/.logsigma/.resample/.N/.m/.dim_ou
 schedules.  Flux test functions (bottleneck/flux.py) need UFL facet integrals and stay out of scope.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -37,9 +38,10 @@ def _as_f64(value, device):
 class VoPlan(object):
     """One gpde_vo_plan: fine-mesh element data and the Dirichlet map, resident on a device."""
 
-    def __init__(self, physics, device, cell_to_input=None, n_inputs=None, load=None):
+    def __init__(self, physics, device, cell_to_input=None, n_inputs=None, load=None, experiment=None):
         self._lib = _lib.load()
         self.device = _lib.require_cuda(device, "virtual observables")
+        self._ctor = (physics, cell_to_input, n_inputs, load)
         mesh = physics.mesh
         if cell_to_input is None:
             cell_to_input, n_inputs = np.arange(mesh.num_cells), mesh.num_cells
@@ -54,9 +56,20 @@ class VoPlan(object):
             host["load"] = np.ascontiguousarray(load, dtype=np.float64)
         p = {k: v.ctypes.data_as(ctypes.c_void_p) for k, v in host.items()}
         self.handle = ctypes.c_void_p()
-        rc = self._lib.gpde_vo_plan_create(ctypes.byref(self.handle), mesh.num_nodes, mesh.num_cells, p["cells"],
-                                           p["Ke"], p["c2i"], int(n_inputs), p["free"], host["free"].size, p["bc"],
-                                           host["bc"].size, p.get("load"), self.device.index)
+        # the library reads its experiment switches (GPDE_* environment variables, A/B runs of the kernel families) ONCE,
+        # here; ``experiment`` sets them for this plan only
+        saved = {k: os.environ.get(k) for k in (experiment or {})}
+        os.environ.update({k: str(v) for k, v in (experiment or {}).items()})
+        try:
+            rc = self._lib.gpde_vo_plan_create(ctypes.byref(self.handle), mesh.num_nodes, mesh.num_cells, p["cells"],
+                                               p["Ke"], p["c2i"], int(n_inputs), p["free"], host["free"].size, p["bc"],
+                                               host["bc"].size, p.get("load"), self.device.index)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
         _lib.check(rc, "gpde_vo_plan_create")
         info = (ctypes.c_int64 * 8)()
         _lib.check(self._lib.gpde_vo_plan_info(self.handle, info), "gpde_vo_plan_info")
@@ -71,6 +84,11 @@ class VoPlan(object):
                 self._lib.gpde_vo_plan_destroy(handle)
             except Exception:
                 pass
+
+    def variant(self, **experiment):
+        """A second plan on the same mesh data with experiment switches (tests and A/B timing runs)."""
+        physics, c2i, n_in, load = self._ctor
+        return VoPlan(physics, self.device, c2i, n_in, load, experiment=experiment)
 
     @classmethod
     def cached(cls, physics, device, pixel_input=False):
@@ -113,8 +131,8 @@ class VoPlan(object):
             buf = out.buf
         else:
             buf = torch.empty(need, dtype=torch.uint8, device=self.device)
-        rc = self._lib.gpde_vo_pack_weights_f64(self.handle, _lib.ptr(Vc), m, 1 if ignore_load else 0, _lib.ptr(buf),
-                                                _lib.stream_of(Vc.device))
+        rc = self._lib.gpde_vo_pack_weights_f64(self.handle, _lib.ptr(Vc, self.device), m, 1 if ignore_load else 0,
+                                                _lib.ptr(buf, self.device), _lib.stream_of(self.device))
         if rc == 1:
             return Vc
         _lib.check(rc, "gpde_vo_pack_weights_f64")
@@ -128,7 +146,10 @@ class VoPlan(object):
         Returns r, or (r, rho) when want_rho / V is None."""
         dt = a.dtype
         sfx = _lib.suffix(dt)
-        B = y.shape[0] if y is not None else (a.shape[0] if a.dim() == 2 else 1)
+        sizes = [t.shape[0] for t in (y, a, g) if t is not None and t.dim() == 2]
+        B = sizes[0] if sizes else 1
+        if any(n != B for n in sizes):   # e.g. a shared 1-D field with y = None and a batched g: every batched argument counts
+            raise ValueError("inconsistent batch sizes %r among a, y, g" % (sizes,))
         a = a.contiguous()
         packed = None
         if isinstance(V, PackedWeights):
@@ -145,10 +166,11 @@ class VoPlan(object):
         rho = a.new_empty((B, self.d)) if (want_rho or not m) else None
         fn = getattr(self._lib, "gpde_vo_residual_" + sfx)
         ws = packed.buf if packed is not None else (self._workspace(B, m) if m else None)
-        rc = fn(self.handle, _lib.ptr(a), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(y),
-                _lib.ptr(g), (self.n_bc if g.dim() == 2 else 0) if g is not None else 0, _lib.ptr(Vc), m,
-                _lib.ptr(r), _lib.ptr(rho), _lib.ptr(ws) if m else None,
-                (1 if ignore_load else 0) | (2 if packed is not None else 0), B, _lib.stream_of(a.device))
+        dev = self.device
+        rc = fn(self.handle, _lib.ptr(a, dev), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(y, dev),
+                _lib.ptr(g, dev), (self.n_bc if g.dim() == 2 else 0) if g is not None else 0, _lib.ptr(Vc, dev), m,
+                _lib.ptr(r, dev), _lib.ptr(rho, dev), _lib.ptr(ws, dev) if m else None,
+                (1 if ignore_load else 0) | (2 if packed is not None else 0), B, _lib.stream_of(dev))
         _lib.check(rc, "gpde_vo_residual_" + sfx)
         return (r, rho) if rho is not None else r
 
@@ -160,10 +182,54 @@ class VoPlan(object):
         B, m = s.shape
         q = a.new_empty((B, self.d))
         fn = getattr(self._lib, "gpde_vo_residual_T_" + sfx)
-        rc = fn(self.handle, _lib.ptr(a), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(Vc), m,
-                _lib.ptr(s), _lib.ptr(q), _lib.ptr(self._workspace(B, m)), B, _lib.stream_of(a.device))
+        dev = self.device
+        rc = fn(self.handle, _lib.ptr(a, dev), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(Vc, dev), m,
+                _lib.ptr(s, dev), _lib.ptr(q, dev), _lib.ptr(self._workspace(B, m), dev), B, _lib.stream_of(dev))
         _lib.check(rc, "gpde_vo_residual_T_" + sfx)
         return q
+
+
+    def _weights_arg(self, V):
+        """(contiguous float64 V, v_stride): [d,m] shared by the data points or [N,d,m] one matrix per data point."""
+        V = V.to(torch.float64).contiguous()
+        if V.dim() == 2:
+            return V, 0, int(V.shape[1])
+        assert V.dim() == 3 and V.shape[1] == self.d
+        return V, int(V.shape[1] * V.shape[2]), int(V.shape[2])
+
+    def posterior(self, a, V, rho, noise_var, g, prec, info=None):
+        """Gaussian conditioning of N data points in ONE launch, matrix-free (gpde_vo_posterior_f64):
+        (mean [N,d], vars [N,d]) of N(g, diag(1/prec)) given Gamma y = alpha + eps, eps ~ N(0, diag(noise_var)), with
+        Gamma^T = K_ff(a_n) V_n never stored.  a: conductivities [N,n_inputs] (or one shared field), rho [N,d] the fine
+        residual of the prior mean (``residual(a, g, g_bc, None)``), V [d,m] or [N,d,m]."""
+        dev = self.device
+        N = int(g.shape[0])
+        a = a.to(torch.float64).contiguous()
+        V, v_stride, m = self._weights_arg(V)
+        rho, g, prec = (t.to(torch.float64).contiguous() for t in (rho, g, prec))
+        noise_var = noise_var.to(torch.float64).contiguous()
+        mean, vars_ = torch.empty_like(g), torch.empty_like(g)
+        rc = self._lib.gpde_vo_posterior_f64(self.handle, _lib.ptr(a, dev), self.n_inputs if a.dim() == 2 else 0,
+                                             _lib.ptr(V, dev), v_stride, m, _lib.ptr(rho, dev), _lib.ptr(noise_var, dev),
+                                             _lib.ptr(g, dev), _lib.ptr(prec, dev), _lib.ptr(mean, dev), _lib.ptr(vars_, dev),
+                                             _lib.ptr(info, dev), N, _lib.stream_of(dev))
+        _lib.check(rc, "gpde_vo_posterior_f64")
+        return mean, vars_
+
+    def moments(self, a, V, rho, v):
+        """(r [N,m], s2 [N,m]) = (V_n^T rho_n, sum_i Gamma_n[:,i]^2 v[n,i]) for all data points in one launch
+        (gpde_vo_moments_f64): the two terms of the precision hyper-update (VirtualObservables.py:985-990)."""
+        dev = self.device
+        N = int(rho.shape[0])
+        a = a.to(torch.float64).contiguous()
+        V, v_stride, m = self._weights_arg(V)
+        rho, v = rho.to(torch.float64).contiguous(), v.to(torch.float64).contiguous()
+        out_r, out_s2 = rho.new_empty((N, m)), rho.new_empty((N, m))
+        rc = self._lib.gpde_vo_moments_f64(self.handle, _lib.ptr(a, dev), self.n_inputs if a.dim() == 2 else 0,
+                                           _lib.ptr(V, dev), v_stride, m, _lib.ptr(rho, dev), _lib.ptr(v, dev),
+                                           _lib.ptr(out_r, dev), _lib.ptr(out_s2, dev), N, _lib.stream_of(dev))
+        _lib.check(rc, "gpde_vo_moments_f64")
+        return out_r, out_s2
 
 
 class PackedWeights(object):
@@ -307,6 +373,7 @@ class BaseSampler(object):
     precision_mask: -1 = infinite precision, +1 = learnable (VirtualObservables.py:120-168)."""
 
     is_constant = False
+    provides_V = True     # False: the sampler only has (Gamma, alpha) (flux constraints); the ensemble then conditions densely
 
     def __init__(self, qp):
         self._qp = qp
@@ -376,14 +443,16 @@ class CoarseGrainedResidualSampler(BaseSampler):
 
     def __init__(self, qp, W):
         super().__init__(qp)
-        self._W = W
-        self._cached = qp.weak_galerkin_on_device(W)
-        self.m = int(self._cached[1].numel())
+        self._W = W          # numpy [d,n] or ONE float64 device tensor shared by the samplers of all data points
+        self._cached = None
+        self.m = int(W.shape[1])
 
     def _sample(self):
         return self._W
 
     def sample(self):
+        if self._cached is None:   # dense (Gamma, alpha) only when somebody asks for them
+            self._cached = self.qp.weak_galerkin_on_device(self._W)
         return self._cached
 
 
@@ -397,7 +466,32 @@ class ConcatenatedSamplers(BaseSampler):
     qp = property(lambda self: self._samplers[0].qp)
     m = property(lambda self: sum(s.m for s in self._samplers))
     is_constant = property(lambda self: all(s.is_constant for s in self._samplers))
+    provides_V = property(lambda self: all(s.provides_V for s in self._samplers))
     precision_mask = property(lambda self: np.concatenate([s.precision_mask for s in self._samplers]))
+
+    def sample(self):
+        """(Gamma, alpha) of every member stacked (VirtualObservables.py:283-294).  Constant members (V = W, flux
+        constraints) return their cached pair; the others share ONE pass of the residual kernels over their columns."""
+        if any(isinstance(s, FluxConstrainSampler) for s in self._samplers) or any(s.is_constant for s in self._samplers):
+            pairs = []
+            fresh = [s for s in self._samplers if not s.is_constant]
+            fresh_pair = None
+            if fresh:
+                Vs = [s.sample_V() for s in fresh]
+                dev = next((p.device for p in Vs if isinstance(p, torch.Tensor)), None)
+                V = torch.cat([_as_f64(p, dev) for p in Vs], dim=1) if dev is not None else np.hstack(Vs)
+                fresh_pair = self.qp.weak_galerkin_on_device(V)
+            lo = 0
+            for s in self._samplers:
+                if s.is_constant:
+                    pairs.append(s.sample())
+                else:
+                    pairs.append((fresh_pair[0][lo:lo + s.m], fresh_pair[1][lo:lo + s.m]))
+                    lo += s.m
+            dev = pairs[0][0].device
+            return (torch.cat([_as_f64(G, dev) for G, _ in pairs], dim=0),
+                    torch.cat([_as_f64(al, dev).reshape(-1) for _, al in pairs], dim=0))
+        return self.qp.weak_galerkin_on_device(self._sample())
 
     def _sample(self):
         parts = [s.sample_V() for s in self._samplers]
@@ -413,6 +507,7 @@ class FluxConstrainSampler(BaseSampler):
     are, constant, learnable precision (VirtualObservables.py:323-349)."""
 
     is_constant = True
+    provides_V = False
 
     def __init__(self, qp, FluxConstrain):
         super().__init__(qp=qp)
@@ -435,17 +530,27 @@ class FluxConstrainSampler(BaseSampler):
 
 # ======================================================================================= linear query
 class LinearQuerry(object):
-    """Holds Gamma [m,d], Gamma^T and alpha [m] of one data point as float64 device tensors
-    (VirtualObservables.py:353-447)."""
+    """Gamma [m,d], Gamma^T and alpha [m] of one data point as float64 device tensors (VirtualObservables.py:353-447).
+
+    What is KEPT is the weighting matrix V [d,m] of the sampler; the dense Gamma = V^T K / alpha = V^T f are produced by the
+    residual kernels the first time somebody reads them (the ensemble's batched update never does: it works on V)."""
 
     def __init__(self, querry_point, sampler, dtype, device):
         self._querry_point, self._sampler = querry_point, sampler
         self.dtype, self.device = dtype, device
         self._store = {}
+        self._V = None
         self.resample(ForceResample=True)
+
+    def _materialise(self):
+        if "Gamma" not in self._store:
+            if self._V is None:
+                raise RuntimeError("LinearQuerry holds neither V nor (Gamma, alpha)")
+            self._set(*self._querry_point.weak_galerkin_on_device(self._V, device=self.device))
 
     def _f64_slot(name):
         def get(self):
+            self._materialise()
             return self._store.get(name)
 
         def put(self, value):
@@ -458,21 +563,29 @@ class LinearQuerry(object):
     alpha = _f64_slot("alpha")
     del _f64_slot
 
-    m = property(lambda self: self.Gamma.shape[0], doc="number of virtual observables")
-    dim_out = property(lambda self: self.Gamma.shape[1])
+    V = property(lambda self: self._V, doc="weighting matrix [d,m] (None for samplers that only provide Gamma, alpha)")
+    m = property(lambda self: int(self._V.shape[1]) if self._V is not None else self.Gamma.shape[0],
+                 doc="number of virtual observables")
+    dim_out = property(lambda self: int(self._V.shape[0]) if self._V is not None else self.Gamma.shape[1])
     precision_mask = property(lambda self: self._sampler.precision_mask)
 
     def _set(self, Gamma, alpha):
-        self.Gamma = _as_f64(Gamma, self.device)
-        self.alpha = _as_f64(alpha, self.device)
-        self.GammaTransposed = self.Gamma.t()
+        self._store["Gamma"] = _as_f64(Gamma, self.device)
+        self._store["alpha"] = _as_f64(alpha, self.device)
+        self._store["GammaTransposed"] = self._store["Gamma"].t()
 
     def resample(self, ForceResample=False):
         if ForceResample or not self._sampler.is_constant:
-            self._set(*self._sampler())
+            self._store.clear()
+            if getattr(self._sampler, "provides_V", True):
+                self._V = _as_f64(self._sampler.sample_V(), self.device)
+            else:
+                self._V = None
+                self._set(*self._sampler())
 
     def temporary_set_galerkin_manually(self, V):
-        self._set(*self._querry_point.weak_galerkin_on_device(V, device=self.device))
+        self._V = _as_f64(V, self.device)
+        self._store.clear()
         self.precision = -torch.ones(self.m, dtype=torch.double, device=self.device)
 
 
@@ -513,11 +626,12 @@ class QuerryEnsemble(object):
         if N_rbf > 0:
             assert l_rbf is not None
         querries = []
+        W_dev = _as_f64(W, device)      # ONE device copy of W shared by the samplers of all data points
         for qp in QuerryPointEnsemble:
             qp._device = device
             parts = []
             if CGR:
-                parts.append(CoarseGrainedResidualSampler(qp, W))
+                parts.append(CoarseGrainedResidualSampler(qp, W_dev))
             if N_gaussian > 0:
                 parts.append(GaussianSketchingSampler(qp, N_gaussian))
             if N_rbf > 0:
@@ -546,10 +660,19 @@ class VirtualObservable(BaseVirtualObservable):
         assert isinstance(querry, LinearQuerry)
         self._querry = querry
         self._mean = self._vars = self._noise = None
+        # member of a VirtualObservablesEnsemble: its batched update keeps the posterior of ALL data points in two [N,d]
+        # tensors; this object reads its row from there unless it has been updated on its own since (generation counter)
+        self._ens, self._k, self._own_gen = None, -1, -1
+
+    def _posterior_row(self, which):
+        ens = self._ens
+        if ens is not None and ens._post is not None and self._own_gen != ens._post_gen:
+            return ens._post[which][self._k]
+        return self._mean if which == 0 else self._vars
 
     querry = property(lambda self: self._querry)
-    mean = property(lambda self: self._mean)
-    vars = property(lambda self: self._vars)
+    mean = property(lambda self: self._posterior_row(0))
+    vars = property(lambda self: self._posterior_row(1))
     m = property(lambda self: self._querry.m)
 
     @property
@@ -566,6 +689,10 @@ class VirtualObservable(BaseVirtualObservable):
 
     def _set_posterior(self, mean, vars_):
         self._mean, self._vars = mean, vars_
+        if self._ens is not None:
+            self._own_gen = self._ens._post_gen
+            self._ens._members_dirty = True
+            self._ens.flush_cache()
 
     @torch.no_grad()
     def update(self, g, prec, iteration, *, ForceUpdate=False):
@@ -631,11 +758,19 @@ class BaseVirtualObservablesEnsemble(object):
 
 
 class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
-    """VirtualObservables.py:908-998, batched: ``update`` conditions all N data points together and
-    ``residuals`` evaluates all N residual vectors in one kernel launch."""
+    """VirtualObservables.py:908-998 with every loop over the data points replaced by a launch over all of them:
 
-    # per-chunk budget for the stacked Gamma [n,m,d] used by the batched conditioning
+      update               rho(G) -> gpde_vo_posterior_f64          (2 launches; the reference: N x [3 einsum + cholesky + ...])
+      update_vo_precision  rho(mean) -> gpde_vo_moments_f64 -> sum  (2 launches + one [N,m] reduction)
+      residuals            one residual launch
+
+    all matrix-free on the samplers' weighting matrices V (no dense Gamma [N,m,d]).  Ensembles that contain samplers
+    without a weighting matrix (flux constraints) or more than 64 virtual observables per data point condition densely
+    (``condition_gaussian``: torch / cuBLAS / cuSOLVER), chunked by ``max_stack_bytes``."""
+
+    # per-chunk budget for the stacked Gamma [n,m,d] of the dense route
     max_stack_bytes = 1 << 30
+    max_kernel_m = 64
 
     def __init__(self, QuerryPointEnsemble, QuerryEnsemble, dtype, device):
         vos = [VirtualObservable(q, qp, dtype=dtype, device=device) for q, qp in zip(QuerryEnsemble, QuerryPointEnsemble)]
@@ -650,6 +785,10 @@ class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
         self._set_member_variance_values(self._mean_vo_variances)
         self._precision_initialized = False
         self._resident = None
+        self._post, self._post_gen, self._members_dirty = None, 0, False
+        self._info = None
+        for k, vo in enumerate(self._virtual_observables):
+            vo._ens, vo._k = self, k
 
     infinite_precision_mask = property(lambda self: self._infinite_precision_mask)
     fixed_precision = property(lambda self: bool(self._infinite_precision_mask.all().item()))
@@ -661,49 +800,123 @@ class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
 
     def _set_member_variance_values(self, mean_vo_vars):
         for vo in self._virtual_observables:
-            vo.vo_variances = mean_vo_vars
+            vo._noise = mean_vo_vars
+
+    def _stacked(self, what):
+        # posterior of all data points straight from the batched update unless a member was updated on its own since
+        if self._post is not None and not self._members_dirty and what in ("mean", "vars"):
+            return self._post[0 if what == "mean" else 1].to(dtype=self.dtype).detach()
+        return super()._stacked(what)
 
     # -- device-resident inputs of the whole ensemble -------------------------------------------
     def _inputs(self):
+        """(plan, conductivities a[N,*], Dirichlet values g[N,n_bc]) of all data points, resident on the device.
+
+        The fields of the data points never change, so exp(x) is taken ONCE here (the reference likewise evaluates
+        np.exp(x) once per QuerryPoint when it assembles and caches K, VirtualObservables.py:52-59) and every
+        residual launch runs with a_is_log = 0.  When the DG0 fields come from images (both cells of a pixel carry
+        the same value, bottleneck/utils.py:123-129) the per-pixel layout and the structured-grid kernels are used."""
         if self._resident is None:
             qpe = self._QuerryPointEnsemble
-            plan = VoPlan.cached(qpe[0].physics, self.device)
-            self._resident = (plan, qpe.X(_F64, self.device), qpe.dirichlet_values(_F64, self.device))
+            physics = qpe[0].physics
+            X = np.stack([qp.x for qp in qpe])
+            plan, field = None, X
+            try:
+                pix = physics.mesh.pixel_of_cell()
+                img = np.empty((X.shape[0], physics.mesh.nx * physics.mesh.ny))
+                img[:, pix] = X
+                if np.array_equal(img[:, pix], X):
+                    plan, field = VoPlan.cached(physics, self.device, pixel_input=True), img
+            except Exception:   # noqa: BLE001 -- not a pixel mesh: per-cell input
+                plan = None
+            if plan is None:
+                plan = VoPlan.cached(physics, self.device)
+            a = torch.exp(_as_f64(field, self.device))
+            self._resident = (plan, a, qpe.dirichlet_values(_F64, self.device))
         return self._resident
+
+    def _weights(self):
+        """Weighting matrices of the data points for the batched kernels: one shared [d,m] tensor (every LinearQuerry holds
+        the SAME tensor: V = W of the coarse-grained-residual sampler) or the stack [N,d,m]; None when some data point has
+        no weighting matrix or m exceeds the kernels' limit (dense route).  The stack is rebuilt after resample()."""
+        Vs = [vo.querry.V for vo in self._virtual_observables]
+        if any(v is None for v in Vs) or Vs[0].shape[1] > self.max_kernel_m:
+            return None
+        if all(v is Vs[0] for v in Vs):
+            return Vs[0]
+        key = tuple((v.data_ptr(), v._version) for v in Vs)
+        cached = getattr(self, "_stacked_V", None)
+        if cached is None or cached[0] != key:
+            cached = (key, Vs, torch.stack(Vs))        # (holds the members: their addresses cannot be recycled under the key)
+            self._stacked_V = cached
+        return cached[2]
+
+    def _shared_weights(self, V, B):
+        """V as the residual kernels take it.  A contiguous float64 tensor on this device is packed once and the packed
+        copy reused while it stays the same tensor at the same version (V = W of the coarse-grained-residual sampler only
+        changes at resample(), VirtualObservables.py:297-321); the cache holds a reference to exactly that tensor, so its
+        address cannot be recycled under the key.  Anything else (numpy, other dtype / device, strided) is converted and
+        packed inside the call, every call."""
+        plan = self._inputs()[0]
+        if not (isinstance(V, torch.Tensor) and V.dtype == _F64 and V.is_cuda and V.device == plan.device and V.is_contiguous()):
+            return _as_f64(V, self.device)
+        key = (V.data_ptr(), V._version, tuple(V.shape), int(B))
+        cached = getattr(self, "_packed_weights", None)
+        if cached is None or cached[0] != key or cached[1] is not V:
+            cached = (key, V, plan.pack_weights(V, int(B)))
+            self._packed_weights = cached
+        return cached[2]
 
     def residuals(self, Y, V):
         """r[N,m] = V^T (K_fom(x_n) y~_n - f) for all data points in ONE launch; V [d,m] is a weighting
         matrix shared by the ensemble (e.g. V = W of the coarse-grained-residual sampler)."""
-        plan, X, G = self._inputs()
-        Vd = _as_f64(V, self.device)
-        # the weighting matrix of a sampler stays the same tensor between resample() calls (V = W of the
-        # coarse-grained-residual sampler, VirtualObservables.py:297-321): pack it once, keyed by storage and version
-        key = (Vd.data_ptr(), Vd._version, tuple(Vd.shape), int(Y.shape[0]))
-        cached = getattr(self, "_packed_weights", None)
-        if cached is None or cached[0] != key:
-            cached = (key, plan.pack_weights(Vd, int(Y.shape[0])))
-            self._packed_weights = cached
-        return plan.residual(X, Y.to(_F64), G, cached[1])
+        plan, a, G = self._inputs()
+        return plan.residual(a, _as_f64(Y, self.device), G, self._shared_weights(V, Y.shape[0]), a_is_log=False)
 
     def residual_gradients(self, S, V):
         """q[N,d] = K_ff(x_n) V s_n for all data points in one launch (S [N,m])."""
-        plan, X, _ = self._inputs()
-        return plan.residual_T(X, _as_f64(V, self.device), S.to(_F64))
+        plan, a, _ = self._inputs()
+        return plan.residual_T(a, _as_f64(V, self.device), _as_f64(S, self.device), a_is_log=False)
+
+    def _fine_residual(self, Y):
+        """rho[N,d] = (K_fom(a_n) y~_n - f)_free of all data points: one rho-only residual launch."""
+        plan, a, gbc = self._inputs()
+        _, rho = plan.residual(a, Y, gbc, None, a_is_log=False)
+        return rho
+
+    def check(self):
+        """Reads and clears the device info word of the batched update; raises if some Lambda_n was not positive definite
+        (torch.cholesky raises at the same point of the reference, VirtualObservables.py:658)."""
+        if self._info is not None:
+            flag = int(self._info.item())
+            if flag:
+                self._info.zero_()
+                raise RuntimeError("virtual-observable update: Lambda = Gamma C Gamma^T + Sigma is not positive definite")
 
     @torch.no_grad()
     def update(self, G, PREC, iteration, writer=None):
         self.update_vo_precision(iteration, writer)
-        vos = self._virtual_observables
-        per = 8 * self.m * self.dim_out
-        step = max(1, int(self.max_stack_bytes // max(per, 1)))
-        for lo in range(0, self.N, step):
-            chunk = vos[lo:lo + step]
-            Gam = torch.stack([vo.querry.Gamma for vo in chunk])
-            alp = torch.stack([vo.querry.alpha for vo in chunk])
-            mean, vars_ = condition_gaussian(Gam, alp, self._mean_vo_variances, G[lo:lo + step].to(_F64),
-                                             PREC[lo:lo + step].to(_F64))
-            for k, vo in enumerate(chunk):
-                vo._set_posterior(mean[k], vars_[k])
+        G64, P64 = _as_f64(G, self.device), _as_f64(PREC, self.device)
+        V = self._weights()
+        if V is not None:
+            plan, a, _ = self._inputs()
+            if self._info is None:
+                self._info = torch.zeros(1, dtype=torch.int32, device=self.device)
+            mean, vars_ = plan.posterior(a, V, self._fine_residual(G64), self._mean_vo_variances, G64, P64, info=self._info)
+            self._post, self._members_dirty = (mean, vars_), False
+            self._post_gen += 1
+        else:
+            vos = self._virtual_observables
+            per = 8 * self.m * self.dim_out
+            step = max(1, int(self.max_stack_bytes // max(per, 1)))
+            self._post = None
+            for lo in range(0, self.N, step):
+                chunk = vos[lo:lo + step]
+                Gam = torch.stack([vo.querry.Gamma for vo in chunk])
+                alp = torch.stack([vo.querry.alpha for vo in chunk])
+                mean, vars_ = condition_gaussian(Gam, alp, self._mean_vo_variances, G64[lo:lo + step], P64[lo:lo + step])
+                for k, vo in enumerate(chunk):
+                    vo._set_posterior(mean[k], vars_[k])
         self.flush_cache()
 
     @torch.no_grad()
@@ -715,10 +928,17 @@ class VirtualObservablesEnsemble(BaseVirtualObservablesEnsemble):
             raise RuntimeError
         if self.fixed_precision:
             return
-        beta = torch.zeros(self.m, dtype=torch.double, device=self.device)
-        for vo in self._virtual_observables:   # VirtualObservables.py:985-990
-            Gam = vo.querry.Gamma
-            beta += (Gam @ vo.mean - vo.querry.alpha) ** 2 + (Gam ** 2) @ vo.vars
+        V = self._weights()
+        if V is not None:     # VirtualObservables.py:985-990 for all data points: two launches and one reduction
+            plan, a, _ = self._inputs()
+            mean, vars_ = _as_f64(self._stacked("mean"), self.device), _as_f64(self._stacked("vars"), self.device)
+            r, s2 = plan.moments(a, V, self._fine_residual(mean), vars_)
+            beta = (r * r + s2).sum(dim=0)
+        else:
+            beta = torch.zeros(self.m, dtype=torch.double, device=self.device)
+            for vo in self._virtual_observables:
+                Gam = vo.querry.Gamma
+                beta += (Gam @ vo.mean - vo.querry.alpha) ** 2 + (Gam ** 2) @ vo.vars
         self._prec_beta = 0.5 * beta + self._beta_0
         self._mean_vo_variances = self._get_mean_vo_variances()
         self._set_member_variance_values(self._mean_vo_variances)

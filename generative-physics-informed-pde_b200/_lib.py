@@ -50,6 +50,8 @@ SIGNATURES = {
     "gpde_vo_residual_f32": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_vp, c_i32, c_vp, c_vp,
                                      c_vp, c_i32, c_i64, c_vp]),
     "gpde_vo_pack_weights_f64": (c_i32, [c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "gpde_vo_posterior_f64": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpde_vo_moments_f64": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gpde_vo_residual_T_f64": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gpde_vo_residual_T_f32": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }
@@ -84,10 +86,16 @@ def check(rc, what):
         raise GpdeLibraryError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
 
 
-def ptr(t):
-    """Device/host pointer of a contiguous tensor (or NULL)."""
+def ptr(t, device=None):
+    """Device/host pointer of a contiguous tensor (or NULL).  With ``device`` the tensor must live on that CUDA
+    device: a CPU tensor or a tensor of another GPU would make the kernel dereference a foreign pointer (sticky
+    illegal-address fault); the reference raises a clean torch device-mismatch error in that situation, so do we."""
     if t is None:
         return None
+    if device is not None:
+        if not t.is_cuda or t.device != device:
+            raise RuntimeError("Expected all tensors to be on the same device, but found a tensor on %s "
+                               "(the physics-layer plan lives on %s)" % (t.device, device))
     assert t.is_contiguous(), "non-contiguous tensor passed to the C ABI"
     return ctypes.c_void_p(t.data_ptr())
 

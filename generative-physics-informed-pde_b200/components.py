@@ -40,7 +40,8 @@ class _ProlongPlan(object):
         B = u.shape[0]
         out = torch.empty((B, self.n if transpose else self.d), dtype=u.dtype, device=u.device)
         fn = getattr(self._lib, "gpde_prolong_apply_%s%s" % ("T_" if transpose else "", sfx))
-        _lib.check(fn(self.handle, _lib.ptr(u), _lib.ptr(out), B, _lib.stream_of(u.device)), "gpde_prolong_apply")
+        _lib.check(fn(self.handle, _lib.ptr(u, self.device), _lib.ptr(out, self.device), B, _lib.stream_of(self.device)),
+                   "gpde_prolong_apply")
         return out
 
 

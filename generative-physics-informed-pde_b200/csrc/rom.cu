@@ -47,23 +47,11 @@ struct RomDev {
     const char *arena;
     int arena_bytes;
 };
-}  // namespace gpde
-
-struct gpde_rom_plan {
-    gpde::RomDev dev;
-    int device;
-    int tps;                // 1: thread-per-sample kernels (rom_tps.cuh) serve this plan; fixes the factor layout
-    int lanes;              // G
-    int n_contrib;
-    size_t smem_fwd, smem_adj;  // bytes per sample
-    std::vector<void *> allocs;
-};
-
-namespace gpde {
 
 constexpr int kRomThreads = 128;
 
 __device__ __forceinline__ double ld_as_double(const double *p) { return *p; }
+__device__ __forceinline__ double ld_as_double(const float *p) { return (double)*p; }
 
 // 1/d for a positive, finite pivot: hardware seed + two Newton steps (<= 1 ulp; the IEEE division sequence is
 // ~4x the instructions and sits on the critical path of every elimination step)
@@ -74,7 +62,22 @@ __device__ __forceinline__ double fast_rcp(double d) {
     r = fma(r, fma(-d, r, 1.0), r);
     return r;
 }
-__device__ __forceinline__ double ld_as_double(const float *p) { return (double)*p; }
+}  // namespace gpde
+
+#include "rom_tps.cuh"
+
+struct gpde_rom_plan {
+    gpde::RomDev dev;
+    int device;
+    int tps;                // 1: the thread-per-sample kernels (rom_tps.cuh) serve this plan (no factor stash)
+    gpde::TpsAdjTab<gpde::TpsShape4x4> tps_tab;   // their tables, passed by value with every launch
+    int lanes;              // G
+    int n_contrib;
+    size_t smem_fwd, smem_adj;  // bytes per sample
+    std::vector<void *> allocs;
+};
+
+namespace gpde {
 
 // ---------------------------------------------------------------------------------------------
 // Shared building blocks (all called by the G lanes of one sample, converged).
@@ -236,15 +239,17 @@ rom_forward_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__
     bad |= factor_band<G>(P, gl, Ab, dinv, z, wv);
     backward_subst<G>(P, gl, Ab, dinv, wv, z, Fs, P.free_dof);
 
+    if (factor) {   // uniform branch: every lane of the warp reaches the barrier, the stores are predicated per sample
+        double *fb = factor + b * (long long)P.n_band;
+        // band entries as they are; the diagonal slots then receive 1/d_k (no index divisions)
+        if (active)
+            for (int p = gl; p < P.n_band; p += G) fb[p] = Ab[p];
+        __syncwarp();
+        if (active)
+            for (int k = gl; k < P.n_free; k += G) fb[k * P.bw1] = dinv[k];
+    }
     if (active) {
         for (int i = gl; i < P.n; i += G) u[b * P.n + i] = (T)Fs[i];
-        if (factor) {
-            double *fb = factor + b * (long long)P.n_band;
-            // band entries as they are; the diagonal slots then receive 1/d_k (no index divisions)
-            for (int p = gl; p < P.n_band; p += G) fb[p] = Ab[p];
-            __syncwarp();
-            for (int k = gl; k < P.n_free; k += G) fb[k * P.bw1] = dinv[k];
-        }
         if (bad && info) atomicOr(info, bad);
     }
 }
@@ -320,9 +325,6 @@ rom_adjoint_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__
     }
 }
 
-}  // namespace gpde
-#include "rom_tps.cuh"
-namespace gpde {
 
 // ---------------------------------------------------------------------------------------------
 // GetStiffness: K[n,n,B] (batch last, ROM.py:93), Dirichlet rows -> identity rows (:97-98)
@@ -348,6 +350,72 @@ __global__ void rom_stiffness_kernel(RomDev P, const double *__restrict__ X, dou
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Tables of the thread-per-sample kernels for shape S; false if M does not fit the shape (sizes, bandwidth, or more
+// terms per entry than the shape provides): the plan then stays on the cooperative kernels.
+template <class S>
+static bool build_tps_tables(int n, int E, int nf, int hbw, const std::vector<int> &free_dof, const std::vector<int> &bc_dof,
+                             const std::vector<unsigned char> &is_bc, const double *M, TpsAdjTab<S> &A) {
+    if (n != S::N || E != S::E || nf != S::NF || hbw != S::HBW) return false;
+    static_assert(S::N <= S::E, "the adjoint kernel stages u into the columns of x");
+    static_assert(S::E * kTpsPitch < 65536 && S::N * kTpsPitch < 65536, "column offsets are 16-bit");
+    auto Mat = [&](int i, int j, int e) { return M[((size_t)i * n + j) * E + e]; };
+    memset(&A, 0, sizeof(A));
+    TpsFwdTab<S> &Ft = A.f;
+    for (int i = 0; i < nf; ++i) {
+        Ft.free_dof[i] = (unsigned short)(free_dof[i] * kTpsPitch);
+        int cnt = 0;
+        for (int e = 0; e < E; ++e) {
+            const double v = Mat(free_dof[i], free_dof[i], e);
+            if (v == 0.0) continue;
+            if (cnt == S::TD) return false;
+            Ft.diag_coef[i * S::TD + cnt] = v;
+            Ft.diag_elem[i * S::TD + cnt] = (unsigned short)(e * kTpsPitch);
+            ++cnt;
+        }
+        for (int s = 1; s <= hbw && s <= i; ++s) {
+            cnt = 0;
+            for (int e = 0; e < E; ++e) {
+                const double v = Mat(free_dof[i], free_dof[i - s], e);
+                if (v == 0.0) continue;
+                if (cnt == S::TO) return false;
+                const int k = (i * S::HBW + s - 1) * S::TO + cnt;
+                Ft.off_coef[k] = v;
+                Ft.off_elem[k] = (unsigned short)(e * kTpsPitch);
+                ++cnt;
+            }
+        }
+        cnt = 0;
+        for (size_t c = 0; c < bc_dof.size(); ++c)
+            for (int e = 0; e < E; ++e) {
+                const double v = Mat(free_dof[i], bc_dof[c], e);
+                if (v == 0.0) continue;
+                if (cnt == S::TR) return false;
+                const int k = i * S::TR + cnt;
+                Ft.rhs_coef[k] = v;
+                Ft.rhs_elem[k] = (unsigned short)(e * kTpsPitch);
+                Ft.rhs_dof[k] = (unsigned short)(bc_dof[c] * kTpsPitch);
+                ++cnt;
+            }
+    }
+    for (int e = 0; e < E; ++e) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            if (is_bc[i]) continue;   // overwritten rows contribute nothing
+            for (int j = 0; j < n; ++j) {
+                const double v = Mat(i, j, e);
+                if (v == 0.0) continue;
+                if (cnt == S::TG) return false;
+                const int k = e * S::TG + cnt;
+                A.grad_coef[k] = v;
+                A.grad_i[k] = (unsigned short)(i * kTpsPitch);
+                A.grad_j[k] = (unsigned short)(j * kTpsPitch);
+                ++cnt;
+            }
+        }
+    }
+    return true;
+}
+
 template <typename T>
 static int track(gpde_rom_plan *pl, const T **dst, const std::vector<T> &src) {
     T *p = nullptr;
@@ -393,11 +461,12 @@ static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     if (!X || !F || !u) return fail(GPDE_ERR_ARG, "rom_forward: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->tps) {
-        auto kern = rom_tps_forward_kernel<T, 15, 3>;
-        const size_t smem = tps_smem_forward(pl->dev);
+    if (pl->tps) {   // thread per sample, no factor stash (``factor`` is not touched)
+        using S = TpsShape4x4;
+        auto kern = rom_tps_forward_kernel<T, S>;
+        constexpr size_t smem = tps_smem_forward<S>();
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, F, u, factor, info, B);
+        kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->tps_tab.f, X, x_is_log, F, u, info, B);
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
     }
@@ -416,11 +485,20 @@ static int rom_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
     if (!X || !u || !gbar || !gradX) return fail(GPDE_ERR_ARG, "rom_adjoint: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->tps) {
-        auto kern = rom_tps_adjoint_kernel<T, 15, 3>;
-        const size_t smem = tps_smem_adjoint(pl->dev);
-        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)((B + kTpsThreads - 1) / kTpsThreads), kTpsThreads, smem, st>>>(pl->dev, X, x_is_log, u, factor, gbar, gradX, gradF, B);
+    if (pl->tps) {   // re-assembles and re-factorises: cheaper than a factor round trip through HBM at this size
+        using S = TpsShape4x4;
+        const unsigned grid = (unsigned)((B + kTpsThreads - 1) / kTpsThreads);
+        if (gradF) {
+            auto kern = rom_tps_adjoint_kernel<T, S, true>;
+            constexpr size_t smem = tps_smem_adjoint<S>(true);
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kTpsThreads, smem, st>>>(pl->tps_tab, X, x_is_log, u, gbar, gradX, gradF, B);
+        } else {
+            auto kern = rom_tps_adjoint_kernel<T, S, false>;
+            constexpr size_t smem = tps_smem_adjoint<S>(false);
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kTpsThreads, smem, st>>>(pl->tps_tab, X, x_is_log, u, gbar, gradX, gradF, B);
+        }
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
     }
@@ -604,22 +682,19 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
     const int pairs = D.n_pairs;
     pl->lanes = pairs <= 8 ? 8 : (pairs <= 16 ? 16 : 32);
     pl->n_contrib = (int)band_elem.size();
-    // thread-per-sample kernels (rom_tps.cuh): instantiated for the reference's 4x4 coarse mesh (15 free dofs, half
-    // bandwidth 3 in this package's x-fastest numbering; the half-bandwidth-4 instantiations were dropped: they doubled this
-    // file's compile time for a path that is opt-in and slower).  MEASURED SLOWER than the
-    // cooperative kernels on B200 (B = 4096: 51 + 39 us vs 18.5 + 15.3 us, only 32 CTAs; B = 131072: 248 M vs
-    // 415 M solves/s, 8 resident warps per SM of serial FP64 chains), so they are opt-in: GPDE_ROM_PATH=tps.
-    // Decided once per plan: it fixes the factor layout.
+    // thread-per-sample kernels (rom_tps.cuh) when M fits their compile-time shape (the reference's 4x4 coarse mesh);
+    // GPDE_ROM_PATH=coop keeps the plan on the cooperative kernels (A/B runs; read once, here).  Decided once per plan:
+    // it fixes whether a factor stash exists.
     {
         const char *e = getenv("GPDE_ROM_PATH");
-        pl->tps = (nf == 15 && hbw == 3 && tps_smem_adjoint(D) <= 227 * 1024 && e && strcmp(e, "tps") == 0) ? 1 : 0;
+        const bool want = !(e && strcmp(e, "coop") == 0);
+        pl->tps = (want && build_tps_tables<TpsShape4x4>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, pl->tps_tab)) ? 1 : 0;
     }
-    // per-sample scratch; with 8 lanes per sample a 64-bit shared-memory wavefront serves two samples, so the pitch is
-    // padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint halves of the banks
-    // (GPDE_ROM_PAD=0 keeps the unpadded pitch for A/B runs)
+    // per-sample scratch of the cooperative kernels; with 8 lanes per sample a 64-bit shared-memory wavefront serves two
+    // samples, so the pitch is padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint
+    // halves of the banks
     auto pad_pitch = [&](size_t doubles) {
-        const char *e = getenv("GPDE_ROM_PAD");
-        if (pl->lanes != 8 || (e && atoi(e) == 0)) return doubles;
+        if (pl->lanes != 8) return doubles;
         while (doubles % 16 != 8) ++doubles;
         return doubles;
     };
@@ -646,12 +721,12 @@ int gpde_rom_plan_destroy(gpde_rom_plan *pl) {
 int gpde_rom_plan_info(const gpde_rom_plan *pl, int64_t out[8]) {
     if (!pl || !out) return fail(GPDE_ERR_ARG, "rom_plan_info: null");
     out[0] = pl->dev.n; out[1] = pl->dev.E; out[2] = pl->dev.n_free; out[3] = pl->dev.hbw;
-    out[4] = pl->dev.n_band; out[5] = pl->n_contrib; out[6] = pl->tps ? 1 : pl->lanes; out[7] = pl->device;
+    out[4] = pl->tps ? 0 : pl->dev.n_band; out[5] = pl->n_contrib; out[6] = pl->tps ? 1 : pl->lanes; out[7] = pl->device;
     return GPDE_OK;
 }
 
 size_t gpde_rom_factor_bytes(const gpde_rom_plan *pl, int64_t B) {
-    if (!pl || B < 0) return 0;
+    if (!pl || B < 0 || pl->tps) return 0;   // the thread-per-sample kernels keep no stash
     return sizeof(double) * (size_t)pl->dev.n_band * (size_t)B;
 }
 

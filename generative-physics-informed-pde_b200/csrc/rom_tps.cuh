@@ -1,118 +1,143 @@
-// Coarse-grained model, one THREAD per sample (small systems).  Included by rom.cu.
-// EXPERIMENT, opt-in with GPDE_ROM_PATH=tps: measured slower than the cooperative kernels of rom.cu on B200
-// (see gpde_rom_plan_create); kept for A/B runs and as the starting point of a register-resident variant.
+// Coarse-grained model, one THREAD per sample, structure fixed at compile time.  Included by rom.cu.
 //
-// For the reference's 4x4 coarse mesh (n_free = 15, half bandwidth 3-4: presets highres32 and BASELINE configs
-// 1, 2, 4) the whole banded LDL^T fits in the registers of one thread when the loops are unrolled at compile
-// time (template <NF, HBW>): no cross-lane cooperation, no barrier per elimination step, no idle lanes -- the
-// cooperative kernels of rom.cu spend > 90 % of their instructions on that.  Same maths, same tables
-// (bottleneck/ROM.py:59-100 and its autograd):
-//   * the CTA's 128 samples are loaded with coalesced reads and transposed through shared memory into
-//     per-thread columns (pitch 129 doubles: conflict-free both ways); exp(X)+1e-8 is applied on the way in;
-//   * assembly walks the plan's (uniform) contribution tables from shared memory: Ab[p] += coef * x[elem];
-//   * factorisation, forward and backward substitution are fully unrolled over the band held in registers;
-//   * the factor is stashed TRANSPOSED, factor[p][B] (diagonal slots hold 1/d_k), so that both kernels read /
-//     write it coalesced (the stash is opaque to callers: gpde_rom_factor_bytes);
-//   * the adjoint reuses it, then forms dL/dX[e] = -sum_t coef * lam[i_t] * u[j_t] (* exp(X)) from
-//     shared-memory columns of lam and u.
+// For the reference's 4x4 coarse mesh (presets highres32 and BASELINE configs 1, 2, 4: 15 free dofs, half bandwidth 3,
+// 32 cells, 25 dofs) the banded LDL^T of K_ff fits in the registers of one thread, so one sample needs no cross-lane
+// cooperation, no barrier per elimination step and no index table on its critical path:
+//   * everything that depends on the mesh is a SHAPE (template <TpsShape>): loop bounds, band positions and the number
+//     of terms per band entry are compile-time constants, every loop is fully unrolled and the band lives in registers;
+//   * everything that depends on M (coefficients, which element feeds which entry) sits in a table passed BY VALUE as a
+//     __grid_constant__ kernel parameter: the coefficients are constant-bank operands of the DFMAs and the element
+//     offsets uniform-register offsets of the shared-memory loads -- no dependent table walk (the first
+//     thread-per-sample kernels walked band_ptr -> band_elem -> x through shared memory: a ~100-cycle dependent chain per
+//     term, 51 + 39 us for 4096 samples);
+//   * the CTA's 128 samples are read with coalesced loads and transposed through shared memory into per-thread columns
+//     (pitch 129 doubles: conflict-free both ways), exp(X)+1e-8 (components.py:298) applied on the way in;
+//   * no factor stash: the adjoint re-assembles and re-factorises (about 500 instructions per sample) instead of
+//     writing and re-reading 480 bytes per sample through HBM;
+//   * dL/dX[e] = -sum_t coef_t lam[i_t] u[j_t] (* exp(X)) from shared-memory columns of lam and u, terms per element
+//     padded to the shape's TG.
+// Same maths as the cooperative kernels of rom.cu (bottleneck/ROM.py:59-100 and its autograd).
+// gpde_rom_plan_create checks that M fits the shape (sizes, bandwidth, terms per entry) and otherwise keeps the plan on
+// the cooperative kernels.
 #pragma once
+#include "exp256.cuh"
 
 namespace gpde {
 
 constexpr int kTpsThreads = 128;
 constexpr int kTpsPitch = kTpsThreads + 1;   // doubles between consecutive rows of a per-thread column array
 
-static __constant__ double kRomExpTab[16] = {1.0,
-                                             1.0442737824274138,
-                                             1.0905077326652577,
-                                             1.1387886347566916,
-                                             1.189207115002721,
-                                             1.241857812073484,
-                                             1.2968395546510096,
-                                             1.3542555469368927,
-                                             1.4142135623730951,
-                                             1.4768261459394993,
-                                             1.5422108254079407,
-                                             1.6104903319492543,
-                                             1.681792830507429,
-                                             1.7562521603732995,
-                                             1.8340080864093424,
-                                             1.9152065613971474};
+// NF free dofs, half bandwidth HBW, E cells, N dofs; terms per off-diagonal band entry / diagonal entry / right-hand-side
+// row (couplings to Dirichlet dofs) / element of the gradient
+template <int NF_, int HBW_, int E_, int N_, int TO_, int TD_, int TR_, int TG_>
+struct TpsShape {
+    static constexpr int NF = NF_, HBW = HBW_, E = E_, N = N_, TO = TO_, TD = TD_, TR = TR_, TG = TG_;
+};
+using TpsShape4x4 = TpsShape<15, 3, 32, 25, 2, 6, 2, 7>;
 
-// exp(x) = 2^e * T[j] * P6(r), |r| <= ln2/32 (~5e-16 relative for |x| <= 700); libm outside that range
-__device__ __forceinline__ double rom_exp(double x, const double *tab) {
-    if ((__double2hiint(x) & 0x7fffffff) > 0x4085e000) return exp(x);
-    const double t = fma(x, 23.083120654223414, 6755399441055744.0);
-    const int ki = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    double r = fma(kd, -0.04332169877307024, x);
-    r = fma(kd, -1.1926343307941173e-11, r);
-    double p = 1.38888888888888888889e-03;
-    p = fma(p, r, 8.33333333333333333333e-03);
-    p = fma(p, r, 4.16666666666666666667e-02);
-    p = fma(p, r, 1.66666666666666666667e-01);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double v = p * tab[ki & 15];
-    return __hiloint2double(__double2hiint(v) + ((ki >> 4) << 20), __double2loint(v));
+// element / dof entries are column offsets (index * kTpsPitch); padding terms have coefficient 0 and offset 0
+template <class S>
+struct TpsFwdTab {
+    double off_coef[S::NF * S::HBW * S::TO];    // entry (i, s >= 1) = A[i][i-s], term t: [(i * HBW + s - 1) * TO + t]
+    double diag_coef[S::NF * S::TD];
+    double rhs_coef[S::NF * S::TR];             // z_i = F[free_i] - sum_t rhs_coef * x[rhs_elem] * F[rhs_dof]
+    unsigned short off_elem[S::NF * S::HBW * S::TO];
+    unsigned short diag_elem[S::NF * S::TD];
+    unsigned short rhs_elem[S::NF * S::TR], rhs_dof[S::NF * S::TR];
+    unsigned short free_dof[S::NF];
+};
+template <class S>
+struct TpsAdjTab {
+    TpsFwdTab<S> f;
+    double grad_coef[S::E * S::TG];             // dL/dx_e = -sum_t grad_coef * lam[grad_i] * u[grad_j]
+    unsigned short grad_i[S::E * S::TG], grad_j[S::E * S::TG];   // dof columns (grad_i is a free dof)
+};
+
+// Coalesced load of rows [b0, b0+rows) x [0, W) of a row-major [B, W] array: element threadIdx.x + 128 k of the CTA's block
+// into raw[k].  All W loads are issued before anything consumes them (one DRAM latency per array, not one per few elements:
+// with one or two warps per scheduler nothing else hides it).  Rows past the batch get ``fill``.
+template <typename T, int W>
+__device__ __forceinline__ void tps_fetch(const T *__restrict__ src, long long b0, int rows, double fill, T (&raw)[W]) {
+    const T *p = src + b0 * W;
+    const int limit = rows * W;
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int i = threadIdx.x + k * kTpsThreads;
+        raw[k] = i < limit ? p[i] : (T)fill;
+    }
 }
-
-// Coalesced load of rows [b0, b0+128) x [0, width) of a row-major [B, width] array into per-thread columns
-// col[j * pitch + thread].  WITH_EXP: x = exp(v) + 1e-8 (components.py:298), dcol receives exp(v) (chain rule);
-// returns GPDE_INFO_NONPOSITIVE_X if any loaded conductivity is <= 1e-12 (ROM.py:74-76).
-template <typename T>
-__device__ __forceinline__ int tps_load(const T *__restrict__ src, int width, long long b0, long long B, double *col,
-                                        double *dcol, bool conductivity, int x_is_log, const double *tab) {
+// ... and their transposition into per-thread columns col[j * pitch + row] (values as loaded).
+template <typename T, int W>
+__device__ __forceinline__ void tps_scatter(const T (&raw)[W], double *col) {
+#pragma unroll
+    for (int k = 0; k < W; ++k) {
+        const int i = threadIdx.x + k * kTpsThreads;
+        const int row = i / W, j = i - row * W;
+        col[j * kTpsPitch + row] = (double)raw[k];
+    }
+}
+// Conductivities of this thread's sample, in place in its column: x = exp(v) + 1e-8 when x_is_log (components.py:298), dcol
+// receives dx/dv (exp(v), or 1 for conductivity input).  A ROLLED loop: the fully unrolled version of this and of the
+// gradient loop made the kernels 60 KB of straight-line code whose instruction fetch stalled the few resident warps
+// (no_instruction 1.5 stalled warps per issue, r2b profile).  Returns GPDE_INFO_NONPOSITIVE_X if a conductivity is
+// <= 1e-12 (ROM.py:74-76).
+template <int E>
+__device__ __forceinline__ int tps_conductivities(double *x, double *dx, int x_is_log, unsigned etab) {
     int bad = 0;
-    const long long base = b0 * width;
-    const long long limit = min((long long)kTpsThreads, B - b0) * width;
-    for (long long i = threadIdx.x; i < limit; i += kTpsThreads) {
-        const int row = (int)(i / width), j = (int)(i - (long long)row * width);
-        double v = ld_as_double(src + base + i);
-        if (conductivity) {
-            double dv = 1.0;
-            if (x_is_log) {
-                dv = rom_exp(v, tab);
-                v = dv + 1e-8;
-            }
-            if (!(v > 1e-12)) bad = GPDE_INFO_NONPOSITIVE_X;
-            if (dcol) dcol[j * kTpsPitch + row] = dv;
+#pragma unroll 2
+    for (int e = 0; e < E; ++e) {
+        double v = x[e * kTpsPitch], dv = 1.0;
+        if (x_is_log) {
+            dv = exp256_in_range(v) ? exp_tab256c(v, etab) : exp(v);
+            v = dv + 1e-8;
+            x[e * kTpsPitch] = v;
         }
-        col[j * kTpsPitch + row] = v;
+        if (!(v > 1e-12)) bad = GPDE_INFO_NONPOSITIVE_X;
+        if (dx) dx[e * kTpsPitch] = dv;
     }
     return bad;
 }
 
-template <typename T>
-__device__ __forceinline__ void tps_store(T *__restrict__ dst, int width, long long b0, long long B, const double *col) {
-    const long long base = b0 * width;
-    const long long limit = min((long long)kTpsThreads, B - b0) * width;
-    for (long long i = threadIdx.x; i < limit; i += kTpsThreads) {
-        const int row = (int)(i / width), j = (int)(i - (long long)row * width);
-        dst[base + i] = (T)col[j * kTpsPitch + row];
+template <typename T, int W>
+__device__ __forceinline__ void tps_stage_out(T *__restrict__ dst, long long b0, int rows, const double *col) {
+    T *p = dst + b0 * W;
+    const int limit = rows * W;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < limit; i += kTpsThreads) {
+        const int row = i / W, j = i - row * W;
+        p[i] = (T)col[j * kTpsPitch + row];
     }
 }
 
-// Ab[i][s] = A[i][i-s] of K_ff(x) for this thread's sample (xs = its conductivity column)
-template <int NF, int HBW>
-__device__ __forceinline__ void tps_assemble(const RomDev &P, const double *xs, double (&Ab)[NF][HBW + 1]) {
+// Ab[i][s] = A[i][i-s] of K_ff(x) for this thread's sample (x = its conductivity column)
+template <class S>
+__device__ __forceinline__ void tps_assemble(const TpsFwdTab<S> &tab, const double *x, double (&Ab)[S::NF][S::HBW + 1]) {
 #pragma unroll
-    for (int i = 0; i < NF; ++i)
+    for (int i = 0; i < S::NF; ++i) {
+        double acc = 0.0;
 #pragma unroll
-        for (int s = 0; s <= HBW; ++s) {
-            const int p = i * (HBW + 1) + s;
-            double acc = 0.0;
-            const int t1 = P.band_ptr[p + 1];
-            for (int t = P.band_ptr[p]; t < t1; ++t) acc = fma(P.band_coef[t], xs[P.band_elem[t] * kTpsPitch], acc);
-            Ab[i][s] = acc;
+        for (int t = 0; t < S::TD; ++t) acc = fma(tab.diag_coef[i * S::TD + t], x[tab.diag_elem[i * S::TD + t]], acc);
+        Ab[i][0] = acc;
+#pragma unroll
+        for (int s = 1; s <= S::HBW; ++s) {
+            double off = 0.0;
+            if (i - s >= 0) {
+#pragma unroll
+                for (int t = 0; t < S::TO; ++t) {
+                    const int k = (i * S::HBW + s - 1) * S::TO + t;
+                    off = fma(tab.off_coef[k], x[tab.off_elem[k]], off);
+                }
+            }
+            Ab[i][s] = off;
         }
+    }
 }
 
 // In-place LDL^T (column entries stay unscaled); the diagonal slot Ab[k][0] ends up holding 1/d_k;
 // z (if WITH_RHS) becomes w = D^-1 L^-1 z
-template <int NF, int HBW, bool WITH_RHS>
-__device__ __forceinline__ int tps_factor(double (&Ab)[NF][HBW + 1], double (&z)[NF]) {
+template <class S, bool WITH_RHS>
+__device__ __forceinline__ int tps_factor(double (&Ab)[S::NF][S::HBW + 1], double (&z)[S::NF]) {
+    constexpr int NF = S::NF, HBW = S::HBW;
     int bad = 0;
 #pragma unroll
     for (int k = 0; k < NF; ++k) {
@@ -140,149 +165,160 @@ __device__ __forceinline__ int tps_factor(double (&Ab)[NF][HBW + 1], double (&z)
 }
 
 // w = D^-1 L^-1 z with a stored factor (in place)
-template <int NF, int HBW>
-__device__ __forceinline__ void tps_forward_subst(const double (&Ab)[NF][HBW + 1], double (&z)[NF]) {
+template <class S>
+__device__ __forceinline__ void tps_forward_subst(const double (&Ab)[S::NF][S::HBW + 1], double (&z)[S::NF]) {
 #pragma unroll
-    for (int k = 0; k < NF; ++k) {
+    for (int k = 0; k < S::NF; ++k) {
         const double wk = z[k] * Ab[k][0];
 #pragma unroll
-        for (int s = 1; s <= HBW; ++s)
-            if (k + s < NF) z[k + s] = fma(-Ab[k + s][s], wk, z[k + s]);
+        for (int s = 1; s <= S::HBW; ++s)
+            if (k + s < S::NF) z[k + s] = fma(-Ab[k + s][s], wk, z[k + s]);
         z[k] = wk;
     }
 }
 
 // L^T sol = w (in place): sol_k = w_k - dinv_k * sum_s Ab[k+s][s] sol_{k+s}
-template <int NF, int HBW>
-__device__ __forceinline__ void tps_backward_subst(const double (&Ab)[NF][HBW + 1], double (&z)[NF]) {
+template <class S>
+__device__ __forceinline__ void tps_backward_subst(const double (&Ab)[S::NF][S::HBW + 1], double (&z)[S::NF]) {
 #pragma unroll
-    for (int k = NF - 1; k >= 0; --k) {
+    for (int k = S::NF - 1; k >= 0; --k) {
         double acc = 0.0;
 #pragma unroll
-        for (int s = 1; s <= HBW; ++s)
-            if (k + s < NF) acc = fma(Ab[k + s][s], z[k + s], acc);
+        for (int s = 1; s <= S::HBW; ++s)
+            if (k + s < S::NF) acc = fma(Ab[k + s][s], z[k + s], acc);
         z[k] = fma(-Ab[k][0], acc, z[k]);
     }
 }
 
-// shared memory: [table arena][exp table 16][columns ...]
-template <typename T, int NF, int HBW>
-__global__ void __launch_bounds__(kTpsThreads)
-rom_tps_forward_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__restrict__ F, T *__restrict__ u,
-                       double *__restrict__ factor, int *info, long long B) {
-    extern __shared__ __align__(16) double smem_all[];
-    double *smem;
-    const RomDev P = stage_tables(P0, smem_all, &smem);
-    double *tab = smem;                       // [16]
-    double *xs = tab + 16;                    // [E][pitch]
-    double *Fs = xs + P.E * kTpsPitch;        // [n][pitch]  F, then u
-    if (threadIdx.x < 16) tab[threadIdx.x] = kRomExpTab[threadIdx.x];
-    __syncthreads();
+// shared memory: [exp table 256][x: E columns][F -> u: N columns]
+template <typename T, class S>
+__global__ void __launch_bounds__(kTpsThreads, 2)
+rom_tps_forward_kernel(const __grid_constant__ TpsFwdTab<S> tab, const T *__restrict__ X, int x_is_log,
+                       const T *__restrict__ F, T *__restrict__ u, int *info, long long B) {
+    extern __shared__ __align__(16) double tps_smem[];
+    double *etab = tps_smem;
+    double *xs = etab + 256;
+    double *fs = xs + S::E * kTpsPitch;
     const long long b0 = (long long)blockIdx.x * kTpsThreads;
-    int bad = tps_load<T>(X, P.E, b0, B, xs, nullptr, true, x_is_log, tab);
-    tps_load<T>(F, P.n, b0, B, Fs, nullptr, false, 0, tab);
+    const int rows = (int)min((long long)kTpsThreads, B - b0);
+    {
+        T xr[S::E], fr[S::N];
+        tps_fetch<T, S::E>(X, b0, rows, x_is_log ? 0.0 : 1.0, xr);
+        tps_fetch<T, S::N>(F, b0, rows, 0.0, fr);
+        for (int i = threadIdx.x; i < 256; i += kTpsThreads) etab[i] = kExp256Tab[i];
+        tps_scatter<T, S::E>(xr, xs);
+        tps_scatter<T, S::N>(fr, fs);
+    }
     __syncthreads();
-    const long long b = b0 + threadIdx.x;
-    if (b < B) {
+    int bad = tps_conductivities<S::E>(xs + threadIdx.x, nullptr, x_is_log, smem_u32_of(etab));
+    if ((int)threadIdx.x >= rows) bad = 0;
+    {
         const double *x = xs + threadIdx.x;
-        double *f = Fs + threadIdx.x;
-        double Ab[NF][HBW + 1], z[NF];
-        tps_assemble<NF, HBW>(P, x, Ab);
+        double *f = fs + threadIdx.x;
+        double Ab[S::NF][S::HBW + 1], z[S::NF];
+        tps_assemble<S>(tab, x, Ab);
 #pragma unroll
-        for (int i = 0; i < NF; ++i) {
-            double acc = f[P.free_dof[i] * kTpsPitch];
-            const int t1 = P.rhs_ptr[i + 1];
-            for (int t = P.rhs_ptr[i]; t < t1; ++t)
-                acc = fma(-P.rhs_coef[t] * x[P.rhs_elem[t] * kTpsPitch], f[P.rhs_dof[t] * kTpsPitch], acc);
+        for (int i = 0; i < S::NF; ++i) {
+            double acc = f[tab.free_dof[i]];
+#pragma unroll
+            for (int t = 0; t < S::TR; ++t) {
+                const int k = i * S::TR + t;
+                acc = fma(-tab.rhs_coef[k] * x[tab.rhs_elem[k]], f[tab.rhs_dof[k]], acc);
+            }
             z[i] = acc;
         }
-        bad |= tps_factor<NF, HBW, true>(Ab, z);
-        tps_backward_subst<NF, HBW>(Ab, z);
+        const int fbad = tps_factor<S, true>(Ab, z);
+        if ((int)threadIdx.x < rows) bad |= fbad;
+        tps_backward_subst<S>(Ab, z);
 #pragma unroll
-        for (int i = 0; i < NF; ++i) f[P.free_dof[i] * kTpsPitch] = z[i];
-        if (factor) {   // transposed stash: entry p of sample b at factor[p * B + b]; diagonal slots hold 1/d_k
-#pragma unroll
-            for (int i = 0; i < NF; ++i)
-#pragma unroll
-                for (int s = 0; s <= HBW; ++s) factor[(long long)(i * (HBW + 1) + s) * B + b] = Ab[i][s];
-        }
+        for (int i = 0; i < S::NF; ++i) f[tab.free_dof[i]] = z[i];
     }
     if (bad && info) atomicOr(info, bad);
     __syncthreads();
-    tps_store<T>(u, P.n, b0, B, Fs);
+    tps_stage_out<T, S::N>(u, b0, rows, fs);
 }
 
-template <typename T, int NF, int HBW>
-__global__ void __launch_bounds__(kTpsThreads)
-rom_tps_adjoint_kernel(RomDev P0, const T *__restrict__ X, int x_is_log, const T *__restrict__ u,
-                       const double *__restrict__ factor, const T *__restrict__ gbar, T *__restrict__ gradX,
+// shared memory: [exp table 256][x: E columns (then u when !GRADF)][exp(X) -> dL/dX: E columns][gbar -> lambda: N columns]
+//                ([u: N columns] when GRADF: x stays live until the constrained rows of lambda are formed)
+template <typename T, class S, bool GRADF>
+__global__ void __launch_bounds__(kTpsThreads, GRADF ? 1 : 2)
+rom_tps_adjoint_kernel(const __grid_constant__ TpsAdjTab<S> tab, const T *__restrict__ X, int x_is_log,
+                       const T *__restrict__ u, const T *__restrict__ gbar, T *__restrict__ gradX,
                        T *__restrict__ gradF, long long B) {
-    extern __shared__ __align__(16) double smem_all[];
-    double *smem;
-    const RomDev P = stage_tables(P0, smem_all, &smem);
-    double *tab = smem;                        // [16]
-    double *xs = tab + 16;                     // [E][pitch]  x, then dL/dX
-    double *us = xs + P.E * kTpsPitch;         // [n][pitch]
-    double *gs = us + P.n * kTpsPitch;         // [n][pitch]  gbar, then dL/dF
-    double *ls = gs + P.n * kTpsPitch;         // [NF][pitch] lambda on the free dofs
-    if (threadIdx.x < 16) tab[threadIdx.x] = kRomExpTab[threadIdx.x];
-    __syncthreads();
+    extern __shared__ __align__(16) double tps_smem[];
+    double *etab = tps_smem;
+    double *xs = etab + 256;
+    double *dxs = xs + S::E * kTpsPitch;
+    double *gs = dxs + S::E * kTpsPitch;
+    double *us = GRADF ? gs + S::N * kTpsPitch : xs;
     const long long b0 = (long long)blockIdx.x * kTpsThreads;
-    tps_load<T>(X, P.E, b0, B, xs, nullptr, true, x_is_log, tab);
-    tps_load<T>(u, P.n, b0, B, us, nullptr, false, 0, tab);
-    tps_load<T>(gbar, P.n, b0, B, gs, nullptr, false, 0, tab);
+    const int rows = (int)min((long long)kTpsThreads, B - b0);
+    T ur[S::N];   // u is fetched with the other inputs; without GRADF it waits in registers until the columns of x are free
+    {
+        T xr[S::E], gr[S::N];
+        tps_fetch<T, S::E>(X, b0, rows, x_is_log ? 0.0 : 1.0, xr);
+        tps_fetch<T, S::N>(gbar, b0, rows, 0.0, gr);
+        tps_fetch<T, S::N>(u, b0, rows, 0.0, ur);
+        for (int i = threadIdx.x; i < 256; i += kTpsThreads) etab[i] = kExp256Tab[i];
+        tps_scatter<T, S::E>(xr, xs);
+        tps_scatter<T, S::N>(gr, gs);
+        if (GRADF) tps_scatter<T, S::N>(ur, us);
+    }
     __syncthreads();
-    const long long b = b0 + threadIdx.x;
-    if (b < B) {
-        double *x = xs + threadIdx.x, *uu = us + threadIdx.x, *gg = gs + threadIdx.x;
-        double *lam = ls + threadIdx.x;
-        double Ab[NF][HBW + 1], z[NF];
-        if (factor) {
+    tps_conductivities<S::E>(xs + threadIdx.x, dxs + threadIdx.x, x_is_log, smem_u32_of(etab));
+    const double *x = xs + threadIdx.x;
+    double *g = gs + threadIdx.x;
+    {
+        double Ab[S::NF][S::HBW + 1], z[S::NF];
+        tps_assemble<S>(tab.f, x, Ab);
+        tps_factor<S, false>(Ab, z);
 #pragma unroll
-            for (int i = 0; i < NF; ++i)
+        for (int i = 0; i < S::NF; ++i) z[i] = g[tab.f.free_dof[i]];
+        tps_forward_subst<S>(Ab, z);
+        tps_backward_subst<S>(Ab, z);
+        if (GRADF) {   // lambda on the constrained rows: gbar_c - sum_f K_fc lambda_f  (same couplings as the forward rhs)
 #pragma unroll
-                for (int s = 0; s <= HBW; ++s) Ab[i][s] = factor[(long long)(i * (HBW + 1) + s) * B + b];
-        } else {
-            tps_assemble<NF, HBW>(P, x, Ab);
-            tps_factor<NF, HBW, false>(Ab, z);
+            for (int i = 0; i < S::NF; ++i)
+#pragma unroll
+                for (int t = 0; t < S::TR; ++t) {
+                    const int k = i * S::TR + t;
+                    g[tab.f.rhs_dof[k]] = fma(-tab.f.rhs_coef[k] * x[tab.f.rhs_elem[k]], z[i], g[tab.f.rhs_dof[k]]);
+                }
         }
 #pragma unroll
-        for (int i = 0; i < NF; ++i) z[i] = gg[P.free_dof[i] * kTpsPitch];
-        tps_forward_subst<NF, HBW>(Ab, z);
-        tps_backward_subst<NF, HBW>(Ab, z);
-#pragma unroll
-        for (int i = 0; i < NF; ++i) lam[i * kTpsPitch] = z[i];
-        if (gradF) {   // lambda on constrained rows first (needs gbar there), then the free rows overwrite gs
-            for (int c = 0; c < P.n_bc; ++c) {
-                double acc = gg[P.bc_dof[c] * kTpsPitch];
-                const int t1 = P.cf_ptr[c + 1];
-                for (int t = P.cf_ptr[c]; t < t1; ++t)
-                    acc = fma(-P.cf_coef[t] * x[P.cf_elem[t] * kTpsPitch], lam[P.cf_free[t] * kTpsPitch], acc);
-                gg[P.bc_dof[c] * kTpsPitch] = acc;
-            }
-#pragma unroll
-            for (int i = 0; i < NF; ++i) gg[P.free_dof[i] * kTpsPitch] = z[i];
-        }
-        for (int e = 0; e < P.E; ++e) {
+        for (int i = 0; i < S::NF; ++i) g[tab.f.free_dof[i]] = z[i];
+    }
+    if (!GRADF) {   // x is dead: its columns take u
+        __syncthreads();
+        tps_scatter<T, S::N>(ur, us);
+        __syncthreads();
+    }
+    {
+        const double *uu = us + threadIdx.x;
+        double *dx = dxs + threadIdx.x;
+#pragma unroll 1
+        for (int e = 0; e < S::E; ++e) {      // rolled: the tables are read with a run-time index from the constant bank
             double acc = 0.0;
-            const int t1 = P.grad_ptr[e + 1];
-            for (int t = P.grad_ptr[e]; t < t1; ++t)
-                acc = fma(P.grad_coef[t] * lam[P.grad_i[t] * kTpsPitch], uu[P.grad_j[t] * kTpsPitch], acc);
-            // chain rule through x = exp(X) + 1e-8: dx/dX = exp(X) = x - 1e-8 (exact to an ulp of x)
-            const double dx = x_is_log ? x[e * kTpsPitch] - 1e-8 : 1.0;
-            x[e * kTpsPitch] = -acc * dx;
+#pragma unroll
+            for (int t = 0; t < S::TG; ++t) {
+                const int k = e * S::TG + t;
+                acc = fma(tab.grad_coef[k] * g[tab.grad_i[k]], uu[tab.grad_j[k]], acc);
+            }
+            dx[e * kTpsPitch] = -acc * dx[e * kTpsPitch];   // chain rule through x = exp(X) + 1e-8 (dx = 1 for conductivity input)
         }
     }
     __syncthreads();
-    tps_store<T>(gradX, P.E, b0, B, xs);
-    if (gradF) tps_store<T>(gradF, P.n, b0, B, gs);
+    tps_stage_out<T, S::E>(gradX, b0, rows, dxs);
+    if (GRADF) tps_stage_out<T, S::N>(gradF, b0, rows, gs);
 }
 
-static inline size_t tps_smem_forward(const RomDev &D) {
-    return (size_t)D.arena_bytes + sizeof(double) * (16 + (size_t)(D.E + D.n) * kTpsPitch);
+template <class S>
+constexpr size_t tps_smem_forward() {
+    return sizeof(double) * (256 + (size_t)(S::E + S::N) * kTpsPitch);
 }
-static inline size_t tps_smem_adjoint(const RomDev &D) {
-    return (size_t)D.arena_bytes + sizeof(double) * (16 + (size_t)(D.E + 2 * D.n + D.n_free) * kTpsPitch);
+template <class S>
+constexpr size_t tps_smem_adjoint(bool gradF) {
+    return sizeof(double) * (256 + (size_t)(2 * S::E + S::N + (gradF ? S::N : 0)) * kTpsPitch);
 }
 
 }  // namespace gpde

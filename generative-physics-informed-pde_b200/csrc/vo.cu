@@ -45,13 +45,46 @@ constexpr int kVoThreads = 256;
 #include "vo_grid2.cuh"
 #include "vo_expand.cuh"
 #include "vo_gemm.cuh"
+#include "vo_posterior.cuh"
+
+namespace gpde {
+// Experiment switches (A/B runs of the kernel families).  Read from the environment ONCE per plan, in gpde_vo_plan_create,
+// never on a launch path.
+struct VoEnv {
+    int grid_r = 2;           // GPDE_GRID_R: node rows per stage of the general grid kernel (1 or 2)
+    bool path_v1 = false;     // GPDE_VO_PATH=v1: version-1 kernels only
+    bool path_fused = false;  // GPDE_VO_PATH=fused: no structured-grid kernels
+    bool no_grid2 = false;    // GPDE_GRID_V=1: general grid kernel instead of the lean one
+    int grid2_nvs = 0;        // GPDE_GRID2_NVS: V stages of the lean kernel (2 or 3; 0 = automatic)
+    int grid2_flags = 0;      // GPDE_GRID2_FLAGS
+    bool grid2_pdl = true;    // GPDE_GRID2_PDL=0: no programmatic dependent launch
+    int grid_debug = 0;       // GPDE_GRID_DEBUG
+    bool sync_staging = false;   // GPDE_VO_SYNC_STAGING
+    bool expand_gemm = false;    // GPDE_VO_EXPAND=gemm
+    VoEnv() {
+        const char *e;
+        if ((e = getenv("GPDE_GRID_R"))) grid_r = atoi(e);
+        if ((e = getenv("GPDE_VO_PATH"))) { path_v1 = strcmp(e, "v1") == 0; path_fused = strcmp(e, "fused") == 0; }
+        if ((e = getenv("GPDE_GRID_V"))) no_grid2 = atoi(e) == 1;
+        if ((e = getenv("GPDE_GRID2_NVS"))) grid2_nvs = atoi(e);
+        if ((e = getenv("GPDE_GRID2_FLAGS"))) grid2_flags = atoi(e);
+        if ((e = getenv("GPDE_GRID2_PDL"))) grid2_pdl = atoi(e) != 0;
+        if ((e = getenv("GPDE_GRID_DEBUG"))) grid_debug = atoi(e);
+        sync_staging = getenv("GPDE_VO_SYNC_STAGING") != nullptr;
+        if ((e = getenv("GPDE_VO_EXPAND"))) expand_gemm = strcmp(e, "gemm") == 0;
+    }
+};
+}  // namespace gpde
 
 struct gpde_vo_plan {
     gpde::VoDev dev;
     gpde::VoTiles tiles;
     gpde::GridDev grid;
+    gpde::VoCsrDev csr;     // K_ff as CSR term lists (vo_posterior.cuh)
     size_t fused_smem;
     int device;
+    int n_sm;
+    gpde::VoEnv env;
     std::vector<void *> allocs;
 };
 
@@ -271,6 +304,56 @@ static cudaError_t build_fused_tiles(gpde_vo_plan *pl, int n_nodes, int n_cells,
 }
 
 
+// K_ff(a) as CSR over the free dofs with, per stored entry, the list of (conductivity input, element-matrix entry) terms:
+// K_ij(a) = sum_t a[term_in[t]] * term_coef[t].  Used by the batched posterior update (vo_posterior.cuh).
+static cudaError_t build_csr_terms(gpde_vo_plan *pl, int n_cells, const int32_t *cell_dofs, const double *Ke,
+                                   const int32_t *cell_to_input, int d, const std::vector<int> &src) {
+    struct Term { int in; double coef; };
+    std::vector<std::vector<std::pair<int, std::vector<Term>>>> rows(d);
+    for (int c = 0; c < n_cells; ++c)
+        for (int l = 0; l < 3; ++l) {
+            const int i = src[cell_dofs[3 * c + l]];
+            if (i < 0) continue;
+            for (int l2 = 0; l2 < 3; ++l2) {
+                const int j = src[cell_dofs[3 * c + l2]];
+                const double v = Ke[9 * c + 3 * l + l2];
+                if (j < 0 || v == 0.0) continue;
+                std::vector<Term> *hit = nullptr;
+                for (auto &e : rows[i])
+                    if (e.first == j) hit = &e.second;
+                if (!hit) {
+                    rows[i].push_back({j, {}});
+                    hit = &rows[i].back().second;
+                }
+                hit->push_back(Term{cell_to_input[c], v});
+            }
+        }
+    std::vector<int> row_ptr(d + 1, 0), col, term_ptr(1, 0), term_in;
+    std::vector<double> term_coef;
+    int max_row = 1;
+    for (int i = 0; i < d; ++i) {
+        std::sort(rows[i].begin(), rows[i].end(), [](const auto &x, const auto &y) { return x.first < y.first; });
+        for (auto &e : rows[i]) {
+            col.push_back(e.first);
+            for (const Term &t : e.second) {
+                term_in.push_back(t.in);
+                term_coef.push_back(t.coef);
+            }
+            term_ptr.push_back((int)term_in.size());
+        }
+        row_ptr[i + 1] = (int)col.size();
+        max_row = std::max(max_row, row_ptr[i + 1] - row_ptr[i]);
+    }
+    VoCsrDev &C = pl->csr;
+    C.d = d; C.nnz = (int)col.size(); C.max_row = max_row;
+    cudaError_t e = track_vo(pl, &C.row_ptr, row_ptr);
+    if (e == cudaSuccess) e = track_vo(pl, &C.col, col);
+    if (e == cudaSuccess) e = track_vo(pl, &C.term_ptr, term_ptr);
+    if (e == cudaSuccess) e = track_vo(pl, &C.term_in, term_in);
+    if (e == cudaSuccess) e = track_vo(pl, &C.term_coef, term_coef);
+    return e;
+}
+
 // Structured-grid detection for vo_grid.cuh.  Leaves pl->grid.ok = 0 unless the element data is exactly the
 // 5-point pixel operator the grid kernel evaluates (every check below is against the arrays the caller
 // passed, nothing is assumed from names):
@@ -395,8 +478,7 @@ static inline size_t grid_packed_bytes(const GridDev &G, int NT) {
 //     C = 8, W =  8, R = 2 : 176 us   (8 fat warps, half the per-step overhead per node)
 // The kernel is latency-bound at 4 warps per scheduler: more resident warps win over less overhead per node.
 // GPDE_GRID_R=1 forces one row per stage (A/B runs).
-static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t &stage) {
-    const char *e = getenv("GPDE_GRID_R");
+static inline bool grid_pick(const VoEnv &env, GridDev &G, int NT, int &R, int &NS, int &W, size_t &stage) {
     const int C = 4;
     W = 16;
     if (grid_nstrips(G.ncol, C) > W) return false;
@@ -404,7 +486,7 @@ static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t
     G.nstrips = grid_nstrips(G.ncol, C);
     G.groups = W / G.nstrips;
     const size_t budget = 225 * 1024 - 512;
-    for (R = (e ? atoi(e) : 2); R >= 1; --R) {
+    for (R = env.grid_r; R >= 1; --R) {
         stage = grid_layout(G, R, NT);
         NS = (int)std::min<size_t>(R == 2 ? 3 : 4, budget / stage);
         if (NS >= 2) return true;
@@ -414,16 +496,12 @@ static inline bool grid_pick(GridDev &G, int NT, int &R, int &NS, int &W, size_t
 
 // GPDE_VO_PATH=v1 forces the unfused version-1 kernels (A/B testing, fallback check)
 static bool use_fused(const gpde_vo_plan *pl) {
-    if (!pl->tiles.ok) return false;
-    const char *e = getenv("GPDE_VO_PATH");
-    return !(e && strcmp(e, "v1") == 0);
+    return pl->tiles.ok && !pl->env.path_v1;
 }
 
 // GPDE_VO_PATH=fused keeps the structured-grid kernel out as well (generic fused kernel instead)
 static bool use_grid(const gpde_vo_plan *pl) {
-    if (!pl->grid.ok) return false;
-    const char *e = getenv("GPDE_VO_PATH");
-    return !(e && (strcmp(e, "v1") == 0 || strcmp(e, "fused") == 0));
+    return pl->grid.ok && !pl->env.path_v1 && !pl->env.path_fused;
 }
 
 // Lean structured-grid kernel (vo_grid2.cuh): nx in {16, 32, 64, 128}, even ny, no load vector.  Returns 1 if it
@@ -432,10 +510,7 @@ static bool use_grid(const gpde_vo_plan *pl) {
 // mesh-side conditions and the decomposition of the lean kernel for m weighting functions (rho: no V inside)
 static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid2Dev &G, int &NT, int &NX, size_t &smem) {
     const GridDev &G0 = pl->grid;
-    {
-        const char *e = getenv("GPDE_GRID_V");
-        if (e && atoi(e) == 1) return false;
-    }
+    if (pl->env.no_grid2) return false;
     const int nx = G0.nx, ny = G0.ny;
     if (!G0.ok || !(nx == 16 || nx == 32 || nx == 64 || nx == 128) || ny < 2 || (ny & 1)) return false;
     if (G0.has_load && sub_f) return false;
@@ -457,24 +532,21 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     G.y_pitch = 2 * nx + 8;
     G.y_off = S * G.a_pitch * 8;
     G.v_off = 0;
-    G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128);
+    G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128) + kGrid2MaskBytes;
     G.stage_bytes = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
     const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 258 * sizeof(double);
     // V ring: three 2-row stages when they fit (the sample groups of a CTA may then drift a stage apart), else two
     G.nvs = rho ? 0 : ((fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2);
-    {
-        const char *e = getenv("GPDE_GRID2_NVS");
-        if (e && !rho && (atoi(e) == 2 || atoi(e) == 3)) G.nvs = atoi(e);
-    }
+    if (!rho && (pl->env.grid2_nvs == 2 || pl->env.grid2_nvs == 3)) G.nvs = pl->env.grid2_nvs;
     smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
     if (smem > 227 * 1024) return false;
-    G.flags = getenv("GPDE_GRID2_FLAGS") ? atoi(getenv("GPDE_GRID2_FLAGS")) : 0;
+    G.flags = pl->env.grid2_flags;
     return true;
 }
 
-static void grid2_pack(const Grid2Dev &G, const double *V, int m, int NT, int NX, double *Vp, cudaStream_t st) {
+static void grid2_pack(const Grid2Dev &G, const double *V, int m, int NT, int NX, double *Vp, int n_sm, cudaStream_t st) {
     const long long total = (long long)(G.ny + 1) * G.v_row_bytes / 8;
-    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)n_sm * 8);
     vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
 }
 
@@ -492,15 +564,11 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     if (!rho && ((uintptr_t)workspace & 15)) return 0;
     const int S = 8 * G.groups;
     double *Vp = (double *)workspace;
-    if (!rho && !prepacked) grid2_pack(G, V, m, NT, NX, Vp, st);
+    if (!rho && !prepacked) grid2_pack(G, V, m, NT, NX, Vp, pl->n_sm, st);
     const unsigned grid = (unsigned)((B + S - 1) / S);
     // the residual kernel is launched as a programmatic dependent of the packing kernel (its prologue and first
     // a / y stages overlap the packing); GPDE_GRID2_PDL=0 keeps the plain stream order
-    bool pdl = !rho && !prepacked;
-    {
-        const char *e = getenv("GPDE_GRID2_PDL");
-        if (e && atoi(e) == 0) pdl = false;
-    }
+    const bool pdl = !rho && !prepacked && pl->env.grid2_pdl;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -556,16 +624,16 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
     int R, NS, W;
     size_t stage;
-    if (!grid_pick(G, NT, R, NS, W, stage)) return 0;
+    if (!grid_pick(pl->env, G, NT, R, NS, W, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     double *Vp = (double *)workspace;
     {
         const long long total = (long long)grid_packed_bytes(G, NT) / 8;
-        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 8);
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 8);
         vo_grid_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, Vp);
     }
     const int S = 8 * G.groups;
-    const int dbg = getenv("GPDE_GRID_DEBUG") ? atoi(getenv("GPDE_GRID_DEBUG")) : 0;   // timing experiments only
+    const int dbg = pl->env.grid_debug;   // timing experiments only
     const unsigned grid = (unsigned)((B + S - 1) / S);
     const size_t smem = (size_t)NS * stage + 2 * NS * sizeof(unsigned long long) + 16 * sizeof(double);
 #define GPDE_LAUNCH_GRID(NTV, RV, WV, CV)                                                                        \
@@ -602,7 +670,7 @@ static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
     int R, NS, W;
     size_t stage;                                     // no V rows in the stage
-    if (!grid_pick(G, 0, R, NS, W, stage)) return 0;
+    if (!grid_pick(pl->env, G, 0, R, NS, W, stage)) return 0;
     if (!sub_f) G.has_load = 0;
     const int S = 8 * G.groups;
     const unsigned grid = (unsigned)((B + S - 1) / S);
@@ -626,7 +694,7 @@ static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride
     const VoDev &P = pl->dev;
     const size_t per = sizeof(double) * (size_t)P.n_inputs;
     const size_t cap = 200 * 1024;
-    const int nsm = sm_count(pl->device);
+    const int nsm = pl->n_sm;
     int S = 1;
     if (B >= 4LL * nsm * 2 && 4 * per <= cap) S = 4;
     else if (B >= 2LL * nsm * 2 && 2 * per <= cap) S = 2;
@@ -675,7 +743,7 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
         const unsigned grid = (unsigned)((B + kFS - 1) / kFS);
         const int sub_f = (flags & 1) ? 0 : 1;
         constexpr bool kCanAsync = sizeof(T) == 8;
-        const bool use_async = kCanAsync && pl->tiles.async_ok && !getenv("GPDE_VO_SYNC_STAGING");
+        const bool use_async = kCanAsync && pl->tiles.async_ok && !pl->env.sync_staging;
 #define GPDE_LAUNCH_FUSED(WN)                                                                                  \
     {                                                                                                          \
         auto kern = use_async ? vo_fused_kernel<T, WN, kCanAsync> : vo_fused_kernel<T, WN, false>;             \
@@ -710,7 +778,7 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
         double *Vp = ws + (size_t)B * dp;
         {
             const long long total = (long long)dp * ldb;
-            const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 8);
+            const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 8);
             vo_gemm_pack_kernel_t<T><<<grid, 256, 0, st>>>(V, d, m, Vp, dp, ldb);
         }
         dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
@@ -743,8 +811,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
         if (use_grid(pl) && !((uintptr_t)a & 15) && !(a_stride & 1) && !((uintptr_t)workspace & 15)) {
             const int d = pl->dev.d, mp = gemm_dp(m), bn = 128, ldb = (d + bn - 1) / bn * bn;
             double *Sp = (double *)workspace, *Vt = Sp + (size_t)B * mp, *w = Vt + (size_t)mp * ldb;
-            const char *ev = getenv("GPDE_VO_EXPAND");   // GPDE_VO_EXPAND=gemm: the general GEMM also for m <= 32 (A/B runs)
-            if (m <= 32 && !(ev && strcmp(ev, "gemm") == 0)) {
+            if (m <= 32 && !pl->env.expand_gemm) {   // GPDE_VO_EXPAND=gemm: the general GEMM also for m <= 32 (A/B runs)
                 // contraction length m <= 32: one launch, operands read in place (vo_expand.cuh)
                 w = (double *)workspace;
                 Grid2Dev G2;
@@ -754,7 +821,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
                 const long long ldw = lean ? (((long long)d + 3) & ~3ll) : d;   // the general grid kernel wants y contiguous
                 const int n_tiles = (d + 7) / 8;
                 const unsigned gx = (unsigned)((B + 8 * kExpandMT * kExpandWarps - 1) / (8 * kExpandMT * kExpandWarps));
-                const int nch = std::max(1, std::min(n_tiles, (int)(4 * sm_count(pl->device) / gx)));
+                const int nch = std::max(1, std::min(n_tiles, (int)(4 * pl->n_sm / gx)));
                 const int tpc = std::min((n_tiles + nch - 1) / nch, 64);         // <= 64 n-tiles of V per CTA in shared memory
                 const dim3 grid(gx, (unsigned)((n_tiles + tpc - 1) / tpc));
                 const size_t smem = (size_t)tpc * 8 * kExpandVPitch * sizeof(double);
@@ -780,7 +847,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
             } else {
             {
                 const long long total = (long long)B * mp;
-                const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 8);
+                const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 8);
                 vo_gemm_pad_rows_kernel<<<grid, 256, 0, st>>>((const double *)s, (long long)B, m, Sp, mp);
                 vo_gemm_pack_transposed_kernel<<<dim3((unsigned)(ldb / 32), (unsigned)((mp + 31) / 32)), dim3(32, 8), 0, st>>>(
                     (const double *)V, d, m, Vt, mp, ldb);
@@ -810,7 +877,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     }
     double *w = (double *)workspace;
     const long long total = B * (long long)pl->dev.d;
-    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)sm_count(pl->device) * 16);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 16);
     vo_expand_kernel<T><<<grid, 256, 0, st>>>(s, V, w, B, pl->dev.d, m);
     GPDE_CUDA_OK(cudaGetLastError());
     return launch_matvec<T, double, T>(pl, a, a_stride, a_is_log, w, (const T *)nullptr, 0, 0, (double *)nullptr, 0,
@@ -877,8 +944,9 @@ int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int
     if (f_full)
         for (int i = 0; i < d; ++i) f_free[i] = f_full[free_dofs[i]];
 
-    gpde_vo_plan *pl = new gpde_vo_plan();
+    gpde_vo_plan *pl = new gpde_vo_plan();   // (its VoEnv member reads the experiment switches here, once)
     pl->device = device;
+    pl->n_sm = sm_count(device);
     DeviceGuard guard(device);
     VoDev &D = pl->dev;
     D.n_nodes = n_nodes; D.n_cells = n_cells; D.n_inputs = n_inputs; D.d = d; D.n_bc = n_bc; D.nslots = nslots;
@@ -890,6 +958,7 @@ int gpde_vo_plan_create(gpde_vo_plan **plan, int n_nodes, int n_cells, const int
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c1, c1);
     if (e == cudaSuccess) e = track_vo(pl, &D.ell_c2, c2);
     if (e == cudaSuccess) e = track_vo(pl, &D.f_free, f_free);
+    if (e == cudaSuccess) e = build_csr_terms(pl, n_cells, cell_dofs, Ke, cell_to_input, d, src);
     if (e == cudaSuccess) e = build_fused_tiles(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, d, src, f_free);
     if (e == cudaSuccess)
         e = build_grid_plan(pl, n_nodes, n_cells, cell_dofs, Ke, cell_to_input, n_inputs, free_dofs, d, bc_dofs, n_bc,
@@ -935,7 +1004,8 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
         const size_t mp = (size_t)gemm_dp(m), ldb = ((size_t)pl->dev.d + 127) / 128 * 128;
         need = std::max(need, sizeof(double) * ((size_t)B * mp + mp * ldb + (size_t)B * pl->dev.d));
     }
-    if (pl->grid.ok && m > 0 && m <= 32) need = std::max(need, grid_packed_bytes(pl->grid, 4));   // packed V
+    if (pl->grid.ok && m > 0 && m <= 32)   // packed V (+ the per-row tile masks of the lean kernel)
+        need = std::max(need, grid_packed_bytes(pl->grid, 4) + (size_t)(pl->grid.ny + 1) * kGrid2MaskBytes);
     return need;
 }
 
@@ -948,7 +1018,58 @@ int gpde_vo_pack_weights_f64(const gpde_vo_plan *pl, const double *V, int m, int
     size_t smem;
     if (!use_grid(pl) || !grid2_setup(pl, m, false, (flags & 1) ? 0 : 1, G, NT, NX, smem)) return 1;
     DeviceGuard guard(pl->device);
-    grid2_pack(G, V, m, NT, NX, (double *)workspace, (cudaStream_t)stream);
+    grid2_pack(G, V, m, NT, NX, (double *)workspace, pl->n_sm, (cudaStream_t)stream);
+    GPDE_CUDA_OK(cudaGetLastError());
+    return GPDE_OK;
+}
+
+int gpde_vo_posterior_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, const double *V, int64_t v_stride,
+                          int m, const double *rho, const double *noise_var, const double *g, const double *prec,
+                          double *mean, double *vars, int *info, int64_t N, gpde_stream_t stream) {
+    if (!pl || N < 0 || m <= 0) return fail(GPDE_ERR_ARG, "vo_posterior: bad argument");
+    if (m > 64) return fail(GPDE_ERR_SIZE, "vo_posterior: m = %d > 64 weighting functions per data point", m);
+    if (N == 0) return GPDE_OK;
+    if (!a || !V || !rho || !noise_var || !g || !prec || !mean || !vars) return fail(GPDE_ERR_ARG, "vo_posterior: null argument");
+    if (v_stride != 0 && v_stride != (int64_t)pl->dev.d * m) return fail(GPDE_ERR_ARG, "vo_posterior: v_stride must be 0 or d*m");
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m <= 32) {
+        auto kern = vo_posterior_kernel<32>;
+        const size_t smem = post_smem_bytes<32>(pl->csr.max_row);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)N, kPostThreads, smem, st>>>(pl->csr, a, (long long)a_stride, V, (long long)v_stride, m, rho, noise_var, g,
+                                                      prec, mean, vars, info);
+    } else {
+        auto kern = vo_posterior_kernel<64>;
+        const size_t smem = post_smem_bytes<64>(pl->csr.max_row);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)N, kPostThreads, smem, st>>>(pl->csr, a, (long long)a_stride, V, (long long)v_stride, m, rho, noise_var, g,
+                                                      prec, mean, vars, info);
+    }
+    GPDE_CUDA_OK(cudaGetLastError());
+    return GPDE_OK;
+}
+
+int gpde_vo_moments_f64(const gpde_vo_plan *pl, const double *a, int64_t a_stride, const double *V, int64_t v_stride, int m,
+                        const double *rho, const double *v, double *out_r, double *out_s2, int64_t N, gpde_stream_t stream) {
+    if (!pl || N < 0 || m <= 0) return fail(GPDE_ERR_ARG, "vo_moments: bad argument");
+    if (m > 64) return fail(GPDE_ERR_SIZE, "vo_moments: m = %d > 64 weighting functions per data point", m);
+    if (N == 0) return GPDE_OK;
+    if (!a || !V || !rho || !v || !out_r || !out_s2) return fail(GPDE_ERR_ARG, "vo_moments: null argument");
+    if (v_stride != 0 && v_stride != (int64_t)pl->dev.d * m) return fail(GPDE_ERR_ARG, "vo_moments: v_stride must be 0 or d*m");
+    DeviceGuard guard(pl->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m <= 32) {
+        auto kern = vo_moments_kernel<32>;
+        const size_t smem = moments_smem_bytes<32>(pl->csr.max_row);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)N, kPostThreads, smem, st>>>(pl->csr, a, (long long)a_stride, V, (long long)v_stride, m, rho, v, out_r, out_s2);
+    } else {
+        auto kern = vo_moments_kernel<64>;
+        const size_t smem = moments_smem_bytes<64>(pl->csr.max_row);
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)N, kPostThreads, smem, st>>>(pl->csr, a, (long long)a_stride, V, (long long)v_stride, m, rho, v, out_r, out_s2);
+    }
     GPDE_CUDA_OK(cudaGetLastError());
     return GPDE_OK;
 }

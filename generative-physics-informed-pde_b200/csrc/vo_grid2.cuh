@@ -21,6 +21,7 @@
 // Shared memory: 2 a/y stages | 2-3 V stages | barriers | exp table; the a/y stages are zero-initialised once so that the
 // few halo reads that fall outside a sample's rows see finite numbers.
 #pragma once
+#include "exp256.cuh"
 
 namespace gpde {
 
@@ -97,110 +98,34 @@ __device__ __forceinline__ double exp_tab16c(double x, unsigned tab) {   // tab 
     return __hiloint2double(__double2hiint(v) + ((ki << 16) & 0xfff00000), __double2loint(v));
 }
 
-// exp(x) = 2^e * T[j] * P4(r),  x = (256 e + j) ln2/256 + r,  |r| <= ln2/512: degree 4 suffices (r^5/120 < 4e-17), two FP64
-// operations less per value than the 16-entry scheme; T = 2^(j/256) in shared memory (2 KB)
-__constant__ double kExp256Tab[256] = {
-    1.0, 1.0027112750502025, 1.0054299011128027, 1.0081558981184175,
-    1.0108892860517005, 1.0136300849514894, 1.016378314910953, 1.019133996077738,
-    1.0218971486541166, 1.0246677928971357, 1.0274459491187637, 1.030231637686041,
-    1.0330248790212284, 1.0358256936019572, 1.0386341019613787, 1.041450124688316,
-    1.0442737824274138, 1.0471050958792898, 1.0499440858006872, 1.0527907730046264,
-    1.0556451783605572, 1.0585073227945128, 1.061377227289262, 1.0642549128844645,
-    1.0671404006768237, 1.0700337118202419, 1.0729348675259756, 1.075843889062791,
-    1.0787607977571199, 1.0816856149932152, 1.0846183622133092, 1.0875590609177697,
-    1.0905077326652577, 1.0934643990728858, 1.0964290818163769, 1.099401802630222,
-    1.102382583307841, 1.1053714457017412, 1.1083684117236787, 1.1113735033448175,
-    1.1143867425958924, 1.1174081515673693, 1.1204377524096067, 1.12347556733302,
-    1.1265216186082418, 1.129575928566288, 1.1326385195987192, 1.1357094141578055,
-    1.1387886347566916, 1.1418762039695616, 1.1449721444318042, 1.148076478840179,
-    1.1511892299529827, 1.154310420590216, 1.1574400736337511, 1.1605782120274988,
-    1.1637248587775775, 1.1668800369524817, 1.1700437696832502, 1.1732160801636373,
-    1.1763969916502812, 1.1795865274628758, 1.182784710984341, 1.1859915656609938,
-    1.189207115002721, 1.1924313825831512, 1.1956643920398273, 1.1989061670743806,
-    1.202156731452703, 1.2054161090051239, 1.2086843236265816, 1.2119613992768012,
-    1.215247359980469, 1.2185422298274085, 1.2218460329727576, 1.2251587936371455,
-    1.22848053610687, 1.2318112847340759, 1.2351510639369334, 1.2384998981998165,
-    1.241857812073484, 1.245224830175258, 1.2486009771892048, 1.2519862778663162,
-    1.255380757024691, 1.2587844395497165, 1.2621973503942507, 1.2656195145788063,
-    1.2690509571917332, 1.2724917033894028, 1.275941778396392, 1.2794012075056693,
-    1.2828700160787783, 1.2863482295460256, 1.2898358734066657, 1.2933329732290895,
-    1.2968395546510096, 1.3003556433796506, 1.3038812651919358, 1.3074164459346773,
-    1.3109612115247644, 1.3145155879493546, 1.318079601266064, 1.3216532776031575,
-    1.3252366431597413, 1.3288297242059544, 1.3324325470831615, 1.3360451382041458,
-    1.339667524053303, 1.3432997311868353, 1.3469417862329458, 1.3505937158920345,
-    1.3542555469368927, 1.3579273062129011, 1.3616090206382248, 1.365300717204012,
-    1.3690024229745905, 1.3727141650876684, 1.3764359707545302, 1.380167867260238,
-    1.383909881963832, 1.387662042298529, 1.3914243757719262, 1.3951969099662003,
-    1.3989796725383112, 1.4027726912202048, 1.4065759938190154, 1.4103896082172707,
-    1.4142135623730951, 1.4180478843204152, 1.4218926021691656, 1.4257477441054942,
-    1.42961333839197, 1.433489413367789, 1.4373759974489824, 1.4412731191286257,
-    1.4451808069770467, 1.449099089642035, 1.4530279958490526, 1.4569675544014438,
-    1.460917794180647, 1.4648787441464057, 1.4688504333369818, 1.4728328908693675,
-    1.4768261459394993, 1.4808302278224719, 1.4848451658727524, 1.488870989524397,
-    1.4929077282912648, 1.4969554117672355, 1.5010140696264256, 1.5050837316234065,
-    1.5091644275934228, 1.5132561874526098, 1.5173590411982147, 1.5214730189088146,
-    1.5255981507445384, 1.529734466947287, 1.533881997840956, 1.5380407738316568,
-    1.5422108254079407, 1.5463921831410214, 1.550584877685, 1.5547889397770887,
-    1.559004400237837, 1.5632312899713576, 1.567469639965553, 1.5717194812923414,
-    1.5759808451078865, 1.5802537626528246, 1.5845382652524937, 1.588834384317164,
-    1.593142151342267, 1.597461597908627, 1.6017927556826934, 1.606135656416771,
-    1.6104903319492543, 1.6148568142048607, 1.6192351351948637, 1.6236253270173289,
-    1.6280274218573478, 1.632441451987275, 1.6368674497669644, 1.6413054476440063,
-    1.645755478153965, 1.6502175739206177, 1.6546917676561943, 1.6591780921616162,
-    1.6636765803267364, 1.6681872651305825, 1.6727101796415966, 1.6772453570178785,
-    1.681792830507429, 1.6863526334483934, 1.6909247992693053, 1.6955093614893326,
-    1.7001063537185235, 1.7047158096580513, 1.709337763100463, 1.713972247929926,
-    1.718619298122478, 1.723278947746274, 1.7279512309618377, 1.732636182022311,
-    1.7373338352737062, 1.7420442251551564, 1.746767386199169, 1.7515033530318782,
-    1.7562521603732995, 1.761013843037584, 1.7657884359332727, 1.7705759740635547,
-    1.7753764925265212, 1.7801900265154245, 1.785016611318935, 1.789856282321401,
-    1.7947090750031072, 1.7995750249405351, 1.804454167806624, 1.809346539371032,
-    1.8142521755003989, 1.8191711121586085, 1.8241033854070534, 1.8290490314048973,
-    1.8340080864093424, 1.8389805867758937, 1.843966568958626, 1.8489660695104508,
-    1.8539791250833855, 1.8590057724288205, 1.864046048397789, 1.8690999899412386,
-    1.8741676341103, 1.8792490180565602, 1.8843441790323345, 1.8894531543909392,
-    1.8945759815869656, 1.8997126981765553, 1.9048633418176741, 1.9100279502703899,
-    1.9152065613971474, 1.9203992131630474, 1.925605943636125, 1.930826790987627,
-    1.9360617934922943, 1.9413109895286405, 1.9465744175792332, 1.9518521162309783,
-    1.9571441241754002, 1.9624504802089273, 1.9677712232331759, 1.9731063922552343,
-    1.978456026387951, 1.9838201648502194, 1.9891988469672663, 1.9945921121709402,
-};
-__constant__ double kExpQ[6] = {369.3299304675746, -0.002707606173999011, -6.327543041662719e-14,
-                                4.16666666666666666667e-02, 1.66666666666666666667e-01, 0.5};
-__device__ __forceinline__ double exp_tab256c(double x, unsigned tab) {
-    const double t = fma(x, kExpQ[0], 6755399441055744.0);   // 1.5*2^52: low word = rint(256 x / ln2)
-    const int ki = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    double r = fma(kd, kExpQ[1], x);                          // 34-bit head of ln2/256: the product is exact
-    r = fma(kd, kExpQ[2], r);
-    double p = fma(kExpQ[3], r, kExpQ[4]);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const double v = p * lds64(tab + ((ki << 3) & 0x7f8));
-    return __hiloint2double(__double2hiint(v) + ((ki << 12) & 0xfff00000), __double2loint(v));
-}
-
-// V[d,m] row-major -> per node row t: [strip q][pair p < 2 NT][lane][2] then [strip q][k][4] (NX = 1 only).
-//   pair p, half h: idx = 2 p + h = jj * NT + tt; lane = 4 n + kk holds V[t*ncol + 16 q + 4 kk + jj][8 tt + n];
+// V[d,m] row-major -> per node row t: [strip q][n-tile tt < NT][half ph < 2][lane][2], then [strip q][k][4] (NX = 1 only),
+// then one 32-bit mask per strip (8 words, 32 bytes).
+//   tile tt, half ph, element h: k-step jj = 2 ph + h; lane = 4 n + kk holds V[t*ncol + 16 q + 4 kk + jj][8 tt + n];
 //   extra column: V[t*ncol + 16 q + 4 k + j][8 NT]     (0 outside the matrix)
+//   mask of (t, q): bit tt set <=> the 16 x 8 block of V behind n-tile tt has a non-zero entry, bit 7 <=> the extra column
+//   has one.  The residual kernel skips the B-fragment loads and the four DMMAs of a tile whose block is all zero
+//   (exact: it only drops products with 0): V = W of the coarse-grained-residual sampler (VirtualObservables.py:297-321)
+//   has <= 4 non-zero columns per block (P1 hat functions of the coarse mesh), i.e. 1-2 of its 3-4 tiles.
+constexpr int kGrid2MaskBytes = 32;
 __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, int m, int NT, int NX,
                                      double *__restrict__ Vp) {
     // programmatic dependent launch: the residual kernel may start its prologue (shared-memory setup, first a / y
     // stages) now; it waits for this grid (griddepcontrol.wait) before it touches the packed rows
     asm volatile("griddepcontrol.launch_dependents;");
     const int per_strip = 4 * NT * 32, per_row = G.v_row_bytes / 8, main = G.nstrips * per_strip;
+    const int data = main + (NX ? G.nstrips * 16 : 0);     // doubles of a row before the masks
     const long long total = (long long)(G.ny + 1) * per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int t = (int)(i / per_row);
         int rem = (int)(i - (long long)t * per_row);
+        if (rem >= data) continue;                           // mask words: written below
         int c, col;
         if (rem < main) {
             const int q = rem / per_strip;
             rem -= q * per_strip;
             const int h = rem & 1, lane = (rem >> 1) & 31, p = rem >> 6;
-            const int idx = 2 * p + h, jj = idx / NT, tt = idx - jj * NT;
+            const int tt = p >> 1, jj = 2 * (p & 1) + h;
             c = 16 * q + 4 * (lane & 3) + jj;
             col = 8 * tt + (lane >> 2);
         } else {
@@ -209,6 +134,51 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
             col = 8 * NT;
         }
         Vp[i] = (c < G.ncol && col < m && (NX || col < 8 * NT)) ? V[((long long)t * G.ncol + c) * m + col] : 0.0;
+    }
+    // masks: one warp per (node row, strip)
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int mcols = min(m, 8 * NT + (NX ? 1 : 0));
+    for (long long w = warp; w < (long long)(G.ny + 1) * 8; w += nwarps) {
+        const int t = (int)(w >> 3), q = (int)(w & 7);
+        unsigned bits = 0;
+        if (q < G.nstrips) {
+            for (int i = lane; i < 16 * mcols; i += 32) {
+                const int c = 16 * q + i / mcols, col = i % mcols;
+                if (c < G.ncol && V[((long long)t * G.ncol + c) * m + col] != 0.0) bits |= col < 8 * NT ? 1u << (col >> 3) : 0x80u;
+            }
+        }
+        bits = __reduce_or_sync(0xffffffffu, bits);
+        if (lane == 0) reinterpret_cast<unsigned *>(Vp + (long long)t * per_row + data)[q] = bits;
+    }
+}
+
+// the B fragments and DMMAs of the n-tiles named by the compile-time MASK (straight-line code per mask value: the tiles'
+// accumulator chains are independent and interleave)
+template <int NT, int MASK, typename LoadPair>
+__device__ __forceinline__ void grid2_contract_tiles(double (&acc)[NT][2], const double (&Sv)[4], LoadPair load_pair) {
+    double bf[NT][4];
+#pragma unroll
+    for (int tt = 0; tt < NT; ++tt)
+        if (MASK >> tt & 1) {
+            const double2 v0 = load_pair(2 * tt), v1 = load_pair(2 * tt + 1);
+            bf[tt][0] = v0.x; bf[tt][1] = v0.y; bf[tt][2] = v1.x; bf[tt][3] = v1.y;
+        }
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int tt = 0; tt < NT; ++tt)
+            if (MASK >> tt & 1) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[tt][jj]);
+}
+template <int NT, typename LoadPair>
+__device__ __forceinline__ void grid2_contract(unsigned msk, double (&acc)[NT][2], const double (&Sv)[4], LoadPair load_pair) {
+    switch (msk & ((1u << NT) - 1u)) {
+#define GPDE_G2_CASE(M) case M: if constexpr (M < (1 << NT)) grid2_contract_tiles<NT, M>(acc, Sv, load_pair); break;
+        GPDE_G2_CASE(1) GPDE_G2_CASE(2) GPDE_G2_CASE(3) GPDE_G2_CASE(4) GPDE_G2_CASE(5) GPDE_G2_CASE(6) GPDE_G2_CASE(7)
+        GPDE_G2_CASE(8) GPDE_G2_CASE(9) GPDE_G2_CASE(10) GPDE_G2_CASE(11) GPDE_G2_CASE(12) GPDE_G2_CASE(13)
+        GPDE_G2_CASE(14) GPDE_G2_CASE(15)
+#undef GPDE_G2_CASE
+        default: break;
     }
 }
 
@@ -345,6 +315,8 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     const unsigned a_lane1 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? nx * 8 : 0);   // pixel row 2 ts + 1
     const unsigned v_lane = (q * NP * 32 + lane) * 16;                       // inside a V stage
     const unsigned x_lane = G.nstrips * NP * 512 + (q * 4 + k) * 32;
+    const int mask_dbl = (G.v_row_bytes - kGrid2MaskBytes) >> 3;          // doubles of a packed row before its masks
+    const unsigned m_lane = G.v_row_bytes - kGrid2MaskBytes + 4 * q;
     const unsigned row_bytes = ncol * 8;
     const double rh = G.rh;
 
@@ -369,7 +341,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 
     // one node row: new row (un, an) in, residual of the row below (uc between ap and an) out
     auto node_row = [&](const double (&un)[4], double unl, double unr, const double (&an)[5], unsigned v_addr,
-                        unsigned x_addr, const double *v_glob, int t_out) {
+                        unsigned x_addr, unsigned msk_s, const double *v_glob, int t_out) {
         double fh[5];
         fh[0] = (ap[0] + an[0]) * (uc[0] - ulc);
 #pragma unroll
@@ -391,36 +363,31 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                 if (!is_right) dst[3] = G.scale * Sv[3];
             }
         } else {
-            double bf[4 * NT];
             if (v_glob) {   // last node row: packed V row from global memory
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double2 v = __ldg(reinterpret_cast<const double2 *>(v_glob) + (q * NP + p) * 32 + lane);
-                    bf[2 * p] = v.x; bf[2 * p + 1] = v.y;
+                const unsigned msk = __ldg(reinterpret_cast<const unsigned *>(v_glob + mask_dbl) + q);
+                const double2 *vg = reinterpret_cast<const double2 *>(v_glob) + q * NP * 32 + lane;
+                grid2_contract<NT>(msk, acc, Sv, [&](int p) { return __ldg(vg + p * 32); });
+                if constexpr (NX > 0) {
+                    if (msk & 0x80u) {
+                        const double2 *xp = reinterpret_cast<const double2 *>(v_glob) + G.nstrips * NP * 32 + (q * 4 + k) * 2;
+                        const double2 x0 = __ldg(xp), x1 = __ldg(xp + 1);
+                        accx = fma(Sv[0], x0.x, accx);
+                        accx = fma(Sv[1], x0.y, accx);
+                        accx = fma(Sv[2], x1.x, accx);
+                        accx = fma(Sv[3], x1.y, accx);
+                    }
                 }
             } else {
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    const double2 v = lds128(v_addr + p * 512);
-                    bf[2 * p] = v.x; bf[2 * p + 1] = v.y;
+                grid2_contract<NT>(msk_s, acc, Sv, [&](int p) { return lds128(v_addr + p * 512); });
+                if constexpr (NX > 0) {
+                    if (msk_s & 0x80u) {
+                        const double2 x0 = lds128(x_addr), x1 = lds128(x_addr + 16);
+                        accx = fma(Sv[0], x0.x, accx);
+                        accx = fma(Sv[1], x0.y, accx);
+                        accx = fma(Sv[2], x1.x, accx);
+                        accx = fma(Sv[3], x1.y, accx);
+                    }
                 }
-            }
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-                for (int tt = 0; tt < NT; ++tt) dmma884(acc[tt][0], acc[tt][1], Sv[jj], bf[jj * NT + tt]);
-            if constexpr (NX > 0) {
-                double2 x0, x1;
-                if (v_glob) {
-                    const double2 *xp = reinterpret_cast<const double2 *>(v_glob) + G.nstrips * NP * 32 + (q * 4 + k) * 2;
-                    x0 = __ldg(xp); x1 = __ldg(xp + 1);
-                } else {
-                    x0 = lds128(x_addr); x1 = lds128(x_addr + 16);
-                }
-                accx = fma(Sv[0], x0.x, accx);
-                accx = fma(Sv[1], x0.y, accx);
-                accx = fma(Sv[2], x1.x, accx);
-                accx = fma(Sv[3], x1.y, accx);
             }
         }
 #pragma unroll
@@ -457,6 +424,8 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const unsigned ya = sb + y_lane + rr * row_bytes;
+            unsigned msk_rr = 0;
+            if constexpr (!RHO) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(msk_rr) : "r"(vb + m_lane + rr * G.v_row_bytes));
             double un[4], unl, unr, an[5];
             unl = lds64(ya - 8);
 #pragma unroll
@@ -483,7 +452,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                     for (int j = 0; j < 5; ++j) an[j] = exp(lds64(aa + 8 * j));
                 }
             }
-            node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, nullptr,
+            node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, msk_rr, nullptr,
                      2 * ts + rr);
         }
         if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
@@ -506,7 +475,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     {
         if (!RHO) asm volatile("griddepcontrol.wait;" ::: "memory");   // packed row ny is read with plain loads
         const double un[4] = {0.0, 0.0, 0.0, 0.0}, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        node_row(un, 0.0, 0.0, an, 0u, 0u,
+        node_row(un, 0.0, 0.0, an, 0u, 0u, 0u,
                  RHO ? nullptr : reinterpret_cast<const double *>(reinterpret_cast<const char *>(Vp) + (size_t)ny * G.v_row_bytes),
                  ny);
     }

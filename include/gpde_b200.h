@@ -164,6 +164,27 @@ int gpde_vo_residual_f32(const gpde_vo_plan *plan, const float *a, int64_t a_str
 int gpde_vo_pack_weights_f64(const gpde_vo_plan *plan, const double *V, int m, int flags, void *workspace,
                              gpde_stream_t stream);
 
+/* Batched Gaussian conditioning of all data points of a virtual-observable ensemble in ONE launch, matrix-free
+ * (VirtualObservable.update, bottleneck/VirtualObservables.py:642-669, looped over the data points at :891-898):
+ *     Lambda_n = Gamma_n C_n Gamma_n^T + diag(noise_var),  C_n = diag(1 / prec_n),  Gamma_n^T = K_ff(a_n) V_n
+ *     mean_n   = g_n - C_n Gamma_n^T Lambda_n^-1 (Gamma_n g_n - alpha_n),   Gamma_n g_n - alpha_n = V_n^T rho_n
+ *     vars_n   = diag(C_n) - diag(C_n Gamma_n^T Lambda_n^-1 Gamma_n C_n)
+ * a [N, n_inputs] conductivities (NOT logs; a_stride = 0: one field shared by all data points); V [d,m] shared
+ * (v_stride = 0) or [N,d,m] (v_stride = d*m); m <= 64; rho [N,d] = the fine residual K_fom(a_n) g~_n - f of the prior
+ * mean (the rho output of gpde_vo_residual with y = g); noise_var [m]; g, prec, mean, vars [N,d].
+ * info (device int32, may be NULL) receives GPDE_INFO_NOT_SPD if some Lambda_n has a non-positive pivot.           */
+int gpde_vo_posterior_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, const double *V,
+                          int64_t v_stride, int m, const double *rho, const double *noise_var, const double *g,
+                          const double *prec, double *mean, double *vars, int *info, int64_t N, gpde_stream_t stream);
+
+/* The two per-data-point terms of the precision hyper-update (VirtualObservablesEnsemble.update_vo_precision,
+ * bottleneck/VirtualObservables.py:985-990), all data points at once:
+ *     out_r [n,j] = (V_n^T rho_n)_j          = (Gamma_n mean_n - alpha_n)_j  for rho_n = rho(mean_n)
+ *     out_s2[n,j] = sum_i Gamma_n[j,i]^2 v[n,i]                                                                  */
+int gpde_vo_moments_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, const double *V, int64_t v_stride,
+                        int m, const double *rho, const double *v, double *out_r, double *out_s2, int64_t N,
+                        gpde_stream_t stream);
+
 /* q[B,d] = K_ff(a_b) (V s_b) = Gamma_b^T s_b  (VirtualObservables.py:663; with s = P r it is the
  * gradient of 1/2 r^T P r w.r.t. y).  With B = m, s = I and a_stride = 0 it yields Gamma itself. */
 int gpde_vo_residual_T_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,

@@ -88,3 +88,18 @@ def test_random_field_statistics_and_cell_average():
 def test_rom_size_guard():
     with pytest.raises(Exception):
         fem.P1Mesh(13, 13).dense_element_tensor()   # 338 cells > 290 (bottleneck/ROM.py:43-44)
+
+
+@pytest.mark.parametrize("nx,l", [(8, 0.1), (32, 0.25)])
+def test_rbf_weighting_matches_oracle_columns(nx, l):
+    """fem.rbf_weighting (vectorised) against oracle/fem_p1.rbf_columns (VirtualObservables.py:184-198,
+    fawkes/Expressions.py:26-31: exp(-|x - r0|^2 / l^2) interpolated at the fine free nodes)."""
+    mesh = fem.P1Mesh(nx, nx)
+    ph = physics.LinearEllipticPhysics('fom', 'ND', mesh)
+    centres = np.random.RandomState(4).uniform(size=(7, 2))
+    c, _ = fem_p1.unit_square_mesh(nx, nx)
+    _, _, free = fem_p1.dirichlet_left_right(c, "ND")
+    V = fem.rbf_weighting(mesh, ph.free_dofs, centres, l)
+    V0 = fem_p1.rbf_columns(c, free, centres, l)
+    assert V.shape == V0.shape == (ph.dim_out, 7)
+    assert np.abs(V - V0).max() < 1e-15

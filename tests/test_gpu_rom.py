@@ -241,9 +241,9 @@ def test_large_batch_config4_shard(dev):
 @pytest.mark.parametrize("dtype", [torch.float64, torch.float32])
 @pytest.mark.parametrize("ptype", ["ND", "NDP"])
 def test_thread_per_sample_kernels_match_cooperative_kernels(dtype, ptype, dev, monkeypatch):
-    """4x4 coarse mesh: the opt-in thread-per-sample kernels (rom_tps.cuh, GPDE_ROM_PATH=tps) and the default
-    cooperative kernels on the same inputs: u, dL/dlogX, dL/dF, with and without the stashed factor,
-    conductivity and log-conductivity input, ragged batch (B % 128 != 0)."""
+    """4x4 coarse mesh: the thread-per-sample kernels (rom_tps.cuh, the default for this shape) and the cooperative
+    kernels (GPDE_ROM_PATH=coop, read once at plan creation) on the same inputs: u, dL/dlogX, dL/dF, with and without
+    a factor argument, conductivity and log-conductivity input, ragged batch (B % 128 != 0)."""
     from gpde_b200 import ROM as rom_mod
     from gpde_b200.ROM import ROM
     from gpde_b200.workloads import Workload
@@ -254,13 +254,14 @@ def test_thread_per_sample_kernels_match_cooperative_kernels(dtype, ptype, dev, 
     gbar = torch.tensor(w.gbar_u, dtype=dtype, device=dev)
     out = {}
     for path in ("tps", "coop"):
-        if path == "tps":
-            monkeypatch.setenv("GPDE_ROM_PATH", "tps")
+        if path == "coop":
+            monkeypatch.setenv("GPDE_ROM_PATH", "coop")
         else:
             monkeypatch.delenv("GPDE_ROM_PATH", raising=False)
         rom = ROM.FromPhysics(w.physics['rom'], dtype=dtype, device=dev)
         plan = rom._get_plan()
         assert plan.lanes == (1 if path == "tps" else 8) and plan.half_bandwidth == 3 and plan.n_free == 15
+        assert plan.factor_doubles == (0 if path == "tps" else 60)    # no factor stash on the thread-per-sample path
         res = []
         for x_is_log, Xin in ((True, X), (False, torch.exp(X))):
             u, factor = rom_mod._launch_forward(plan, Xin, F, x_is_log, want_factor=True, info=rom._info_word(dev))

@@ -276,23 +276,23 @@ def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
     w = Workload("cfg1", B=21, seed=5)
     plan = VoPlan.cached(w.physics['fom'], dev, pixel_input=True)
     assert plan.fused_smem_bytes > 0
+    # the experiment switches are read once, at plan creation: one plan per kernel family
+    plan_fused, plan_v1 = plan.variant(GPDE_VO_PATH="fused"), plan.variant(GPDE_VO_PATH="v1")
+    plan_fused_sync = plan.variant(GPDE_VO_PATH="fused", GPDE_VO_SYNC_STAGING="1")
     a, y, gv = (torch.tensor(t, dtype=dtype, device=dev) for t in (w.log_image, w.y, w.g_fom))
     rng = np.random.RandomState(0)
     tol = 1e-12 if dtype == torch.float64 else 2e-6
     for m in (1, 7, 8, 13, 16, 25, 32, 40):
         V = torch.tensor(rng.normal(size=(w.d, m)), dtype=dtype, device=dev)
         s = torch.tensor(rng.normal(size=(21, m)), dtype=dtype, device=dev)
-        monkeypatch.setenv("GPDE_VO_PATH", "fused")
-        assert plan.kernel_path(m, dtype) == (1 if m <= 32 else 0)
-        r2, rho2 = plan.residual(a, y, gv, V, want_rho=True)
-        q2 = plan.residual_T(a, V, s)
+        assert plan_fused.kernel_path(m, dtype) == (1 if m <= 32 else 0)
+        r2, rho2 = plan_fused.residual(a, y, gv, V, want_rho=True)
+        q2 = plan_fused.residual_T(a, V, s)
         if m <= 32:
-            assert rel_err(plan.residual(a, y, gv, V).cpu(), r2.cpu()) == 0.0    # rho output does not change r
-        monkeypatch.setenv("GPDE_VO_PATH", "v1")
-        assert plan.launches_per_residual(m) == 3 and plan.kernel_path(m, dtype) == 0
-        r1, rho1 = plan.residual(a, y, gv, V, want_rho=True)
-        q1 = plan.residual_T(a, V, s)
-        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            assert rel_err(plan_fused.residual(a, y, gv, V).cpu(), r2.cpu()) == 0.0    # rho output does not change r
+        assert plan_v1.launches_per_residual(m) == 3 and plan_v1.kernel_path(m, dtype) == 0
+        r1, rho1 = plan_v1.residual(a, y, gv, V, want_rho=True)
+        q1 = plan_v1.residual_T(a, V, s)
         assert rel_err(r2.cpu(), r1.cpu()) < tol, m
         assert rel_err(rho2.cpu(), rho1.cpu()) < tol, m
         assert rel_err(q2.cpu(), q1.cpu()) < tol, m
@@ -300,13 +300,9 @@ def test_fused_path_matches_unfused_kernels(dtype, dev, monkeypatch):
     _, rho = plan.residual(a, y, gv, None)
     assert rel_err(rho.cpu(), rho1.cpu()) < tol
     # synchronous staging flavour of the fused kernel (what FP32 inputs and non-monotone rings use)
-    monkeypatch.setenv("GPDE_VO_PATH", "fused")
     V = torch.tensor(rng.normal(size=(w.d, 25)), dtype=dtype, device=dev)
-    monkeypatch.setenv("GPDE_VO_SYNC_STAGING", "1")
-    r3 = plan.residual(a, y, gv, V)
-    monkeypatch.delenv("GPDE_VO_SYNC_STAGING", raising=False)
-    assert torch.equal(r3, plan.residual(a, y, gv, V))
-    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+    r3 = plan_fused_sync.residual(a, y, gv, V)
+    assert torch.equal(r3, plan_fused.residual(a, y, gv, V))
 
 
 def _grid_case(nx, ny, ptype, B, seed, dev, load=False):
@@ -334,10 +330,10 @@ def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
     every column-tile variant, odd batch x odd d (y ends off a 16-byte boundary), shared field / Dirichlet
     data, conductivity (not log) input, load vector on / off."""
     plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 1000 + ny, dev, load=True)
+    plan_v1 = plan.variant(GPDE_VO_PATH="v1")
     T = lambda t: torch.tensor(t, device=dev)
     for m in (1, 8, 9, 16, 25, 32, 33, 70, 130):
         V = T(rng.normal(size=(fom.dim_out, m)))
-        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
         assert plan.kernel_path(m) == (2 if m <= 32 else 3) and plan.launches_per_residual(m) == (2 if m <= 32 else 3)
         variants = [
             dict(a=T(a), y=T(y), g=T(g)),
@@ -347,11 +343,8 @@ def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
         ]
         for kw in variants:
             aa, yy, gg = kw.pop('a'), kw.pop('y'), kw.pop('g')
-            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
             r_grid = plan.residual(aa, yy, gg, V, **kw)
-            monkeypatch.setenv("GPDE_VO_PATH", "v1")
-            r_v1 = plan.residual(aa, yy, gg, V, **kw)
-            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            r_v1 = plan_v1.residual(aa, yy, gg, V, **kw)
             assert rel_err(r_grid.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
     # transposed application q = K_ff (V s): tensor-core expansion + marching kernel against the generic kernels
     for m in (1, 25, 70):
@@ -359,11 +352,8 @@ def test_grid_kernel_matches_generic_kernels(nx, ny, B, dev, monkeypatch):
         sv = T(rng.normal(size=(B, m)))
         for kw in (dict(a=T(a)), dict(a=T(a[0])), dict(a=T(np.exp(a)), a_is_log=False)):
             aa = kw.pop('a')
-            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
             q_grid = plan.residual_T(aa, V, sv, **kw)
-            monkeypatch.setenv("GPDE_VO_PATH", "v1")
-            q_v1 = plan.residual_T(aa, V, sv, **kw)
-            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            q_v1 = plan_v1.residual_T(aa, V, sv, **kw)
             assert rel_err(q_grid.cpu(), q_v1.cpu()) < 1e-12, (m, sorted(kw))
     # unaligned views (odd storage offsets) are served by the generic kernels, same numbers
     V = T(rng.normal(size=(fom.dim_out, 25)))
@@ -381,6 +371,7 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
     CTA), y views starting off a 16-byte boundary (both phases), shared field / Dirichlet rows, no Dirichlet data,
     conductivity input, the rho variant behind residual_T and m > 32."""
     plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 77 + ny, dev, load=False)
+    plan_v1, plan_general = plan.variant(GPDE_VO_PATH="v1"), plan.variant(GPDE_GRID_V="1")
     T = lambda t: torch.tensor(t, device=dev)
     big = torch.zeros(B * fom.dim_out + 1, dtype=torch.float64, device=dev)
     y_odd = big[1:].view(B, fom.dim_out)
@@ -396,21 +387,15 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
         for kw in variants:
             aa, yy, gg = kw.pop('a'), kw.pop('y'), kw.pop('g')
             r_lean = plan.residual(aa, yy, gg, V, **kw)
-            monkeypatch.setenv("GPDE_GRID_V", "1")
-            r_gen = plan.residual(aa, yy.contiguous().clone(), gg, V, **kw)
-            monkeypatch.delenv("GPDE_GRID_V", raising=False)
-            monkeypatch.setenv("GPDE_VO_PATH", "v1")
-            r_v1 = plan.residual(aa, yy, gg, V, **kw)
-            monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+            r_gen = plan_general.residual(aa, yy.contiguous().clone(), gg, V, **kw)
+            r_v1 = plan_v1.residual(aa, yy, gg, V, **kw)
             assert rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12, (m, sorted(kw))
             assert rel_err(r_lean.cpu(), r_gen.cpu()) < 1e-12, (m, sorted(kw))
     for m in (1, 5, 8, 9, 16, 25, 28, 29, 32, 40):   # every k-step count of the expansion kernel (vo_expand.cuh), and m > 32
         V = T(rng.normal(size=(fom.dim_out, m)))
         sv = T(rng.normal(size=(B, m)))
         q_lean = plan.residual_T(T(a), V, sv)
-        monkeypatch.setenv("GPDE_VO_PATH", "v1")
-        q_v1 = plan.residual_T(T(a), V, sv)
-        monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+        q_v1 = plan_v1.residual_T(T(a), V, sv)
         assert rel_err(q_lean.cpu(), q_v1.cpu()) < 1e-12, m
     # extreme log-conductivities take the libm exp() branch: same numbers as the generic kernels
     a2 = a.copy()
@@ -418,9 +403,7 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
     a2[:, 3::11] = -750.0
     V = T(rng.normal(size=(fom.dim_out, 25)))
     r_lean = plan.residual(T(a2), T(y), T(g), V)
-    monkeypatch.setenv("GPDE_VO_PATH", "v1")
-    r_v1 = plan.residual(T(a2), T(y), T(g), V)
-    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+    r_v1 = plan_v1.residual(T(a2), T(y), T(g), V)
     assert torch.isfinite(r_v1).all() and rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12
 
 
@@ -468,12 +451,12 @@ def test_grid_kernel_against_oracle(dev):
 
 def test_unfused_kernels_against_reference_vectors(dev, monkeypatch):
     from gpde_b200.VirtualObservables import VoPlan
-    monkeypatch.setenv("GPDE_VO_PATH", "v1")
     g = load_golden("vo_4x4_32_ndp")
     ph, bce = _setup(g, dev)
-    plan = VoPlan(ph['fom'], dev)
+    plan_v1 = VoPlan(ph['fom'], dev, experiment=dict(GPDE_VO_PATH="v1"))
+    assert plan_v1.kernel_path(g['in_V'].shape[1]) == 0
     a, y, gv, V = (torch.tensor(g[k], device=dev) for k in ('in_X_DG', 'in_Y', 'in_g_fom', 'in_V'))
-    assert rel_err(plan.residual(a, y, gv, V).cpu(), g['out_residual']) < 1e-10
+    assert rel_err(plan_v1.residual(a, y, gv, V).cpu(), g['out_residual']) < 1e-10
 
 
 def test_full_size_properties_config3(dev, monkeypatch):
@@ -485,6 +468,7 @@ def test_full_size_properties_config3(dev, monkeypatch):
     fom = w.physics['fom']
     plan = VoPlan.cached(fom, dev, pixel_input=True)
     assert w.m == 256 and w.d == 16383 and plan.kernel_path(w.m) == 3 and plan.launches_per_residual(w.m) == 3
+    plan_v1 = plan.variant(GPDE_VO_PATH="v1")
     V = torch.tensor(w.V, device=dev)
     gv = torch.tensor(w.g_fom[0], device=dev)
     B = w.B
@@ -498,9 +482,7 @@ def test_full_size_properties_config3(dev, monkeypatch):
     y2 = torch.randn(B, w.d, generator=gen, dtype=torch.float64).to(dev)
     r1 = plan.residual(a, y1, gv, V)
     # against the generic kernels (matvec + the same contraction) on the same inputs
-    monkeypatch.setenv("GPDE_VO_PATH", "v1")
-    r1_v1, rho_v1 = plan.residual(a, y1, gv, V, want_rho=True)
-    monkeypatch.delenv("GPDE_VO_PATH", raising=False)
+    r1_v1, rho_v1 = plan_v1.residual(a, y1, gv, V, want_rho=True)
     assert rel_err(r1.cpu(), r1_v1.cpu()) < 1e-12
     assert rel_err((rho_v1 @ V).cpu(), r1.cpu()) < 1e-12       # torch / cuBLAS FP64 as a third opinion
     # linearity, ragged tail (B % 128 != 0 for the 128-row GEMM tiles), sample independence
