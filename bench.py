@@ -4,12 +4,17 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--dtype f64]
     python bench.py --impl reference ...          # the reference's CPU arithmetic (oracle port), host cores
 
-A "step" is one pass of the physics layer over one batch of synthetic log-normal fields:
-    coarse-grained model forward (logX, F -> u), its adjoint (gbar_u -> dL/dlogX),
-    and the virtual-observable residual r = V^T (K_fom(a) y~ - f) for the same samples.
-``value`` = samples/s with inputs resident in HBM (each sample = 1 CGM fwd+adjoint solve + 1 VO residual
-evaluation); per-unit rates are reported beside it.  ``e2e`` is the same pass through the public
-module API from pinned HOST buffers, copies included.  Prints ONE JSON line on rank 0.
+A "step" is one pass of the physics layer over one batch of synthetic log-normal fields (SURVEY.md section 8d):
+    unit 1  coarse-grained model forward (logX, F -> u) and its adjoint (gbar_u -> dL/dlogX); exp(.)+1e-8 inside,
+            as ReducedOrderModelOperator.forward does (components.py:298);
+    unit 2  virtual-observable residual r = V^T (K_fom(a) y~ - f) for the same samples, a = exp(x) the fine
+            conductivity field (the reference evaluates exp(x) once per data point when it assembles and caches K,
+            VirtualObservables.py:52-59, so the per-step input is the conductivity; the log-input timing is reported
+            beside it in ``components``).
+``value`` = samples/s with inputs resident in HBM (each sample = 1 CGM fwd+adjoint solve + 1 VO residual evaluation).
+``e2e`` is the same pass through the public module API from pinned HOST buffers, copies included (chunked, copies
+overlapped with compute).  ``configs`` holds the other BASELINE.json configurations measured in the same run (config 3,
+config 4 strong-scaled over the ranks, FP32 I/O).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -25,6 +30,7 @@ if ROOT not in sys.path:
 
 METRIC = "CGM fwd+adjoint solves/s & VO residual evals/s"
 UNIT = "samples/s (1 CGM fwd+adjoint solve + 1 VO residual eval per sample)"
+FP64_PEAK_TFLOPS = 37.0   # DMMA/DFMA rate measured on this pool (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry
 
 
 def parse():
@@ -38,57 +44,90 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the records of the other configurations (configs 3, 4, FP32)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-overlap", action="store_true", help="keep the ROM and VO kernels on one stream")
-    ap.add_argument("--no-split-pack", action="store_true",
-                    help="let the VO residual call pack V itself (no ordering of the ROM kernels behind the packing)")
+    ap.add_argument("--log-input", action="store_true", help="VO residual from the log-field (exp inside the kernel) in the step")
+    ap.add_argument("--e2e-chunks", type=int, default=4)
     return ap.parse_args()
+
+
+def workload_config(w):
+    """The ``config`` object: identical in both arms (the driver compares them)."""
+    return dict(w.describe(), vo_input="conductivity a = exp(x) (SURVEY 8d unit 2)", rom_input="log-conductivity (exp inside)",
+                l2="inputs larger than L2: %.0f MB streamed per step per GPU"
+                   % ((w.vo_bytes_per_eval(8) + w.cgm_bytes_per_solve(8)) * w.B / 1e6))
 
 
 # ------------------------------------------------------------------------------- CPU arm (oracle port)
 class CpuReference(object):
-    """The reference's own arithmetic on the host cores: bottleneck/ROM.py ops through autograd
-    (oracle/rom_ref.py) and the per-data-point VO route K -> Gamma = V^T K -> Gamma y - alpha
-    (oracle/vo_ref.py), all torch/MKL threads.  FEniCS assembly itself cannot be timed here (not
-    installable); its place is taken by a precomputed-pattern CSR assembly."""
+    """The reference's own arithmetic on the host cores (oracle port, ``kind: port``: FEniCS is not installable here):
+      CGM   bottleneck/ROM.py ops through torch autograd (oracle/rom_ref.py), all torch threads;
+      VO    (a) ``cached_gamma``: r_n = Gamma_n y_n - alpha_n in a Python loop over data points with Gamma_n = V^T K_n and
+                alpha_n cached, exactly what LinearQuerry / VirtualObservable.update do every step for a constant sampler
+                (VirtualObservables.py:61-69 once, :662 per step) -- the HEADLINE variant;
+            (b) ``assemble``: K_n re-assembled and Gamma_n re-formed per data point per step (what a resample() of a
+                non-constant sampler costs; FEniCS' assemble replaced by a precomputed-pattern CSR assembly);
+            (c) ``vectorised``: (K_n y_n - f_n) V with the cached CSR K_n (SURVEY 8d's fair variant).
+    Works on the first ``n`` samples of the workload."""
 
-    def __init__(self, w, sample):
+    def __init__(self, w, n):
         import numpy as np
         import torch
         from oracle import rom_ref, vo_ref
         self.np, self.torch, self.rom_ref, self.vo_ref = np, torch, rom_ref, vo_ref
         self.cores = os.cpu_count() or 1
         torch.set_num_threads(self.cores)
-        self.w, self.sample = w, int(min(sample, w.B))
+        self.w, self.n = w, int(min(n, w.B))
         rom, fom = w.physics["rom"], w.physics["fom"]
         self.M = torch.tensor(rom.mesh.dense_element_tensor())
         self.bc = torch.tensor(rom.constrained_dofs)
         self.asm = vo_ref.CsrAssembler(fom.mesh.coords, fom.mesh.cells, fom.constrained_dofs, fom.free_dofs,
                                        Ke=fom.mesh.element_stiffness())
         self.pix = fom.mesh.pixel_of_cell()
+        # setup (not timed): K_n, f_n, Gamma_n, alpha_n of the sampled data points, cached as the reference caches them
+        self.K, self.f, self.Gamma, self.alpha = [], [], [], []
+        for b in range(self.n):
+            K, f = self.asm.assemble(np.exp(w.log_image[b][self.pix]), w.g_fom[b])
+            G, al = vo_ref.construct_querry_weak_galerkin(K, f, w.V)
+            self.K.append(K); self.f.append(f); self.Gamma.append(np.ascontiguousarray(G)); self.alpha.append(al)
+        self.tX, self.tF, self.tg = (torch.tensor(t[:self.n]) for t in (w.logX, w.F, w.gbar_u))
 
-    def cgm(self, n):
-        t = self.torch
-        w = self.w
+    def cgm(self):
         t0 = time.perf_counter()
-        self.rom_ref.rom_fwd_adjoint(self.M, self.bc, t.tensor(w.logX[:n]), t.tensor(w.F[:n]), t.tensor(w.gbar_u[:n]))
+        self.rom_ref.rom_fwd_adjoint(self.M, self.bc, self.tX, self.tF, self.tg)
         return time.perf_counter() - t0
 
-    def vo(self, n):
+    def vo_cached_gamma(self):
+        w = self.w
+        t0 = time.perf_counter()
+        for b in range(self.n):   # Python loop over data points, as VirtualObservables.py:895 / :985
+            _ = self.Gamma[b] @ w.y[b] - self.alpha[b]
+        return time.perf_counter() - t0
+
+    def vo_assemble(self, n):
         np_, w = self.np, self.w
         t0 = time.perf_counter()
-        for b in range(n):   # Python loop over data points, as VirtualObservables.py:895 / :985
+        for b in range(n):
             K, f = self.asm.assemble(np_.exp(w.log_image[b][self.pix]), w.g_fom[b])
             Gamma, alpha = self.vo_ref.construct_querry_weak_galerkin(K, f, w.V)
             _ = Gamma @ w.y[b] - alpha
-        return time.perf_counter() - t0
+        return (time.perf_counter() - t0) / n
+
+    def vo_vectorised(self):
+        w = self.w
+        t0 = time.perf_counter()
+        for b in range(self.n):
+            _ = (self.K[b] @ w.y[b] - self.f[b]) @ w.V
+        return (time.perf_counter() - t0) / self.n
 
     def step(self):
-        """One bounded sample: CGM fwd+adjoint on the whole batch, VO on ``sample`` data points."""
-        t_cgm = self.cgm(self.w.B)
-        t_vo = self.vo(self.sample)
-        per_sample = t_cgm / self.w.B + t_vo / self.sample
-        return per_sample, t_cgm / self.w.B, t_vo / self.sample
+        """One step of the arm = the n sampled samples through both units (cached-Gamma VO): seconds."""
+        return self.cgm() + self.vo_cached_gamma()
+
+
+def reference_sample_size(w):
+    return 512 if w.d <= 4095 else 64       # Gamma cache: n * m * d doubles (430 MB at config 2, 2.1 GB / 64 at config 3)
 
 
 def run_reference(args):
@@ -98,31 +137,34 @@ def run_reference(args):
     import gpde_b200  # noqa: F401
     from gpde_b200.workloads import Workload
     from gpde_b200.workloads import CONFIGS
-    # bounded sample: the CPU arm never builds more than 4096 samples of the workload (cfg4 has 131072)
-    w = Workload(args.workload, B=min(int(args.batch or CONFIGS[args.workload]["B"]), 4096), seed=0)
-    sample = 64 if w.d <= 4095 else 8
-    ref = CpuReference(w, sample)
-    for _ in range(min(args.warmup, 2)):
+    full = Workload(args.workload, B=int(args.batch or min(CONFIGS[args.workload]["B"], 4096)), seed=0)
+    n = reference_sample_size(full)
+    ref = CpuReference(full, n)
+    for _ in range(max(3, args.warmup)):      # the first calls pay torch's thread-pool start-up (2 s, 0.6 s, 0.04 s measured)
         ref.step()
-    acc, acc_c, acc_v = 0.0, 0.0, 0.0
+    steps, acc, acc_c, acc_v = 0, 0.0, 0.0, 0.0
     t0 = time.perf_counter()
-    steps = 0
     for _ in range(max(1, args.steps)):
-        p, c, v = ref.step()
-        acc += p; acc_c += c; acc_v += v
+        c, v = ref.cgm(), ref.vo_cached_gamma()
+        acc += c + v; acc_c += c; acc_v += v
         steps += 1
         if time.perf_counter() - t0 > 120.0:
             break
-    per = acc / steps
-    value = 1.0 / per
-    sample_desc = "per step: CGM fwd+adjoint on %d samples (torch, %d threads) + VO route on %d data points" % (
-        w.B, ref.cores, sample)
+    value = steps * ref.n / acc
+    t_asm = ref.vo_assemble(min(ref.n, 32))
+    t_vec = ref.vo_vectorised()
+    sample_desc = ("each step = the first %d samples of the workload batch (%d): CGM fwd+adjoint (torch autograd, %d threads) + "
+                   "VO r = Gamma y - alpha per data point with cached Gamma" % (ref.n, full.B, ref.cores))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * per * w.B, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * acc / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": dict(w.describe(), parallelism="host cores only"),
-        "components": {"cgm_solves_per_s": steps / acc_c, "vo_evals_per_s": steps / acc_v},
+        "config": workload_config(full),
+        "samples_per_step": ref.n,
+        "extrapolated_from": "none: value = samples_per_step / (ms_per_step / 1000); the step is a bounded sample (%d of %d samples)"
+                             % (ref.n, full.B),
+        "components": {"cgm_solves_per_s": steps * ref.n / acc_c, "vo_evals_per_s": steps * ref.n / acc_v,
+                       "vo_evals_per_s_assemble_each_step": 1.0 / t_asm, "vo_evals_per_s_vectorised_cached_K": 1.0 / t_vec},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -197,14 +239,212 @@ def recorded_traffic(workload, dtype):
         return None
 
 
+def bind_near_gpu(index):
+    """Pins this process (and the pinned host buffers it allocates next: first touch) to the CPU cores nvidia-smi reports as
+    local to GPU ``index`` -- with 8 ranks each streaming 270 MB per step from host memory, buffers on the far socket halve
+    the per-GPU copy rate.  Returns the affinity string or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             timeout=20).stdout
+        header = None
+        for ln in out.splitlines():
+            cells = [c.strip() for c in ln.split("\t")]
+            if header is None and any("CPU Affinity" in c for c in cells):
+                header = [c for c in cells if c]
+                continue
+            if header and cells and cells[0].replace("\x1b[4m", "").replace("\x1b[0m", "").strip() == "GPU%d" % index:
+                vals = [c for c in cells if c]
+                aff = vals[1 + [h for h in header].index("CPU Affinity")] if "CPU Affinity" in header else None
+                cores = set()
+                for part in (aff or "").split(","):
+                    if "-" in part:
+                        lo, hi = part.split("-")
+                        cores.update(range(int(lo), int(hi) + 1))
+                    elif part.strip().isdigit():
+                        cores.add(int(part))
+                cores &= set(os.sched_getaffinity(0))
+                if cores:
+                    os.sched_setaffinity(0, cores)
+                    return aff
+    except Exception:
+        pass
+    return None
+
+
+class HotPath(object):
+    """Plans, resident inputs and the launch sequence of one workload on one device."""
+
+    def __init__(self, torch, dev, w, tdt, host_inputs, log_input=False):
+        from gpde_b200 import ROM as rom_mod
+        from gpde_b200.components import ReducedOrderModelOperator
+        from gpde_b200.VirtualObservables import VoPlan
+        self.torch, self.dev, self.w, self.tdt, self.rom_mod, self.log_input = torch, dev, w, tdt, rom_mod, log_input
+        self.op = ReducedOrderModelOperator.FromPhysics(w.physics, dtype=tdt, device=dev)
+        self.rom = self.op.rom
+        self.rom.deferred_checks = True
+        self.plan = self.rom._get_plan()
+        self.vplan = VoPlan.cached(w.physics["fom"], dev, pixel_input=True)
+        self.d = host_inputs
+        self.B = int(self.d["logX"].shape[0])
+        self.path = self.vplan.kernel_path(w.m, tdt)
+        self.vo_stream = torch.cuda.Stream(device=dev)
+        self.packed, self.ev_packed = None, torch.cuda.Event()
+        self.split_pack = self.path == 2 and tdt == torch.float64
+
+    def vo(self, log_input=None):
+        d = self.d
+        log_input = self.log_input if log_input is None else log_input
+        return self.vplan.residual(d["a_log"] if log_input else d["a"], d["y"], d["g"], d["V"], a_is_log=log_input)
+
+    def rom_forward(self):
+        d = self.d
+        return self.rom_mod._launch_forward(self.plan, d["logX"], d["F"], True, want_factor=True, info=self.rom._info_word(self.dev))
+
+    def rom_adjoint(self, u, factor):
+        return self.rom_mod._launch_adjoint(self.plan, self.d["logX"], u, factor, self.d["gbar"], True, want_gradF=False)
+
+    def step(self, overlap=False):
+        """One pass of the physics layer.  The coarse-grained model (forward -> adjoint) and the VO residual are independent:
+        with ``overlap`` the VO kernels go to a second stream (fork / join by events), so the small ROM kernels fill the SMs
+        the VO grid leaves idle."""
+        torch, d = self.torch, self.d
+        cur = torch.cuda.current_stream(self.dev)
+        if overlap:
+            self.vo_stream.wait_stream(cur)
+            with torch.cuda.stream(self.vo_stream):
+                if self.split_pack:
+                    # V packed by its own call; the ROM kernels are held back until the packing has run, so that the VO
+                    # kernel's CTAs (one whole SM each) are placed first and the ROM CTAs take the SMs left
+                    pw = self.vplan.pack_weights(d["V"], self.B, out=self.packed)
+                    if self.packed is None and hasattr(pw, "buf"):
+                        self.packed = pw
+                    self.ev_packed.record(self.vo_stream)
+                    r = self.vplan.residual(d["a_log"] if self.log_input else d["a"], d["y"], d["g"], pw, a_is_log=self.log_input)
+                else:
+                    r = self.vo()
+            if self.split_pack:
+                cur.wait_event(self.ev_packed)
+        u, factor = self.rom_forward()
+        gX, _ = self.rom_adjoint(u, factor)
+        if overlap:
+            cur.wait_stream(self.vo_stream)
+        else:
+            r = self.vo()
+        return u, gX, r
+
+    def launches_per_step(self):
+        return 1 + 1 + self.vplan.launches_per_residual(self.w.m, self.tdt)
+
+
+def graph_timed(torch, fn, K):
+    """Average device milliseconds of ``fn`` over K replays of its CUDA graph (eager launches if capture is refused)."""
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            keep = fn()
+        gr.replay()
+        torch.cuda.synchronize()
+        run, mode = gr.replay, "cuda_graph"
+    except Exception as exc:   # noqa: BLE001
+        sys.stderr.write("bench: CUDA graph capture failed (%s); timing eager launches\n" % (exc,))
+        keep, run, mode = None, fn, "eager"
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for _ in range(K):
+        run()
+    a1.record()
+    torch.cuda.synchronize()
+    return a0.elapsed_time(a1) / K, keep, run, mode
+
+
+def device_inputs(torch, dev, w, B, tdt, seed):
+    """Device-generated stand-ins of the workload's inputs for the secondary records (same shapes and value ranges as the
+    workload generator's fields, without the spatial correlation: generating 131072 correlated 64 x 64 fields on the host
+    would take longer than the whole bench; kernel time does not depend on the values)."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=gen, device=dev, dtype=torch.float64)
+    a_log = (0.4 + 0.8 * rn(B, w.P)).to(tdt)
+    d = dict(a_log=a_log, a=torch.exp(a_log.double()).to(tdt), logX=(0.4 + 0.5 * rn(B, w.E)).to(tdt),
+             F=torch.tensor(w.F[0], device=dev, dtype=tdt).expand(B, -1).contiguous(), gbar=rn(B, w.n).to(tdt),
+             y=(torch.tensor(w.y[0], device=dev).expand(B, -1) + 0.01 * rn(B, w.d)).to(tdt),
+             g=torch.tensor(w.g_fom[0], device=dev, dtype=tdt), V=torch.tensor(w.V, device=dev, dtype=tdt))
+    return d
+
+
+def roofline_record(w, B, s, t_vo, path, workload, dtype, peak, peak_src):
+    vo_bytes = w.vo_bytes_per_eval(s) * B
+    achieved = vo_bytes / (t_vo * 1e-3) / 1e9
+    # FP64 work of one VO evaluation (DESIGN.md section 4): fluxes 10 + contraction m per free node (FMA = 2 flop)
+    vo_flops = 2.0 * w.d * (10 + w.m) * B
+    if path in (0, 3) and w.m > 32:
+        return {"kernel": "vo_grid2_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
+                "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": vo_flops / (t_vo * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "traffic": recorded_traffic(workload, dtype),
+                "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
+                "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
+    return {"kernel": {2: "vo_grid2_kernel", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
+            "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": recorded_traffic(workload, dtype), "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes,
+            "fp64_pipe_frac": vo_flops / (t_vo * 1e-3) / 1e12 / FP64_PEAK_TFLOPS}
+
+
+def sub_record(torch, dist, dev, name, B_total, tdt, K, rank, world, peak, peak_src, strong):
+    """One secondary record: ROM forward + adjoint + VO residual on device-generated inputs, graph-replayed, max over ranks."""
+    from gpde_b200.sharding import shard_range
+    from gpde_b200.workloads import Workload
+    lo, hi = shard_range(B_total, rank, world) if strong else (0, B_total)
+    B = hi - lo
+    w = Workload(name, B=8, seed=0)
+    hp = HotPath(torch, dev, w, tdt, device_inputs(torch, dev, w, B, tdt, 100 + rank))
+    for _ in range(2):
+        hp.step()
+    torch.cuda.synchronize()
+    t_fwd, keep, _, _ = graph_timed(torch, hp.rom_forward, K)
+    t_adj, _, _, _ = graph_timed(torch, lambda: hp.rom_adjoint(*keep), K)
+    t_vo, _, _, _ = graph_timed(torch, hp.vo, K)
+    t_vo_log, _, _, _ = graph_timed(torch, lambda: hp.vo(True), K)
+    _, _, run, mode = graph_timed(torch, lambda: hp.step(overlap=True), 2)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / K
+    hp.rom.check()
+    if world > 1:
+        tt = torch.tensor([ms, t_fwd, t_adj, t_vo, t_vo_log], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, t_fwd, t_adj, t_vo, t_vo_log = (float(x) for x in tt.tolist())
+    s = 8 if tdt == torch.float64 else 4
+    total = B_total if strong else world * B
+    rec = {"workload": name, "desc": w.cfg["desc"], "dtype": "f64" if s == 8 else "f32", "scaling": "strong" if strong else "weak",
+           "global_batch": total, "per_gpu_batch": B, "value": total / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": K,
+           "launch_mode": mode, "data": "synthetic, device-generated (uncorrelated N(0.4, 0.8^2) log-fields of the workload's shapes)",
+           "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo, "ms_vo_residual_log_input": t_vo_log,
+           "cgm_solves_per_s": total / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": total / (t_vo * 1e-3),
+           "cgm_hbm_frac": w.cgm_bytes_per_solve(s) * B / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
+           "vo_kernel_path": hp.path,
+           "roofline": roofline_record(w, B, s, t_vo, hp.path, name, "f64" if s == 8 else "f32", peak, peak_src)}
+    del hp
+    torch.cuda.empty_cache()
+    return rec
+
+
 def run_b200(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
     import gpde_b200  # noqa: F401
-    from gpde_b200 import ROM as rom_mod
-    from gpde_b200.components import ReducedOrderModelOperator
-    from gpde_b200.VirtualObservables import VoPlan
     from gpde_b200.workloads import Workload
 
     rank = int(os.environ.get("RANK", "0"))
@@ -212,12 +452,14 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    affinity = bind_near_gpu(local)      # before the pinned buffers are allocated
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
     s = 8 if args.dtype == "f64" else 4
+    peak, peak_src = measured_peaks()
 
     # per-GPU shard of the sample-sharded batch.  Default: weak scaling, every rank owns a full workload batch.
     # cfg4 (BASELINE config 4): ONE batch of 131072 cut into contiguous shards (gpde_b200.sharding), strong scaling.
@@ -231,57 +473,20 @@ def run_b200(args):
     else:
         w = Workload(args.workload, B=args.batch, seed=rank)
     B = w.B
-    op = ReducedOrderModelOperator.FromPhysics(w.physics, dtype=tdt, device=dev)
-    rom = op.rom
-    rom.deferred_checks = True
-    plan = rom._get_plan()
-    vplan = VoPlan.cached(w.physics["fom"], dev, pixel_input=True)
 
-    host = dict(logX=w.logX, F=w.F, gbar=w.gbar_u, a=w.log_image, y=w.y,
+    host = dict(logX=w.logX, F=w.F, gbar=w.gbar_u, a_log=w.log_image, y=w.y,
                 g=(w.g_fom[0] if w.ptype == "ND" else w.g_fom), V=w.V)
     pinned = {k: torch.tensor(v, dtype=tdt).pin_memory() for k, v in host.items()}
+    pinned["a"] = torch.exp(torch.tensor(w.log_image)).to(tdt).pin_memory()     # conductivities, computed once at setup
     d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
     torch.cuda.synchronize()
-
-    vo_stream = torch.cuda.Stream(device=dev)
-    split_pack = not args.no_split_pack and vplan.kernel_path(w.m, tdt) == 2 and tdt == torch.float64
-    packed, ev_packed = [None], torch.cuda.Event()
-
-    def step_resident(overlap=False):
-        """One pass of the physics layer.  The coarse-grained model (forward -> adjoint) and the VO residual are
-        independent: with ``overlap`` the VO kernels go to a second stream (fork / join by events), so the small
-        ROM kernels fill the SMs the VO grid leaves idle (128 CTAs on 148 SMs at this batch)."""
-        cur = torch.cuda.current_stream(dev)
-        if overlap:
-            vo_stream.wait_stream(cur)
-            with torch.cuda.stream(vo_stream):
-                if split_pack:
-                    # V packed by its own call; the ROM kernels are held back until the packing has run, so that
-                    # the VO kernel's CTAs (one whole SM each) are placed first and the ROM CTAs take the SMs left
-                    pw = vplan.pack_weights(d["V"], B, out=packed[0])
-                    if packed[0] is None and hasattr(pw, "buf"):
-                        packed[0] = pw
-                    ev_packed.record(vo_stream)
-                    r = vplan.residual(d["a"], d["y"], d["g"], pw)
-                else:
-                    r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
-            if split_pack:
-                cur.wait_event(ev_packed)
-        u, factor = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
-        gX, _ = rom_mod._launch_adjoint(plan, d["logX"], u, factor, d["gbar"], True, want_gradF=False)
-        if overlap:
-            cur.wait_stream(vo_stream)
-        else:
-            r = vplan.residual(d["a"], d["y"], d["g"], d["V"])
-        return u, gX, r
-
-    launches_per_step = 1 + 1 + vplan.launches_per_residual(w.m, tdt)    # rom_forward, rom_adjoint, vo residual
+    hp = HotPath(torch, dev, w, tdt, d, log_input=args.log_input)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        step_resident()
+        hp.step()
     torch.cuda.synchronize()
     K = args.steps
 
@@ -290,70 +495,27 @@ def run_b200(args):
     t_host0 = time.perf_counter()
     e_start.record()
     for k in range(K):
-        step_resident()
+        hp.step()
     e_end.record()
     t_host1 = time.perf_counter()
     torch.cuda.synchronize()
-    rom.check()
+    hp.rom.check()
     eager_ms = e_start.elapsed_time(e_end) / K
     host_enqueue_ms = (t_host1 - t_host0) * 1e3 / K
 
-    # ---- (1b) per-kernel-group device times, free of host launch gaps: each group (ROM forward, ROM adjoint,
-    # VO residual) is captured in its own CUDA graph and replayed K times between two events on its stream
-    def timed_group(fn):
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                fn()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            gr = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(gr):
-                keep = fn()
-            gr.replay()
-            torch.cuda.synchronize()
-            run = gr.replay
-        except Exception:   # noqa: BLE001
-            keep, run = None, fn
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(K):
-            run()
-        a1.record()
-        torch.cuda.synchronize()
-        return a0.elapsed_time(a1) / K, keep
+    # ---- (1b) per-kernel-group device times, free of host launch gaps (each group in its own CUDA graph)
+    t_fwd, keep, _, _ = graph_timed(torch, hp.rom_forward, K)
+    t_adj, _, _, _ = graph_timed(torch, lambda: hp.rom_adjoint(*keep), K)
+    t_vo, _, _, _ = graph_timed(torch, hp.vo, K)
+    t_vo_other, _, _, _ = graph_timed(torch, lambda: hp.vo(not hp.log_input), K)
+    hp.rom.check()
 
-    u_ref, f_ref = rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True, info=rom._info_word(dev))
-    t_fwd, _k1 = timed_group(lambda: rom_mod._launch_forward(plan, d["logX"], d["F"], True, want_factor=True,
-                                                             info=rom._info_word(dev)))
-    t_adj, _k2 = timed_group(lambda: rom_mod._launch_adjoint(plan, d["logX"], u_ref, f_ref, d["gbar"], True,
-                                                             want_gradF=False))
-    t_vo, _k3 = timed_group(lambda: vplan.residual(d["a"], d["y"], d["g"], d["V"]))
-    rom.check()
-
-    # ---- (2) the timed region: K steps, each step = the same launches replayed from one CUDA graph (the
-    # step is launch-bound from Python at this batch); falls back to eager launches if capture is refused
-    graph, mode = None, "eager"
-    if not args.no_graph:
-        try:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    step_resident(overlap=not args.no_overlap)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                g_out = step_resident(overlap=not args.no_overlap)
-            for _ in range(3):
-                graph.replay()
-            torch.cuda.synchronize()
-            mode = "cuda_graph"
-        except Exception as exc:   # noqa: BLE001 -- report, keep measuring eagerly
-            sys.stderr.write("bench: CUDA graph capture failed (%s); timing eager launches\n" % (exc,))
-            graph = None
+    # ---- (2) the timed region: K steps, each step = the same launches replayed from one CUDA graph (the step is
+    # launch-bound from Python at this batch); eager launches if capture is refused or --no-graph
+    if args.no_graph:
+        run, mode = (lambda: hp.step(overlap=not args.no_overlap)), "eager"
+    else:
+        _, _, run, mode = graph_timed(torch, lambda: hp.step(overlap=not args.no_overlap), 3)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -361,14 +523,11 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     start.record()
     for k in range(K):
-        if graph is not None:
-            graph.replay()
-        else:
-            step_resident(overlap=not args.no_overlap)
+        run()
     end.record()
     torch.cuda.synchronize()
     t_wall1 = time.perf_counter()
-    rom.check()
+    hp.rom.check()
     elapsed_ms = start.elapsed_time(end)
     if world > 1:
         tt = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
@@ -376,24 +535,49 @@ def run_b200(args):
         elapsed_ms = float(tt.item())
     ms_per_step = elapsed_ms / K
 
-    # ---- end to end through the public module API from pinned host buffers ----
+    # ---- end to end through the public module API from pinned host buffers: the batch is cut into chunks; the copies of
+    # chunk c+1 (copy stream) overlap the kernels of chunk c (compute stream) and the read-back of chunk c-1
     e2e = None
     if not args.no_e2e:
+        from gpde_b200.VirtualObservables import VoPlan  # noqa: F401
+        a_key = "a_log" if hp.log_input else "a"
         outs = dict(u=torch.empty((B, w.n), dtype=tdt).pin_memory(), gX=torch.empty((B, w.E), dtype=tdt).pin_memory(),
                     r=torch.empty((B, w.m), dtype=tdt).pin_memory())
-        names_in = ("logX", "F", "gbar", "a", "y", "g")
+        names_in = ["logX", "F", "gbar", a_key, "y"] + (["g"] if pinned["g"].dim() == 2 else [])
         bytes_in = sum(pinned[k].numel() * pinned[k].element_size() for k in names_in)
         bytes_out = sum(t.numel() * t.element_size() for t in outs.values())
+        nch = max(1, min(args.e2e_chunks, B // 256))
+        bounds = [(c * B // nch, (c + 1) * B // nch) for c in range(nch)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        out_stream = torch.cuda.Stream(device=dev)
+        g_shared = d["g"] if pinned["g"].dim() == 1 else None
 
         def step_e2e():
-            dd = {k: pinned[k].to(dev, non_blocking=True) for k in names_in}
-            lX = dd["logX"].requires_grad_(True)
-            uu = rom.solve_log(lX, dd["F"])            # public API: autograd.Function forward
-            uu.backward(dd["gbar"])                      # ... and its adjoint
-            rr = vplan.residual(dd["a"], dd["y"], dd["g"], d["V"])
-            outs["u"].copy_(uu.detach(), non_blocking=True)
-            outs["gX"].copy_(lX.grad, non_blocking=True)
-            outs["r"].copy_(rr, non_blocking=True)
+            cur = torch.cuda.current_stream(dev)
+            copy_stream.wait_stream(cur)
+            staged = []
+            for (lo, hi) in bounds:                      # all H2D copies are enqueued first, on the copy stream
+                with torch.cuda.stream(copy_stream):
+                    dd = {k: pinned[k][lo:hi].to(dev, non_blocking=True) for k in names_in}
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                staged.append((dd, ev))
+            for (lo, hi), (dd, ev) in zip(bounds, staged):
+                cur.wait_event(ev)
+                for t in dd.values():
+                    t.record_stream(cur)
+                lX = dd["logX"].requires_grad_(True)
+                uu = hp.rom.solve_log(lX, dd["F"])            # public API: autograd.Function forward
+                uu.backward(dd["gbar"])                        # ... and its adjoint
+                rr = hp.vplan.residual(dd[a_key], dd["y"], dd["g"] if g_shared is None else g_shared, d["V"], a_is_log=hp.log_input)
+                out_stream.wait_stream(cur)
+                with torch.cuda.stream(out_stream):
+                    for t in (uu, lX.grad, rr):
+                        t.record_stream(out_stream)
+                    outs["u"][lo:hi].copy_(uu.detach(), non_blocking=True)
+                    outs["gX"][lo:hi].copy_(lX.grad, non_blocking=True)
+                    outs["r"][lo:hi].copy_(rr, non_blocking=True)
+            cur.wait_stream(out_stream)
 
         Ke = max(3, min(K, 10))
         for _ in range(2):
@@ -413,7 +597,20 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e_ms = float(tt.item())
         e2e = {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_in),
-               "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e_ms, "steps": Ke}
+               "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e_ms, "steps": Ke, "chunks": nch,
+               "h2d_gbs_per_gpu": bytes_in / (e_ms * 1e-3) / 1e9, "cpu_affinity": affinity,
+               "bound": "host-to-device copy (PCIe): compute is %.1f %% of the step" % (100.0 * ms_per_step / e_ms)}
+
+    # ---- the other BASELINE configurations, same run (rank 0 prints them under "configs")
+    subs = {}
+    if not args.no_sub and args.workload == "cfg2" and args.batch is None:
+        Ks = max(3, min(K, 10))
+        try:
+            subs["cfg4_strong_b131072"] = sub_record(torch, dist, dev, "cfg4", 131072, torch.float64, Ks, rank, world, peak, peak_src, True)
+            subs["cfg3_b16384"] = sub_record(torch, dist, dev, "cfg3", 16384, torch.float64, max(3, Ks // 2), rank, world, peak, peak_src, False)
+            subs["cfg2_f32"] = sub_record(torch, dist, dev, "cfg2", 4096, torch.float32, Ks, rank, world, peak, peak_src, False)
+        except Exception as exc:   # noqa: BLE001 -- the headline record must survive a failing secondary record
+            subs["error"] = "%s: %s" % (type(exc).__name__, exc)
     if sampler:
         sampler.stop()
 
@@ -422,54 +619,45 @@ def run_b200(args):
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peaks()
-    vo_bytes = w.vo_bytes_per_eval(s) * B
-    achieved = vo_bytes / (t_vo * 1e-3) / 1e9
     cgm_bytes = w.cgm_bytes_per_solve(s) * B
-    path = vplan.kernel_path(w.m, tdt)
-    # FP64 work of one VO evaluation: exp 11 x 1.25, fluxes 10, contraction m (FMA = 2 flop)
-    vo_flops = 2.0 * w.d * (11 * 1.25 + 10 + w.m) * B
-    fp64_peak = 37.0   # TFLOP/s, DMMA/DFMA rate measured on this pool: profiles/r1_fp64_peak.txt
+    other = "ms_vo_residual_conductivity_input" if hp.log_input else "ms_vo_residual_log_input"
     line = {
         "metric": METRIC, "value": (total if strong else world * B) / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
         "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": dict(w.describe(), per_gpu_batch=B, global_batch=(total if strong else world * B),
-                       parallelism="sample-sharded x%d, no data-path collective" % world,
-                       l2="inputs larger than L2: %.0f MB streamed per step per GPU" % ((vo_bytes + cgm_bytes) / 1e6)),
+        "config": workload_config(w),
+        "run": {"per_gpu_batch": B, "global_batch": (total if strong else world * B),
+                "parallelism": "sample-sharded x%d, no data-path collective" % world,
+                "vo_input_in_step": "log-field (exp inside the kernel)" if hp.log_input else "conductivity"},
         "components": {
             "cgm_solves_per_s": world * B / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": world * B / (t_vo * 1e-3),
-            "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo,
-            "launch_mode": mode + ("" if args.no_overlap else " + ROM/VO on two streams"), "ms_per_step_eager": eager_ms, "ms_host_enqueue_per_step": host_enqueue_ms,
+            "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo, other: t_vo_other,
+            "launch_mode": mode + ("" if args.no_overlap else " + ROM/VO on two streams"), "ms_per_step_eager": eager_ms,
+            "ms_host_enqueue_per_step": host_enqueue_ms,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
+            "vo_hbm_frac_log_input": w.vo_bytes_per_eval(s) * B / ((t_vo if hp.log_input else t_vo_other) * 1e-3) / 1e9 / peak,
         },
-        "roofline": ({"kernel": "vo_grid2_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
-                      "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                      "frac": vo_flops / (t_vo * 1e-3) / 1e12 / fp64_peak, "traffic": recorded_traffic(args.workload, args.dtype),
-                      "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
-                      "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
-                     if path in (0, 3) and w.m > 32 else
-                     {"kernel": {2: "vo_grid2_kernel (+ vo_grid2_pack_kernel)", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
-                      "bound": "hbm", "achieved": achieved, "peak": peak,
-                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(args.workload, args.dtype),
-                      "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes,
-                      "fp64_pipe_frac": vo_flops / (t_vo * 1e-3) / 1e12 / fp64_peak}),
-        "gpu_launches": launches_per_step * K,
+        "roofline": roofline_record(w, B, s, t_vo, hp.path, args.workload, args.dtype, peak, peak_src),
+        "gpu_launches": hp.launches_per_step() * K,
         "clocks": sampler.summary(t_wall0, t_wall1) if sampler else None,
         "e2e": e2e,
+        "configs": subs,
     }
     if world == 1 and not args.no_cpu_baseline:
-        ref = CpuReference(w, 32 if w.d <= 4095 else 4)
-        ref.step()
+        ref = CpuReference(w, reference_sample_size(w))
+        for _ in range(3):
+            ref.step()
         t0, n, acc = time.perf_counter(), 0, 0.0
-        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 20):
-            acc += ref.step()[0]
+        while n < 3 or (time.perf_counter() - t0 < 10.0 and n < 50):
+            acc += ref.step()
             n += 1
         line["cpu_baseline"] = {
-            "value": n / acc, "unit": UNIT, "cores": ref.cores, "kind": "port",
-            "sample": "%d x (CGM fwd+adjoint on %d samples via torch autograd + VO per-data-point route on %d samples)"
-                      % (n, B, ref.sample)}
+            "value": n * ref.n / acc, "unit": UNIT, "cores": ref.cores, "kind": "port",
+            "sample": "%d x (CGM fwd+adjoint via torch autograd + VO r = Gamma y - alpha with cached Gamma, Python loop over data "
+                      "points) on the first %d samples of the batch" % (n, ref.n),
+            "vo_evals_per_s_assemble_each_step": 1.0 / ref.vo_assemble(min(ref.n, 32)),
+            "vo_evals_per_s_vectorised_cached_K": 1.0 / ref.vo_vectorised()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

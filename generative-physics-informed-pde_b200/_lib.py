@@ -39,6 +39,10 @@ SIGNATURES = {
     "gpde_prolong_apply_T_f64": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gpde_prolong_apply_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     "gpde_prolong_apply_T_f32": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpde_prolong_loglik_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpde_prolong_loglik_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "gpde_prolong_moments_f64": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
+    "gpde_prolong_moments_f32": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp]),
     "gpde_vo_plan_create": (c_i32, [PP, c_i32, c_i32, c_vp, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_i32,
                                     c_vp, c_i32]),
     "gpde_vo_plan_destroy": (c_i32, [c_vp]),

@@ -45,6 +45,67 @@ class _ProlongPlan(object):
         return out
 
 
+    def loglik(self, u, Y, logsigmas, want_grads=True):
+        """(L [B] float64, gu [B,n], gls [d] float64) of the fused epilogue (gpde_prolong_loglik_*): the diagonal-Gaussian
+        log-likelihood of Y under N(W u, exp(2 logsigmas)) per sample and its gradients, mu_y = W u never materialised."""
+        sfx = _lib.suffix(u.dtype)
+        dev, B = self.device, u.shape[0]
+        u, Y, ls = u.contiguous(), Y.to(u.dtype).contiguous(), logsigmas.detach().to(u.dtype).contiguous()
+        L = torch.empty(B, dtype=torch.float64, device=dev)
+        gu = torch.empty_like(u) if want_grads else None
+        gls = torch.empty(self.d, dtype=torch.float64, device=dev) if want_grads else None
+        fn = getattr(self._lib, "gpde_prolong_loglik_" + sfx)
+        _lib.check(fn(self.handle, _lib.ptr(u, dev), _lib.ptr(Y, dev), _lib.ptr(ls, dev), _lib.ptr(L, dev), _lib.ptr(gu, dev),
+                      _lib.ptr(gls, dev), B, _lib.stream_of(dev)), "gpde_prolong_loglik")
+        return L, gu, gls
+
+    def moments(self, u, logsigmas):
+        """(y_mean [N,d], y_std [N,d]) from the coarse solutions u [N,S,n] of S Monte-Carlo samples per data point
+        (gpde_prolong_moments_*)."""
+        sfx = _lib.suffix(u.dtype)
+        dev = self.device
+        N, S, n = u.shape
+        assert n == self.n
+        u, ls = u.contiguous(), logsigmas.detach().to(u.dtype).contiguous()
+        y_mean = torch.empty((N, self.d), dtype=u.dtype, device=dev)
+        y_std = torch.empty_like(y_mean)
+        fn = getattr(self._lib, "gpde_prolong_moments_" + sfx)
+        _lib.check(fn(self.handle, _lib.ptr(u, dev), _lib.ptr(ls, dev), _lib.ptr(y_mean, dev), _lib.ptr(y_std, dev), N, S,
+                      _lib.stream_of(dev)), "gpde_prolong_moments")
+        return y_mean, y_std
+
+
+class FusedLogLikelihoodFn(torch.autograd.Function):
+    """sum_b log N(Y_b | W rom(exp(effprop_b)+1e-8, F_b), exp(2 logsigmas_y)) in three launches (coarse solve, row pass,
+    weighted transposed prolongation) and one more in backward (adjoint solve); nothing of size [B,d] is written."""
+
+    @staticmethod
+    def forward(ctx, effprop, F, Y, logsigmas, op):
+        from .ROM import _launch_forward
+        rom, pplan = op.rom, op._prolong_plan()
+        plan = rom._get_plan()
+        X, Fc = effprop.contiguous(), F.to(effprop.dtype).contiguous()
+        need = effprop.requires_grad or F.requires_grad or logsigmas.requires_grad
+        u, factor = _launch_forward(plan, X, Fc, True, want_factor=need, info=rom._info_word(X.device))
+        L, gu, gls = pplan.loglik(u, Y, logsigmas, want_grads=need)
+        ctx.plan = plan
+        if need:
+            ctx.save_for_backward(X, u, factor if factor is not None else torch.empty(0, device=X.device), gu, gls)
+        ctx.ls_dtype = logsigmas.dtype
+        return L.sum().to(effprop.dtype)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        from .ROM import _launch_adjoint
+        X, u, factor, gu, gls = ctx.saved_tensors
+        factor = factor if factor.numel() else None
+        gX, gF = _launch_adjoint(ctx.plan, X, u, factor, gu, True, want_gradF=ctx.needs_input_grad[1])
+        g = gout.to(X.dtype)
+        return (gX * g if ctx.needs_input_grad[0] else None, gF * g if gF is not None else None, None,
+                (gls * gout.double()).to(ctx.ls_dtype) if ctx.needs_input_grad[3] else None, None)
+
+
 class ProlongFn(torch.autograd.Function):
     """y[B,d] = u[B,n] W^T ; backward gbar_u = gbar_y W."""
 
@@ -108,6 +169,28 @@ class ReducedOrderModelOperator(torch.nn.Module):
 
         u = self.rom.solve_log(effprop, F)
         return ProlongFn.apply(u, self._prolong_plan())
+
+    # ------------------------------------------------------------------ fused epilogues (opt-in)
+    def log_likelihood(self, effprop, F, Y):
+        """DiagonalGaussianLogLikelihood(Y, *self.forward(effprop, F) with logvars = 2 logsigmas_y) (bottleneck/utils.py:231-241,
+        the term generative.py:438-439 adds to the ELBO), differentiable in effprop, F and logsigmas_y, WITHOUT the
+        intermediate mu_y [B,d]: same value and gradients as the unfused drop-in path up to rounding."""
+        out = FusedLogLikelihoodFn.apply(effprop, F, Y, self.logsigmas_y, self)
+        if not self.rom.deferred_checks:
+            self.rom.check()
+        return out
+
+    @torch.no_grad()
+    def predictive_moments(self, effprops, F):
+        """(Y_mean [N,d], Y_std [N,d]) of the operator output for S samples of the effective property per data point --
+        what GenerativeModel.update_virtual_observables computes in a Python loop over data points with
+        propagate_samples + torch.mean / torch.std (generative.py:198-207).  effprops [N,S,E], F [N,n].  One batched coarse
+        solve and one launch; the output noise is integrated out instead of sampled:
+            Y_std^2 = W Cov_s(u) W^T + exp(2 logsigmas_y)  (the expectation of the reference's sample variance)."""
+        N, S, E = effprops.shape
+        Fx = F.unsqueeze(1).expand(N, S, F.shape[-1]).reshape(N * S, -1)
+        u = self.rom.solve_log(effprops.reshape(N * S, E), Fx)
+        return self._prolong_plan().moments(u.reshape(N, S, -1), self.logsigmas_y)
 
     def propagate_samples(self, effprops, F):
 

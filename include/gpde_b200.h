@@ -108,6 +108,28 @@ int gpde_prolong_apply_f32(const gpde_prolong_plan *plan, const float *u, float 
 int gpde_prolong_apply_T_f32(const gpde_prolong_plan *plan, const float *gy, float *gu, int64_t B,
                              gpde_stream_t stream);
 
+/* Fused operator epilogue: the diagonal-Gaussian log-likelihood of the operator output
+ * DiagonalGaussianLogLikelihood(Y, W u, 2 ls) (bottleneck/utils.py:231-241 on components.py:296-298, as evaluated at
+ * generative.py:438-439) and its gradients, without writing mu_y = W u [B,d]:
+ *     L  [B]   L_b   = -1/2 sum_i [2 ls_i + ((Y_bi - (W u_b)_i) / exp(ls_i))^2 + log 2 pi]        (always double)
+ *     gu [B,n] dL_b/du_b = W^T ((Y_b - W u_b) exp(-2 ls))                          (may be NULL)
+ *     gls[d]   d(sum_b L_b)/dls_i = sum_b (e_bi^2 - 1)                             (always double; may be NULL)
+ * u [B,n], Y [B,d], ls [d] (log standard deviations, the operator's logsigmas_y).  L and gls are zeroed by the call. */
+int gpde_prolong_loglik_f64(const gpde_prolong_plan *plan, const double *u, const double *Y, const double *ls,
+                            double *L, double *gu, double *gls, int64_t B, gpde_stream_t stream);
+int gpde_prolong_loglik_f32(const gpde_prolong_plan *plan, const float *u, const float *Y, const float *ls,
+                            double *L, float *gu, double *gls, int64_t B, gpde_stream_t stream);
+
+/* Monte-Carlo predictive moments of the operator output per data point (generative.py:198-207: propagate_samples, then
+ * torch.mean / torch.std over the S samples) without the [N S, d] samples: with ubar / Cov_u the sample mean / unbiased
+ * covariance of the S coarse solutions u[n,s,:],
+ *     y_mean[n,i] = W_i . ubar_n,     y_std[n,i] = sqrt(W_i Cov_u,n W_i^T + exp(2 ls_i))
+ * (the reference's estimator with the output noise integrated out).  u [N,S,n_coarse], ls [d], y_mean / y_std [N,d]. */
+int gpde_prolong_moments_f64(const gpde_prolong_plan *plan, const double *u, const double *ls, double *y_mean,
+                             double *y_std, int64_t N, int S, gpde_stream_t stream);
+int gpde_prolong_moments_f32(const gpde_prolong_plan *plan, const float *u, const float *ls, float *y_mean,
+                             float *y_std, int64_t N, int S, gpde_stream_t stream);
+
 /* ------------------------------------------------------------------ virtual observables */
 
 /* Replaces QuerryPoint._assemble_system / LinearEllipticPhysics.assemble_system

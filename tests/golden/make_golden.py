@@ -192,13 +192,117 @@ def energy_case(ref, name, nx, refines, N, kind, seed, ell, m_sub, n_it):
     print(name, 'energy VO', np.stack(means).shape, 'T', temps)
 
 
+class _DataSet(object):
+    """What GenerativeModel reads from a data set (utils/data.py is outside the hot path): .get(key) and .N."""
+
+    def __init__(self, **tensors):
+        self._t = tensors
+        self.N = next(iter(tensors.values())).shape[0]
+
+    def get(self, key, random_subset=None):
+        return self._t[key]
+
+    def __bool__(self):
+        return True
+
+
+def elbo_case(ref, name, nx, refines, Ns, Nvo, kind, seed, ell, dim_latent):
+    """The UNMODIFIED GenerativeModel.elbo of the reference (bottleneck/generative.py:247-287, 352-392, 456-500) on a
+    supervised and a virtual-observable data set, with the reference's own ROM / ReducedOrderModelOperator /
+    VirtualObservablesEnsemble / VariationalApproximation / EffectivePropertyMap; the CNN decoder is replaced by
+    oracle/elbo_ref.TinyDecoder.  Stores ELBO, every parameter gradient, the initial parameters and the noise draws."""
+    import importlib
+    from oracle import elbo_ref
+    gen = importlib.import_module("bottleneck.generative")
+    comp, VOm = ref['components'], ref['VirtualObservables']
+    P = fem_p1.build_problem(nx, nx, refines)
+    dt, dev = torch.double, torch.device('cpu')
+    sup = synthetic_inputs(P, Ns, kind, seed, ell)
+    vo = synthetic_inputs(P, Nvo, kind, seed + 1, ell)
+    rng = np.random.RandomState(seed + 50)
+    d, n_pix = len(P['free_dofs_fom']), P['nx_fom'] * P['ny_fom']
+
+    phys_rom = ref_shim.PhysicsLike(P['bc_dofs_rom'], P['free_dofs_rom'], len(P['cells_rom']))
+    rom = ref['ROM'].ROM(phys_rom, torch.tensor(P['M'], dtype=dt), dt, dev)
+    g = comp.ReducedOrderModelOperator(rom, torch.tensor(P['W'], dtype=dt), dtype=dt, device=dev)
+    torch.manual_seed(seed)
+    f = elbo_ref.TinyDecoder(dim_latent, n_pix, dt, dev)
+    gp = comp.EffectivePropertyMap(dim_latent, len(P['cells_rom']), num_hidden_layers=0, independent_X=True, dtype=dt, device=dev)
+    model = gen.GenerativeModel(f=f, g=g, gp=gp, dtype=dt, device=dev)
+
+    # supervised labels: the fine solution of each field (oracle assembler), restricted to the free dofs
+    import scipy.sparse.linalg as spla
+    Y = np.zeros((Ns, d))
+    for b in range(Ns):
+        K, fe = fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], np.exp(sup['X_DG'][b]), P['bc_dofs_fom'],
+                                            sup['g_fom'][b], P['free_dofs_fom'])
+        Y[b] = spla.spsolve(K.tocsc(), fe)
+    ds_s = _DataSet(X=torch.tensor(sup['img'].reshape(Ns, -1)), Y=torch.tensor(Y), F_ROM_BC=torch.tensor(sup['F']))
+    ds_v = _DataSet(X=torch.tensor(vo['img'].reshape(Nvo, -1)), F_ROM_BC=torch.tensor(vo['F']))
+
+    # virtual observables: the reference ensemble with V = W (coarse-grained residuals, infinite precision)
+    class BC(object):
+        def __init__(self, gv):
+            self.g = gv
+
+    def assemble(x, bc):
+        return fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], x, P['bc_dofs_fom'], bc.g, P['free_dofs_fom'])
+
+    phys_fom = ref_shim.PhysicsLike(P['bc_dofs_fom'], P['free_dofs_fom'], len(P['cells_fom']), assemble)
+    V = P['W']
+
+    class FixedSampler(VOm.BaseSampler):
+        def __init__(self, qp):
+            super().__init__(qp)
+            self._GA = qp.construct_querry_weak_galerkin(V)
+        m = property(lambda self: V.shape[1])
+        is_constant = property(lambda self: True)
+        precision_mask = property(lambda self: -np.ones(V.shape[1]))
+
+        def sample(self):
+            return self._GA
+
+    qps = [VOm.QuerryPoint(phys_fom, vo['X_DG'][n], BC(vo['g_fom'][n])) for n in range(Nvo)]
+    qpe = VOm.QuerryPointEnsemble(qps)
+    qe = VOm.QuerryEnsemble([VOm.LinearQuerry(qp, FixedSampler(qp), dt, dev) for qp in qps], dt, dev)
+    ens = VOm.VirtualObservablesEnsemble(qpe, qe, dt, dev)
+    G = rng.normal(size=(Nvo, d)) * 0.1 + (P['W'] @ P['coords_rom'][:, 0])[None]
+    PREC = rng.uniform(20.0, 100.0, size=(Nvo, d))
+    ens.update(torch.tensor(G), torch.tensor(PREC), 0)
+
+    model.register_datasets(dict(supervised=ds_s, vo=ds_v), VO=ens)
+    with torch.no_grad():      # non-trivial variational parameters (the reference initialises them to zero)
+        for key, N in (("supervised", Ns), ("vo", Nvo)):
+            model.q_z[key]._mean.copy_(torch.tensor(rng.normal(size=(N, dim_latent)) * 0.3))
+            model.q_z[key]._logsigma.copy_(torch.tensor(rng.normal(size=(N, dim_latent)) * 0.1 - 1.0))
+            src = sup if key == "supervised" else vo
+            model.q_X[key]._mean.copy_(torch.tensor(src['logX'] + 0.05 * rng.normal(size=src['logX'].shape)))
+            model.q_X[key]._logsigma.copy_(torch.tensor(rng.normal(size=src['logX'].shape) * 0.1 - 2.0))
+        g.logsigmas_y.copy_(torch.tensor(rng.normal(size=d) * 0.1 - 1.5))
+    params = elbo_ref.named_parameters(f, gp, g, model.q_z, model.q_X)
+    init = {k: p.detach().numpy().copy() for k, p in params.items()}
+    with elbo_ref.NoiseTape() as tape:
+        value = model.elbo(step=0)
+    value.backward()
+    grads = {k: p.grad.numpy().copy() for k, p in params.items()}
+    np.savez_compressed(
+        os.path.join(OUT, name + '.npz'), nx=nx, refines=refines, kind=kind, dim_latent=dim_latent,
+        in_sup_img=sup['img'], in_sup_Y=Y, in_sup_F=sup['F'], in_sup_bc_coef=sup['bc_coef'],
+        in_vo_img=vo['img'], in_vo_X_DG=vo['X_DG'], in_vo_F=vo['F'], in_vo_bc_coef=vo['bc_coef'], in_vo_g_fom=vo['g_fom'],
+        in_vo_G=G, in_vo_PREC=PREC, out_vo_mean=ens.mean.numpy(), out_vo_logsigma=ens.logsigma.numpy(),
+        out_elbo=np.array(value.item()), n_noise=len(tape.draws),
+        **{'noise_%d' % i: dr.numpy() for i, dr in enumerate(tape.draws)},
+        **{'init_' + k: v for k, v in init.items()}, **{'grad_' + k: v for k, v in grads.items()})
+    print(name, 'ELBO', value.item(), 'params', len(params), 'noise draws', len(tape.draws))
+
+
 def main():
     if not ref_shim.available():
         raise SystemExit('reference tree not found; fixtures can only be regenerated in the build container')
     ref = ref_shim.load()
     torch.manual_seed(0)
     np.random.seed(0)
-    only = sys.argv[1] if len(sys.argv) > 1 else None            # regenerate one family: rom | vo | energy
+    only = sys.argv[1] if len(sys.argv) > 1 else None            # regenerate one family: rom | vo | energy | elbo
     if only in (None, 'rom'):
         rom_case(ref, 'rom_4x4_ndp', 4, 3, 16, 'NDP', 0, 0.15)      # example.ipynb / highres32 shapes
         rom_case(ref, 'rom_8x8_nd', 8, 2, 8, 'ND', 1, 0.08)         # highres coarse mesh (fine mesh irrelevant here)
@@ -207,6 +311,8 @@ def main():
         vo_case(ref, 'vo_2x2_8_nd', 2, 2, 4, 'ND', 3, 0.3, n_rbf=3)
     if only in (None, 'energy'):
         energy_case(ref, 'energy_2x2_16_ndp', 2, 3, 3, 'NDP', 5, 0.3, m_sub=6, n_it=3)
+    if only in (None, 'elbo'):
+        elbo_case(ref, 'elbo_4x4_16_ndp', 4, 2, 6, 5, 'NDP', 11, 0.2, dim_latent=4)
 
 
 if __name__ == '__main__':

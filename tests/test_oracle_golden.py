@@ -124,3 +124,25 @@ def test_energy_vo_restatement_matches_reference():
             means[n], vars_ = vo_ref.energy_vo_update(K, f, g['in_G'][it, n], g['in_PREC'][it, n], means[n], Vs, T)
             assert rel_err(means[n], g['out_mean'][it, n]) < 1e-12
             assert rel_err(vars_, g['out_vars'][it, n]) < 1e-13
+
+
+def test_elbo_restatement_matches_reference_generative_model():
+    """oracle/elbo_ref.py (the caller of the hot path, generative.py:247-287, 352-392, 456-500) with the oracle's operator
+    and virtual observables reproduces the ELBO and all 15 parameter gradients of the UNMODIFIED GenerativeModel run
+    (tests/golden/elbo_4x4_16_ndp.npz).  The GPU drop-in test swaps the mirrored modules into the same restatement."""
+    from oracle import elbo_ref, fem_p1, vo_ref
+    import elbo_fixture
+    G = load_golden(elbo_fixture.NAME)
+    dt, dev = torch.double, torch.device("cpu")
+    P = fem_p1.build_problem(int(G['nx']), int(G['nx']), int(G['refines']))
+    g = elbo_ref.OracleOperator(torch.tensor(P['M']), torch.tensor(P['bc_dofs_rom']), torch.tensor(P['W']), dt, dev)
+    Gam, alp = [], []
+    for n in range(G['in_vo_X_DG'].shape[0]):
+        K, f = fem_p1.assemble_system_free(P['coords_fom'], P['cells_fom'], np.exp(G['in_vo_X_DG'][n]), P['bc_dofs_fom'],
+                                           G['in_vo_g_fom'][n], P['free_dofs_fom'])
+        Ga, al = vo_ref.construct_querry_weak_galerkin(K, f, P['W'])
+        Gam.append(Ga); alp.append(al)
+    VO = elbo_ref.OracleVO(Gam, alp, torch.zeros(P['W'].shape[1], dtype=dt), G['in_vo_G'], G['in_vo_PREC'], dt)
+    assert rel_err(VO.mean, G['out_vo_mean']) < 1e-9 and rel_err(VO.logsigma, G['out_vo_logsigma']) < 1e-8
+    value, grads = elbo_fixture.run_elbo(g, VO, G, dt, dev)
+    elbo_fixture.compare_with_reference(value, grads, G, 1e-9)
