@@ -289,7 +289,7 @@ class HotPath(object):
         self.path = self.vplan.kernel_path(w.m, tdt)
         self.vo_stream = torch.cuda.Stream(device=dev)
         self.packed, self.ev_packed = None, torch.cuda.Event()
-        self.split_pack = self.path == 2 and tdt == torch.float64
+        self.split_pack = self.path == 2
 
     def vo(self, log_input=None):
         d = self.d

@@ -124,18 +124,20 @@ class VoPlan(object):
         coarse-grained-residual sampler only changes at resample()).  Returns a PackedWeights to pass as ``V``,
         or V itself when this plan / m has no packed layout.  B = the largest batch it will be used with;
         ``out`` = an earlier PackedWeights whose buffer is reused."""
-        Vc = V.to(torch.float64).contiguous()
+        dt = V.dtype if V.dtype in (torch.float32, torch.float64) else torch.float64
+        Vc = V.to(dt).contiguous()
+        sfx = _lib.suffix(dt)
         m = int(Vc.shape[1])
         need = max(8, int(self._lib.gpde_vo_workspace_bytes(self.handle, int(B), m)))
         if out is not None and out.buf.numel() >= need:
             buf = out.buf
         else:
             buf = torch.empty(need, dtype=torch.uint8, device=self.device)
-        rc = self._lib.gpde_vo_pack_weights_f64(self.handle, _lib.ptr(Vc, self.device), m, 1 if ignore_load else 0,
-                                                _lib.ptr(buf, self.device), _lib.stream_of(self.device))
+        rc = getattr(self._lib, "gpde_vo_pack_weights_" + sfx)(self.handle, _lib.ptr(Vc, self.device), m, 1 if ignore_load else 0,
+                                                               _lib.ptr(buf, self.device), _lib.stream_of(self.device))
         if rc == 1:
             return Vc
-        _lib.check(rc, "gpde_vo_pack_weights_f64")
+        _lib.check(rc, "gpde_vo_pack_weights_" + sfx)
         return PackedWeights(Vc, buf, int(B), bool(ignore_load))
 
     def residual(self, a, y, g, V, *, a_is_log=True, want_rho=False, ignore_load=False):
@@ -154,7 +156,7 @@ class VoPlan(object):
         packed = None
         if isinstance(V, PackedWeights):
             # usable as packed only for the kind of call it was packed for; otherwise the plain matrix is used
-            if (dt == torch.float64 and y is not None and not want_rho and B <= V.B and V.ignore_load == bool(ignore_load)
+            if (dt == V.V.dtype and y is not None and not want_rho and B <= V.B and V.ignore_load == bool(ignore_load)
                     and a.data_ptr() % 16 == 0):
                 packed = V
             V = V.V

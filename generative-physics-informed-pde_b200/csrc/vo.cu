@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 
 namespace gpde {
 
@@ -508,7 +509,8 @@ static bool use_grid(const gpde_vo_plan *pl) {
 // served the call, 0 if vo_grid.cuh should.  rho_pitch > 0 selects the rho variant (V, m unused).
 // GPDE_GRID_V=1 keeps it out (A/B runs against the general kernel).
 // mesh-side conditions and the decomposition of the lean kernel for m weighting functions (rho: no V inside)
-static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid2Dev &G, int &NT, int &NX, size_t &smem) {
+static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid2Dev &G, int &NT, int &NX, size_t &smem,
+                        int ea = 8, int ey = 8) {   // ea / ey: bytes per element of a / y (8 or 4)
     const GridDev &G0 = pl->grid;
     if (pl->env.no_grid2) return false;
     const int nx = G0.nx, ny = G0.ny;
@@ -528,12 +530,14 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     G.groups = 16 / G.nstrips;
     G.in0 = G0.in0; G.sy = G0.sy; G.rh = G0.rh; G.scale = G0.scale;
     const int S = 8 * G.groups;
-    G.a_pitch = 2 * nx + 2;
-    G.y_pitch = 2 * nx + 8;
-    G.y_off = S * G.a_pitch * 8;
+    // pitches in elements, chosen against bank conflicts of the warp's reads (vo_grid2.cuh): FP32 rows need a_pitch = 16 mod 32
+    // (LDS.128 of two samples per phase) and y_pitch = 4 mod 8 (the samples' phases then spread the banks)
+    G.a_pitch = ea == 8 ? 2 * nx + 2 : 2 * nx + 16;
+    G.y_pitch = ey == 8 ? 2 * nx + 8 : 2 * nx + 12;
+    G.y_off = S * G.a_pitch * ea;
     G.v_off = 0;
     G.v_row_bytes = rho ? 0 : G.nstrips * (4 * NT * 32 * 8 + NX * 128) + kGrid2MaskBytes;
-    G.stage_bytes = (G.y_off + S * G.y_pitch * 8 + 127) & ~127;
+    G.stage_bytes = (G.y_off + S * G.y_pitch * ey + 127) & ~127;
     const size_t fixed = 2 * (size_t)G.stage_bytes + (4 * 16 + 8) * sizeof(unsigned long long) + 258 * sizeof(double);
     // V ring: three 2-row stages when they fit (the sample groups of a CTA may then drift a stage apart), else two
     G.nvs = rho ? 0 : ((fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2);
@@ -544,23 +548,28 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     return true;
 }
 
-static void grid2_pack(const Grid2Dev &G, const double *V, int m, int NT, int NX, double *Vp, int n_sm, cudaStream_t st) {
+template <typename TV>
+static void grid2_pack(const Grid2Dev &G, const TV *V, int m, int NT, int NX, double *Vp, int n_sm, cudaStream_t st) {
     const long long total = (long long)(G.ny + 1) * G.v_row_bytes / 8;
     const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)n_sm * 8);
-    vo_grid2_pack_kernel<<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
+    vo_grid2_pack_kernel<TV><<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
 }
 
-static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
-                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
+// TA: conductivities, Dirichlet values and V; TY: y; TR: result (r, or the rho rows of the rho variant)
+template <typename TA, typename TY, typename TR>
+static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride, int a_is_log, const TY *y,
+                        const TA *g, long long g_stride, const TA *V, int m, TR *r, void *workspace,
                         int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st, long long y_stride = 0) {
+    constexpr int EA = (int)sizeof(TA), EY = (int)sizeof(TY);
     if (y_stride == 0) y_stride = pl->dev.d;
     if (y_stride != pl->dev.d && rho_pitch <= 0) return 0;   // only the rho variant is built for strided y
     const bool rho = rho_pitch > 0;
     Grid2Dev G;
     int NT, NX;
     size_t smem;
-    if (!grid2_setup(pl, m, rho, sub_f, G, NT, NX, smem)) return 0;
-    if (((uintptr_t)a & 15) || (a_stride & 1) || ((uintptr_t)y & 7)) return 0;
+    if (!grid2_setup(pl, m, rho, sub_f, G, NT, NX, smem, EA, EY)) return 0;
+    // 16-byte pieces of a: base, sample stride and the plan's pixel offsets; y only needs its natural alignment
+    if (((uintptr_t)a & 15) || ((a_stride * EA) & 15) || ((G.in0 * EA) & 15) || ((G.sy * EA) & 15) || ((uintptr_t)y & (EY - 1))) return 0;
     if (!rho && ((uintptr_t)workspace & 15)) return 0;
     const int S = 8 * G.groups;
     double *Vp = (double *)workspace;
@@ -585,40 +594,63 @@ static int launch_grid2(const gpde_vo_plan *pl, const double *a, long long a_str
     // allocation (as a run-time branch the two paths cost each other 4-8 %, measured A/B)
 #define GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, YSV)                                                                \
     {                                                                                                            \
-        auto kern = a_is_log ? vo_grid2_kernel<NTV, NXV, RHOV, YSV, true> : vo_grid2_kernel<NTV, NXV, RHOV, YSV, false>; \
+        auto kern = a_is_log ? vo_grid2_kernel<NTV, NXV, RHOV, YSV, true, TA, TY, TR>                           \
+                             : vo_grid2_kernel<NTV, NXV, RHOV, YSV, false, TA, TY, TR>;                         \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
         GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
                                         (const double *)Vp, m_arg, r, B));                                       \
     }
 #define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV) GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, false)
-    if (rho && y_stride != pl->dev.d) GPDE_LAUNCH_GRID2_YS(1, 0, true, true)
-    else if (rho) GPDE_LAUNCH_GRID2(1, 0, true)
-    else if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)
-    else if (NT == 1) GPDE_LAUNCH_GRID2(1, 1, false)
-    else if (NT == 2 && NX == 0) GPDE_LAUNCH_GRID2(2, 0, false)
-    else if (NT == 2) GPDE_LAUNCH_GRID2(2, 1, false)
-    else if (NT == 3 && NX == 0) GPDE_LAUNCH_GRID2(3, 0, false)
-    else if (NT == 3) GPDE_LAUNCH_GRID2(3, 1, false)
-    else GPDE_LAUNCH_GRID2(4, 0, false)
+    // instantiated type combinations: (T,T,T) every variant but the strided-y one for FP32; (float,float,double) the rho
+    // variant only (rho rows for the FP64 contraction); (T,double,T) the strided-y rho variant only (residual_T)
+    constexpr bool same = std::is_same<TA, TY>::value && std::is_same<TA, TR>::value;
+    constexpr bool ys_ok = std::is_same<TY, double>::value && std::is_same<TA, TR>::value;
+    constexpr bool rho_ok = std::is_same<TA, TY>::value;
+    if (rho && y_stride != pl->dev.d) {
+        if constexpr (ys_ok) GPDE_LAUNCH_GRID2_YS(1, 0, true, true)
+        else return 0;
+    } else if (rho) {
+        if constexpr (rho_ok) GPDE_LAUNCH_GRID2(1, 0, true)
+        else return 0;
+    } else if constexpr (same) {
+        if (NT == 1 && NX == 0) GPDE_LAUNCH_GRID2(1, 0, false)
+        else if (NT == 1) GPDE_LAUNCH_GRID2(1, 1, false)
+        else if (NT == 2 && NX == 0) GPDE_LAUNCH_GRID2(2, 0, false)
+        else if (NT == 2) GPDE_LAUNCH_GRID2(2, 1, false)
+        else if (NT == 3 && NX == 0) GPDE_LAUNCH_GRID2(3, 0, false)
+        else if (NT == 3) GPDE_LAUNCH_GRID2(3, 1, false)
+        else GPDE_LAUNCH_GRID2(4, 0, false)
+    } else {
+        return 0;
+    }
 #undef GPDE_LAUNCH_GRID2
 #undef GPDE_LAUNCH_GRID2_YS
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
 }
 
-// Structured-grid path (FP64 I/O only).  Returns 1 if it served the call, 0 if the caller should use the
-// generic kernels (alignment / size conditions not met), <0 on error.
+// Structured-grid path.  Returns 1 if it served the call, 0 if the caller should use the generic kernels (alignment /
+// size conditions not met), <0 on error.  FP32 I/O: the lean kernel only.
+template <typename T>
+static int launch_grid_lean(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *y,
+                            const T *g, long long g_stride, const T *V, int m, T *r, void *workspace,
+                            int sub_f, bool prepacked, long long B, cudaStream_t st) {
+    if (!y || m < 1 || m > 32) return 0;
+    const int rc2 = launch_grid2<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, prepacked, B, st);
+    if (rc2 != 0) return rc2;
+    if (prepacked)
+        return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) need the lean structured-grid kernel for this call "
+                                  "(16-byte aligned a and sample stride, y given, no load vector)");
+    return 0;
+}
 static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
                        int sub_f, bool prepacked, long long B, cudaStream_t st) {
     GridDev G = pl->grid;
     if (!y || m < 1 || m > 32) return 0;
     {
-        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, prepacked, B, st);
+        const int rc2 = launch_grid_lean<double>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, sub_f, prepacked, B, st);
         if (rc2 != 0) return rc2;
-        if (prepacked)
-            return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) need the lean structured-grid kernel for this call "
-                                      "(16-byte aligned a, even a_stride, y given, no load vector)");
     }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
     const int NT = m <= 8 ? 1 : (m <= 16 ? 2 : 4);
@@ -658,13 +690,20 @@ static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stri
 
 // Structured-grid fine residual rho[B][pitch] (pitch >= d, padding zeroed) for the tensor-core contraction.
 // Returns 1 if it served the call, 0 if the generic matvec kernel should (alignment / size), <0 on error.
+template <typename T, typename TR>
+static int launch_grid_rho_lean(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *y,
+                                const T *g, long long g_stride, TR *rho, int pitch, int sub_f, long long B, cudaStream_t st) {
+    if (!y) return 0;
+    return launch_grid2<T, T, TR>(pl, a, a_stride, a_is_log, y, g, g_stride, (const T *)nullptr, 0, rho, nullptr, pitch, sub_f,
+                                  false, B, st);
+}
 static int launch_grid_rho(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
                            const double *g, long long g_stride, double *rho, int pitch, int sub_f, long long B,
                            cudaStream_t st) {
     GridDev G = pl->grid;
     if (!y) return 0;
     {
-        const int rc2 = launch_grid2(pl, a, a_stride, a_is_log, y, g, g_stride, nullptr, 0, rho, nullptr, pitch, sub_f, false, B, st);
+        const int rc2 = launch_grid_rho_lean<double, double>(pl, a, a_stride, a_is_log, y, g, g_stride, rho, pitch, sub_f, B, st);
         if (rc2 != 0) return rc2;
     }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1)) return 0;
@@ -730,13 +769,21 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
     if (B == 0) return GPDE_OK;
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
-    if constexpr (sizeof(T) == 8) {
-        if (m > 0 && !rho && use_grid(pl)) {
-            const int rc = launch_grid(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y,
-                                       (const double *)g, (long long)g_stride, (const double *)V, m, (double *)r,
-                                       workspace, (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
-            if (rc != 0) return rc < 0 ? rc : GPDE_OK;
-        }
+    if (m > 0 && !rho && use_grid(pl)) {
+        int rc;
+        if constexpr (sizeof(T) == 8)
+            rc = launch_grid(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y,
+                             (const double *)g, (long long)g_stride, (const double *)V, m, (double *)r,
+                             workspace, (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
+        else
+            rc = launch_grid_lean<T>(pl, a, (long long)a_stride, a_is_log, y, g, (long long)g_stride, V, m, r, workspace,
+                                     (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
+        if (rc != 0) return rc < 0 ? rc : GPDE_OK;
+    }
+    if (m == 0 && rho && use_grid(pl)) {   // the fine residual alone: rho rows straight into the caller's [B,d]
+        const int rc = launch_grid_rho_lean<T, T>(pl, a, (long long)a_stride, a_is_log, y, g, (long long)g_stride, rho, pl->dev.d,
+                                                  (flags & 1) ? 0 : 1, (long long)B, st);
+        if (rc != 0) return rc < 0 ? rc : GPDE_OK;
     }
     if (flags & 2) return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) are not usable for this call");
     if (m > 0 && m <= 32 && use_fused(pl)) {
@@ -762,12 +809,14 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
     const int d = pl->dev.d, dp = gemm_dp(d);
     double *ws = m > 0 ? (double *)workspace : nullptr;
     int rc = 0;
-    if constexpr (sizeof(T) == 8) {   // structured pixel grid: the marching kernel produces rho (no V inside)
-        if (m > 0 && !rho && use_grid(pl)) {
+    if (m > 0 && !rho && use_grid(pl)) {   // structured pixel grid: the marching kernel produces rho (no V inside)
+        if constexpr (sizeof(T) == 8)
             rc = launch_grid_rho(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y, (const double *)g,
                                  (long long)g_stride, ws, dp, (flags & 1) ? 0 : 1, (long long)B, st);
-            if (rc < 0) return rc;
-        }
+        else
+            rc = launch_grid_rho_lean<T, double>(pl, a, (long long)a_stride, a_is_log, y, g, (long long)g_stride, ws, dp,
+                                                 (flags & 1) ? 0 : 1, (long long)B, st);
+        if (rc < 0) return rc;
     }
     if (rc == 0) {
         rc = launch_matvec<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, (flags & 1) ? 0 : 1, ws, dp, rho, B, st);
@@ -805,6 +854,40 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     if (!a || !V || !s || !q || !workspace) return fail(GPDE_ERR_ARG, "vo_residual_T: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if constexpr (sizeof(T) == 4) {
+        // FP32 I/O on the reference's pixel meshes, m <= 32: the same two launches as FP64 (s, V converted on load by the
+        // expansion kernel; w stays FP64 workspace; the marching kernel stages a as floats and stores q as floats)
+        Grid2Dev G2;
+        int nt2, nx2;
+        size_t smem2;
+        if (use_grid(pl) && m <= 32 && !((uintptr_t)a & 15) && !((a_stride * 4) & 15) && !((uintptr_t)workspace & 15) &&
+            grid2_setup(pl, 0, true, 0, G2, nt2, nx2, smem2, 4, 8)) {
+            const int d = pl->dev.d;
+            double *w = (double *)workspace;
+            const long long ldw = ((long long)d + 3) & ~3ll;
+            const int n_tiles = (d + 7) / 8;
+            const unsigned gx = (unsigned)((B + 8 * kExpandMT * kExpandWarps - 1) / (8 * kExpandMT * kExpandWarps));
+            const int nch = std::max(1, std::min(n_tiles, (int)(4 * pl->n_sm / gx)));
+            const int tpc = std::min((n_tiles + nch - 1) / nch, 64);
+            const dim3 grid(gx, (unsigned)((n_tiles + tpc - 1) / tpc));
+            const size_t smem = (size_t)tpc * 8 * kExpandVPitch * sizeof(double);
+#define GPDE_LAUNCH_EXPAND_F(KSV)                                                                                   \
+    {                                                                                                               \
+        auto kern = vo_expand_dmma_kernel<KSV, float>;                                                              \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        kern<<<grid, kExpandWarps * 32, smem, st>>>((const float *)s, (const float *)V, w, ldw, (long long)B, d, m, tpc); \
+    }
+            if (m <= 8) GPDE_LAUNCH_EXPAND_F(2)
+            else if (m <= 16) GPDE_LAUNCH_EXPAND_F(4)
+            else if (m <= 28) GPDE_LAUNCH_EXPAND_F(7)
+            else GPDE_LAUNCH_EXPAND_F(8)
+#undef GPDE_LAUNCH_EXPAND_F
+            GPDE_CUDA_OK(cudaGetLastError());
+            const int rc2 = launch_grid2<float, double, float>(pl, (const float *)a, (long long)a_stride, a_is_log, w, nullptr, 0,
+                                                               nullptr, 0, (float *)q, nullptr, d, 0, false, (long long)B, st, ldw);
+            if (rc2 != 0) return rc2 < 0 ? rc2 : GPDE_OK;
+        }
+    }
     if constexpr (sizeof(T) == 8) {
         // structured pixel grid: w = s V^T on the FP64 tensor pipe, then q = K_ff w with the marching kernel
         // (rho of u~ = (w, 0) without the load vector IS K_ff w)
@@ -839,8 +922,9 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
 #undef GPDE_LAUNCH_EXPAND
                 GPDE_CUDA_OK(cudaGetLastError());
                 if (lean) {
-                    const int rc2 = launch_grid2(pl, (const double *)a, (long long)a_stride, a_is_log, w, nullptr, 0, nullptr, 0,
-                                                 (double *)q, nullptr, d, 0, false, (long long)B, st, ldw);
+                    const int rc2 = launch_grid2<double, double, double>(pl, (const double *)a, (long long)a_stride, a_is_log, w,
+                                                                         nullptr, 0, nullptr, 0, (double *)q, nullptr, d, 0, false,
+                                                                         (long long)B, st, ldw);
                     if (rc2 != 0) return rc2 < 0 ? rc2 : GPDE_OK;
                     return fail(GPDE_ERR_ARG, "vo_residual_T: lean grid kernel declined after setup");
                 }
@@ -989,8 +1073,16 @@ int gpde_vo_plan_info(const gpde_vo_plan *pl, int64_t out[8]) {
 
 int gpde_vo_plan_kernel_path(const gpde_vo_plan *pl, int m, int elem_bytes) {
     if (!pl) return fail(GPDE_ERR_ARG, "vo_plan_kernel_path: null");
-    if (m > 0 && m <= 32 && elem_bytes == 8 && use_grid(pl)) return 2;
-    if (m > 32 && elem_bytes == 8 && use_grid(pl)) return 3;
+    if (elem_bytes == 8) {
+        if (m > 0 && m <= 32 && use_grid(pl)) return 2;
+        if (m > 32 && use_grid(pl)) return 3;
+    } else if (use_grid(pl)) {   // FP32 I/O: the lean kernel only (the reference's own meshes)
+        Grid2Dev G;
+        int NT, NX;
+        size_t smem;
+        if (m > 0 && m <= 32 && grid2_setup(pl, m, false, 1, G, NT, NX, smem, 4, 4)) return 2;
+        if (m > 32 && grid2_setup(pl, 0, true, 1, G, NT, NX, smem, 4, 4)) return 3;
+    }
     if (m > 0 && m <= 32 && use_fused(pl)) return 1;
     return 0;
 }
@@ -1019,6 +1111,20 @@ int gpde_vo_pack_weights_f64(const gpde_vo_plan *pl, const double *V, int m, int
     if (!use_grid(pl) || !grid2_setup(pl, m, false, (flags & 1) ? 0 : 1, G, NT, NX, smem)) return 1;
     DeviceGuard guard(pl->device);
     grid2_pack(G, V, m, NT, NX, (double *)workspace, pl->n_sm, (cudaStream_t)stream);
+    GPDE_CUDA_OK(cudaGetLastError());
+    return GPDE_OK;
+}
+
+int gpde_vo_pack_weights_f32(const gpde_vo_plan *pl, const float *V, int m, int flags, void *workspace,
+                             gpde_stream_t stream) {
+    if (!pl || !V || !workspace) return fail(GPDE_ERR_ARG, "vo_pack_weights: null argument");
+    if ((uintptr_t)workspace & 15) return fail(GPDE_ERR_ARG, "vo_pack_weights: workspace must be 16-byte aligned");
+    Grid2Dev G;
+    int NT, NX;
+    size_t smem;
+    if (!use_grid(pl) || !grid2_setup(pl, m, false, (flags & 1) ? 0 : 1, G, NT, NX, smem, 4, 4)) return 1;
+    DeviceGuard guard(pl->device);
+    grid2_pack<float>(G, V, m, NT, NX, (double *)workspace, pl->n_sm, (cudaStream_t)stream);
     GPDE_CUDA_OK(cudaGetLastError());
     return GPDE_OK;
 }

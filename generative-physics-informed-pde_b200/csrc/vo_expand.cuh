@@ -22,9 +22,10 @@ constexpr int kExpandVPitch = 36;                // doubles per V row in shared 
 
 // ldw = row pitch of w in doubles (>= d); even ldw with a 16-byte aligned w lets every lane store its two adjacent
 // columns as one 16-byte piece (a warp's store = 8 rows x 64 contiguous bytes = whole sectors)
-template <int KS>
+// TS: element type of s and V (FP32 I/O converts on load; w is FP64 workspace in both cases)
+template <int KS, typename TS = double>
 __global__ void __launch_bounds__(kExpandWarps * 32, 2)
-vo_expand_dmma_kernel(const double *__restrict__ s, const double *__restrict__ V, double *__restrict__ w, long long ldw,
+vo_expand_dmma_kernel(const TS *__restrict__ s, const TS *__restrict__ V, double *__restrict__ w, long long ldw,
                       long long B, int d, int m, int tiles_per_chunk) {
     extern __shared__ __align__(16) double vsm[];   // [rows of the chunk][kExpandVPitch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,7 +38,7 @@ vo_expand_dmma_kernel(const double *__restrict__ s, const double *__restrict__ V
         const int rows = 8 * (nt1 - nt0), row0 = 8 * nt0;
         for (int idx = threadIdx.x; idx < rows * (4 * KS); idx += kExpandWarps * 32) {
             const int rr = idx / (4 * KS), c = idx - rr * (4 * KS);
-            vsm[rr * kExpandVPitch + c] = (row0 + rr < d && c < m) ? __ldg(V + (long long)(row0 + rr) * m + c) : 0.0;
+            vsm[rr * kExpandVPitch + c] = (row0 + rr < d && c < m) ? (double)__ldg(V + (long long)(row0 + rr) * m + c) : 0.0;
         }
     }
     double af[kExpandMT][KS];
@@ -47,7 +48,7 @@ vo_expand_dmma_kernel(const double *__restrict__ s, const double *__restrict__ V
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
             const int c = 4 * ks + k4;
-            af[mt][ks] = (b < B && c < m) ? __ldg(s + b * m + c) : 0.0;
+            af[mt][ks] = (b < B && c < m) ? (double)__ldg(s + b * m + c) : 0.0;
         }
     }
     __syncthreads();

@@ -20,6 +20,9 @@
 //     allocation: every variant gets its own).
 // Shared memory: 2 a/y stages | 2-3 V stages | barriers | exp table; the a/y stages are zero-initialised once so that the
 // few halo reads that fall outside a sample's rows see finite numbers.
+//   * the I/O element types are template parameters (TA: conductivities and Dirichlet values, TY: y, TR: result): FP32 I/O
+//     stages the rows as floats (half the copies, half the shared memory) and converts when a lane reads its values; the
+//     arithmetic is FP64 in every variant (the reference's model dtype is float32, factories/model.py:181,224).
 #pragma once
 #include "exp256.cuh"
 
@@ -30,7 +33,7 @@ struct Grid2Dev {
     int nstrips, lognstrips, groups;
     long long in0, sy;       // conductivity entry of pixel (cx, cy) = in0 + cy * sy + cx
     double rh, scale;
-    int a_pitch, y_pitch;    // doubles per sample inside a stage
+    int a_pitch, y_pitch;    // elements (of TA / TY) per sample inside a stage
     int y_off, v_off;        // byte offsets inside a stage
     int stage_bytes, v_row_bytes;   // one a/y stage (all samples of the CTA); one packed V row
     int nvs;                        // V stages in the ring (2 or 3)
@@ -39,6 +42,9 @@ struct Grid2Dev {
 
 __device__ __forceinline__ void cp_async8_u32(unsigned smem_dst, const void *gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4_u32(unsigned smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity) {
     unsigned done;
@@ -76,6 +82,21 @@ __device__ __forceinline__ double lds64(unsigned addr) {
     return v;
 }
 
+__device__ __forceinline__ float lds32f(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds128f(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// one staged element as a double
+template <typename T> __device__ __forceinline__ double lds_elem(unsigned addr);
+template <> __device__ __forceinline__ double lds_elem<double>(unsigned addr) { return lds64(addr); }
+template <> __device__ __forceinline__ double lds_elem<float>(unsigned addr) { return (double)lds32f(addr); }
+
 // exp_tab16 (vo_grid.cuh) with its nine 64-bit constants read as constant-bank operands of the FP64 instructions instead
 // of being re-materialised into registers (two moves each) for every row
 __constant__ double kExpK[9] = {23.083120654223414, -0.04332169877307024, -1.1926343307941173e-11,
@@ -107,7 +128,8 @@ __device__ __forceinline__ double exp_tab16c(double x, unsigned tab) {   // tab 
 //   (exact: it only drops products with 0): V = W of the coarse-grained-residual sampler (VirtualObservables.py:297-321)
 //   has <= 4 non-zero columns per block (P1 hat functions of the coarse mesh), i.e. 1-2 of its 3-4 tiles.
 constexpr int kGrid2MaskBytes = 32;
-__global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, int m, int NT, int NX,
+template <typename TV>
+__global__ void vo_grid2_pack_kernel(Grid2Dev G, const TV *__restrict__ V, int m, int NT, int NX,
                                      double *__restrict__ Vp) {
     // programmatic dependent launch: the residual kernel may start its prologue (shared-memory setup, first a / y
     // stages) now; it waits for this grid (griddepcontrol.wait) before it touches the packed rows
@@ -133,7 +155,7 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
             c = rem;             // [q][k][j] = column 16 q + 4 k + j
             col = 8 * NT;
         }
-        Vp[i] = (c < G.ncol && col < m && (NX || col < 8 * NT)) ? V[((long long)t * G.ncol + c) * m + col] : 0.0;
+        Vp[i] = (c < G.ncol && col < m && (NX || col < 8 * NT)) ? (double)V[((long long)t * G.ncol + c) * m + col] : 0.0;
     }
     // masks: one warp per (node row, strip)
     const int lane = threadIdx.x & 31;
@@ -145,7 +167,7 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const double *__restrict__ V, i
         if (q < G.nstrips) {
             for (int i = lane; i < 16 * mcols; i += 32) {
                 const int c = 16 * q + i / mcols, col = i % mcols;
-                if (c < G.ncol && V[((long long)t * G.ncol + c) * m + col] != 0.0) bits |= col < 8 * NT ? 1u << (col >> 3) : 0x80u;
+                if (c < G.ncol && V[((long long)t * G.ncol + c) * m + col] != (TV)0) bits |= col < 8 * NT ? 1u << (col >> 3) : 0x80u;
             }
         }
         bits = __reduce_or_sync(0xffffffffu, bits);
@@ -182,17 +204,18 @@ __device__ __forceinline__ void grid2_contract(unsigned msk, double (&acc)[NT][2
     }
 }
 
-template <int NT, int NX, bool RHO, bool YS, bool ALOG>
+template <int NT, int NX, bool RHO, bool YS, bool ALOG, typename TA = double, typename TY = double, typename TR = double>
 __global__ void __launch_bounds__(512, 1)
-vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, int a_is_log,
-                const double *__restrict__ y, long long y_stride_arg, const double *__restrict__ g, long long g_stride,
-                const double *__restrict__ Vp, int m, double *__restrict__ r, long long B) {
-    // y_stride = doubles between the rows of consecutive samples in y: d for a contiguous [B,d]; only the YS variant
+vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_is_log,
+                const TY *__restrict__ y, long long y_stride_arg, const TA *__restrict__ g, long long g_stride,
+                const double *__restrict__ Vp, int m, TR *__restrict__ r, long long B) {
+    // y_stride = elements between the rows of consecutive samples in y: d for a contiguous [B,d]; only the YS variant
     // takes it from its argument (the expansion kernel of residual_T pads the rows of w to a multiple of 4 doubles):
     // one more live value shifts the register allocation of the other variants by ~3 % (measured A/B on one box)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kThreads = 512, kWarps = 16;
     constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
+    constexpr int EA = (int)sizeof(TA), EY = (int)sizeof(TY);   // bytes per staged element
     // shared memory: 2 a/y stages | nvs V stages | barriers | exp table
     const int v_bytes = 2 * G.v_row_bytes;          // one V stage = 2 packed rows
     unsigned char *v_base = smem_raw + 2 * (size_t)G.stage_bytes;
@@ -242,45 +265,77 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     // ---- staging.  Every sample group (8 samples, nstrips warps) runs its OWN two-stage ring of a / y rows with its
     // own barriers, so the groups drift apart and the four warps of a scheduler (one per group) sit in different
     // phases of the row (exp / fluxes / DMMA / waiting); only the packed V rows are shared by the CTA (ring of nvs
-    // stages, copied by thread 0).  Thread tg of a group copies piece (tg mod nx) of samples (tg / nx) + 2 i, i < 4.
+    // stages, copied by thread 0).  A sample's two rows of a stage are 2 nx E / 16 pieces of 16 bytes (E = element
+    // size): the 2 nx threads of a group copy piece (tg mod pieces) of samples (tg / pieces) + (16 / E) i, i < E / 2
+    // (FP64: 4 pieces per thread and array, samples 2 apart; FP32: 2 pieces, samples 4 apart).
     const int tg = tid & (gthreads - 1);
-    const int piece = tg & (nx - 1), smp0 = 8 * grp + (tg >> G.lognx);
-    int nv = 0;
+    constexpr int NIA = EA / 2, SSA = 16 / EA, NIY = EY / 2, SSY = 16 / EY;
+    const int lpa = G.lognx - (EA == 8 ? 0 : 1), lpy = G.lognx - (EY == 8 ? 0 : 1);   // log2(pieces per sample)
+    const int piece_a = tg & ((1 << lpa) - 1), smp0a = 8 * grp + (tg >> lpa);
+    const int piece = tg & ((1 << lpy) - 1), smp0 = 8 * grp + (tg >> lpy);             // y
+    int nva = 0, nv = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) nv += (cta_b0 + smp0 + 2 * i < B) ? 1 : 0;
-    // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx doubles (lowest address first)
-    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece;
-    const long long a_adv = 16 * G.sy, a_smp = 2 * a_stride * 8;
-    const unsigned a_dst = smp0 * G.a_pitch * 8 + 16 * piece, a_dsmp = 2 * G.a_pitch * 8;
-    // node rows 2 ts + 1, 2 ts + 2: 2 ncol doubles starting on an 8-byte boundary; copied from the enclosing
-    // 16-byte boundary (the phase is the same for all stages and for the 4 samples of a thread: d is odd, the
-    // samples are 2 apart)
+    for (int i = 0; i < NIA; ++i) nva += (cta_b0 + smp0a + SSA * i < B) ? 1 : 0;
+#pragma unroll
+    for (int i = 0; i < NIY; ++i) nv += (cta_b0 + smp0 + SSY * i < B) ? 1 : 0;
+    // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx elements (lowest address first)
+    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0a) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece_a;
+    const long long a_adv = 2 * EA * G.sy, a_smp = SSA * a_stride * EA;
+    const unsigned a_dst = smp0a * G.a_pitch * EA + 16 * piece_a, a_dsmp = SSA * G.a_pitch * EA;
+    // node rows 2 ts + 1, 2 ts + 2: 2 ncol elements starting on an element boundary; copied from the enclosing
+    // 16-byte boundary.  The phase y_sig (in elements) is the same for the samples of a thread (they are 16 / E apart).
+    // FP64: it is the same for all stages too (a stage advances by 16 ncol bytes); FP32: a stage advances by 8 ncol
+    // bytes with ncol odd, so the phase alternates between y_sig and y_sig ^ 2 from stage to stage
     const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * y_stride + ncol);
-    const int y_sig = (int)(((unsigned long long)y_row1 >> 3) & 1);
-    const char *y_src = y_row1 - 8 * y_sig + 16 * piece;
-    const long long y_adv = 16 * ncol, y_smp = 2 * y_stride * 8;
-    // slot of sample sl starts at (sl * y_pitch + 2 * ((sl >> 1) & 1) + 2) doubles; (smp0 + 2 i) >> 1 has the parity of i
-    const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + 2) * 8 + 16 * piece, y_dsmp = 2 * G.y_pitch * 8;
-    const bool y_piece_ok = piece < nx - 1 || y_sig;
-    // the last piece of the batch's last sample would read 8 bytes past the tensor: copied as 8 bytes instead
-    const bool y_tail = y_sig && piece == nx - 1 && nv > 0 && cta_b0 + smp0 + 2 * (nv - 1) == B - 1;
+    int y_sig = (int)(((unsigned long long)y_row1 / EY) & (16 / EY - 1));
+    const char *y_src = y_row1 - EY * y_sig + 16 * piece;
+    const long long y_adv = 2 * EY * ncol, y_smp = SSY * y_stride * EY;
+    // FP64: slot of sample sl starts at (sl * y_pitch + 2 * ((sl >> 1) & 1) + 2) doubles; (smp0 + 2 i) >> 1 has the parity of i.
+    // FP32: at (sl * y_pitch + 4) floats; the phases of consecutive samples differ (d is odd) and y_pitch = 4 mod 8, so the
+    // 8 samples x 4 lanes of a warp read 32 different banks
+    const unsigned y_dst = G.y_off + (smp0 * G.y_pitch + (EY == 8 ? 2 : 4)) * EY + 16 * piece, y_dsmp = SSY * G.y_pitch * EY;
+    // FP64: the last piece is needed only with phase 1; FP32: the window of 2 nx floats always ends in the last piece, and
+    // with phase 3 one more float follows it
+    const bool y_last_piece = piece == (1 << lpy) - 1;
+    const bool y_piece_ok = EY == 8 ? (!y_last_piece || y_sig) : true;
+    // the last piece of the batch's last sample would read past the tensor: copied element-wise instead
+    // (FP32: only when the stage's phase leaves part of the piece outside, decided per stage)
+    const bool y_tail = (EY == 8 ? y_sig != 0 : true) && y_last_piece && nv > 0 && cta_b0 + smp0 + SSY * (nv - 1) == B - 1;
     unsigned long long *my_full = full_ay + 2 * grp, *my_empty = empty_ay + 2 * grp;
 
     auto issue_stage = [&](int ts, int slot) {
         const unsigned sb = sm0 + slot * G.stage_bytes;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (i < nv) cp_async16_u32(sb + a_dst + i * a_dsmp, a_src + i * a_smp);
+        for (int i = 0; i < NIA; ++i)
+            if (i < nva) cp_async16_u32(sb + a_dst + i * a_dsmp, a_src + i * a_smp);
         if (y_piece_ok) {
-            const int nvy = nv - ((y_tail && ts == n_stages - 1) ? 1 : 0);
+            const int nvy = nv - ((y_tail && ts == n_stages - 1 && (EY == 8 || y_sig < 2)) ? 1 : 0);
+            if constexpr (EY == 8) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp + 16 * (i & 1), y_src + i * y_smp);
-            if (nvy != nv) cp_async8_u32(sb + y_dst + (nv - 1) * y_dsmp + 16 * ((nv - 1) & 1), y_src + (nv - 1) * y_smp);
+                for (int i = 0; i < NIY; ++i)
+                    if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp + 16 * (i & 1), y_src + i * y_smp);
+                if (nvy != nv) cp_async8_u32(sb + y_dst + (nv - 1) * y_dsmp + 16 * ((nv - 1) & 1), y_src + (nv - 1) * y_smp);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NIY; ++i)
+                    if (i < nvy) cp_async16_u32(sb + y_dst + i * y_dsmp, y_src + i * y_smp);
+                if (nvy != nv)      // the y_sig + 2 floats of the piece that belong to the tensor
+                    for (int e = 0; e < y_sig + 2; ++e)
+                        cp_async4_u32(sb + y_dst + (nv - 1) * y_dsmp + 4 * e, y_src + (nv - 1) * y_smp + 4 * e);
+                if (y_last_piece && y_sig == 3) {   // the float behind the window (last node of the stage's second row)
+#pragma unroll
+                    for (int i = 0; i < NIY; ++i)
+                        if (i < nv) cp_async4_u32(sb + y_dst + i * y_dsmp + 16, y_src + i * y_smp + 16);
+                }
+            }
         }
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(my_full + slot)) : "memory");
         a_src += a_adv;
         y_src += y_adv;
+        if constexpr (EY == 4) {   // next stage: phase y_sig ^ 2, source re-aligned to its 16-byte boundary
+            y_src -= 4 * ((y_sig ^ 2) - y_sig);
+            y_sig ^= 2;
+        }
     };
     issue_stage(0, 0);
     if (n_stages > 1) issue_stage(1, 1);
@@ -306,18 +361,19 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
 
     // ---- per-lane constants of the consumer
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
-    const double *yb = y + b * y_stride;
-    const double *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
-    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * y_stride + ncol) >> 3) & 1);
+    const TY *yb = y + b * y_stride;
+    const TA *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
+    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * y_stride + ncol) / EY) & (16 / EY - 1));
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
-    const unsigned y_lane = G.y_off + (sl * G.y_pitch + 2 * ((sl >> 1) & 1) + 2 + sig_b + c0) * 8;
-    const unsigned a_lane0 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? 0 : nx * 8);   // pixel row 2 ts
-    const unsigned a_lane1 = (sl * G.a_pitch + c0) * 8 + (G.sy > 0 ? nx * 8 : 0);   // pixel row 2 ts + 1
+    const unsigned y_lane = G.y_off + (sl * G.y_pitch + (EY == 8 ? 2 * ((sl >> 1) & 1) + 2 : 4) + sig_b + c0) * EY;
+    const int y_lane_odd = EY == 4 ? 4 * ((sig_b ^ 2) - sig_b) : 0;   // FP32: odd stages sit at phase sig_b ^ 2
+    const unsigned a_lane0 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? 0 : nx * EA);   // pixel row 2 ts
+    const unsigned a_lane1 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? nx * EA : 0);   // pixel row 2 ts + 1
     const unsigned v_lane = (q * NP * 32 + lane) * 16;                       // inside a V stage
     const unsigned x_lane = G.nstrips * NP * 512 + (q * 4 + k) * 32;
     const int mask_dbl = (G.v_row_bytes - kGrid2MaskBytes) >> 3;          // doubles of a packed row before its masks
     const unsigned m_lane = G.v_row_bytes - kGrid2MaskBytes + 4 * q;
-    const unsigned row_bytes = ncol * 8;
+    const unsigned row_bytes = ncol * EY;
     const double rh = G.rh;
 
     double acc[NT][2], accx = 0.0;
@@ -330,14 +386,14 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
     for (int j = 0; j < 5; ++j) ap[j] = 0.0;
     // node row 0 straight from global memory
     {
-        const double g0 = gp ? __ldg(gp) : 0.0;
+        const double g0 = gp ? (double)__ldg(gp) : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) uc[j] = (c0 + j < ncol) ? __ldg(yb + c0 + j) : 0.0;
-        ulc = is_left ? g0 : __ldg(yb + c0 - 1);
-        urc = (c0 + 4 < ncol) ? __ldg(yb + c0 + 4) : 0.0;
+        for (int j = 0; j < 4; ++j) uc[j] = (c0 + j < ncol) ? (double)__ldg(yb + c0 + j) : 0.0;
+        ulc = is_left ? g0 : (double)__ldg(yb + c0 - 1);
+        urc = (c0 + 4 < ncol) ? (double)__ldg(yb + c0 + 4) : 0.0;
         if (is_right) uc[3] = g0;
     }
-    double gn0 = gp ? __ldg(gp + 2) : 0.0, gn1 = gp ? __ldg(gp + 4) : 0.0;   // Dirichlet values of node rows 1, 2
+    double gn0 = gp ? (double)__ldg(gp + 2) : 0.0, gn1 = gp ? (double)__ldg(gp + 4) : 0.0;   // Dirichlet values of node rows 1, 2
 
     // one node row: new row (un, an) in, residual of the row below (uc between ap and an) out
     auto node_row = [&](const double (&un)[4], double unl, double unr, const double (&an)[5], unsigned v_addr,
@@ -357,10 +413,10 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
         if (is_right) Sv[3] = 0.0;
         if constexpr (RHO) {
             if (b_valid) {
-                double *dst = r + b * (long long)m + (long long)t_out * ncol + c0;
+                TR *dst = r + b * (long long)m + (long long)t_out * ncol + c0;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dst[j] = G.scale * Sv[j];
-                if (!is_right) dst[3] = G.scale * Sv[3];
+                for (int j = 0; j < 3; ++j) dst[j] = (TR)(G.scale * Sv[j]);
+                if (!is_right) dst[3] = (TR)(G.scale * Sv[3]);
             }
         } else {
             if (v_glob) {   // last node row: packed V row from global memory
@@ -423,22 +479,26 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const unsigned ya = sb + y_lane + rr * row_bytes;
+            const unsigned ya = sb + y_lane + rr * row_bytes + (EY == 4 && slot ? y_lane_odd : 0);
             unsigned msk_rr = 0;
             if constexpr (!RHO) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(msk_rr) : "r"(vb + m_lane + rr * G.v_row_bytes));
             double un[4], unl, unr, an[5];
-            unl = lds64(ya - 8);
+            unl = lds_elem<TY>(ya - EY);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) un[j] = lds64(ya + 8 * j);
-            unr = lds64(ya + 32);
+            for (int j = 0; j < 4; ++j) un[j] = lds_elem<TY>(ya + EY * j);
+            unr = lds_elem<TY>(ya + 4 * EY);
             const double gv = rr ? gn1 : gn0;
             if (is_left) unl = gv;
             if (is_right) un[3] = gv;
             const unsigned aa = sb + (rr ? a_lane1 : a_lane0);
-            {
+            if constexpr (EA == 8) {
                 const double2 p0 = lds128(aa), p1 = lds128(aa + 16);
                 an[0] = p0.x; an[1] = p0.y; an[2] = p1.x; an[3] = p1.y;
                 an[4] = lds64(aa + 32);
+            } else {
+                const float4 p0 = lds128f(aa);
+                an[0] = (double)p0.x; an[1] = (double)p0.y; an[2] = (double)p0.z; an[3] = (double)p0.w;
+                an[4] = (double)lds32f(aa + 16);
             }
             if constexpr (ALOG) {
                 int hmax = exp_arg_hi(an[4]);
@@ -449,15 +509,15 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
                 if (hmax > kExpHiMax) {   // |x| > 700, inf or NaN somewhere in the warp's row (rare): libm exp() on the
                                           // values re-read from shared memory, so the common path keeps no copies
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) an[j] = exp(lds64(aa + 8 * j));
+                    for (int j = 0; j < 5; ++j) an[j] = exp(lds_elem<TA>(aa + EA * j));
                 }
             }
             node_row(un, unl, unr, an, vb + v_lane + rr * G.v_row_bytes, vb + x_lane + rr * G.v_row_bytes, msk_rr, nullptr,
                      2 * ts + rr);
         }
         if (gp && ts + 1 < n_stages) {       // Dirichlet values of the next stage's rows 2 ts + 3, 2 ts + 4
-            gn0 = __ldg(gp + 2 * (2 * ts + 3));
-            gn1 = __ldg(gp + 2 * (2 * ts + 4));
+            gn0 = (double)__ldg(gp + 2 * (2 * ts + 3));
+            gn1 = (double)__ldg(gp + 2 * (2 * ts + 4));
         }
         __syncwarp();
         if (lane == 0) {
@@ -484,7 +544,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
         const int pad = m - (int)d;   // zero the K padding [d, m) of this CTA's rows
         for (int idx = tid; idx < S * pad; idx += kThreads) {
             const int si = idx / pad, c = idx - si * pad;
-            if (cta_b0 + si < B) r[(cta_b0 + si) * (long long)m + d + c] = 0.0;
+            if (cta_b0 + si < B) r[(cta_b0 + si) * (long long)m + d + c] = (TR)0;
         }
         return;
     }
@@ -514,7 +574,7 @@ vo_grid2_kernel(Grid2Dev G, const double *__restrict__ a, long long a_stride, in
             const int gi = si >> 3, ss = si & 7;
             double v = 0.0;
             for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * NW + col];
-            r[bs * m + col] = G.scale * v;
+            r[bs * m + col] = (TR)(G.scale * v);
         }
     }
 }

@@ -185,6 +185,9 @@ int gpde_vo_residual_f32(const gpde_vo_plan *plan, const float *a, int64_t a_str
  * 1 when this plan / m has no packed layout (call residual without bit1), < 0 on error. */
 int gpde_vo_pack_weights_f64(const gpde_vo_plan *plan, const double *V, int m, int flags, void *workspace,
                              gpde_stream_t stream);
+/* the same for FP32 I/O calls (gpde_vo_residual_f32 with flags bit1); the packed copy holds doubles either way */
+int gpde_vo_pack_weights_f32(const gpde_vo_plan *plan, const float *V, int m, int flags, void *workspace,
+                             gpde_stream_t stream);
 
 /* Batched Gaussian conditioning of all data points of a virtual-observable ensemble in ONE launch, matrix-free
  * (VirtualObservable.update, bottleneck/VirtualObservables.py:642-669, looped over the data points at :891-898):

@@ -407,6 +407,55 @@ def test_lean_grid_kernel_matches_general_and_generic_kernels(nx, ny, B, dev, mo
     assert torch.isfinite(r_v1).all() and rel_err(r_lean.cpu(), r_v1.cpu()) < 1e-12
 
 
+@pytest.mark.parametrize("nx,ny,B", [(64, 64, 37), (32, 32, 64), (16, 2, 130), (16, 6, 3), (128, 4, 19), (64, 2, 1),
+                                     (32, 8, 129)])
+def test_lean_grid_kernel_fp32_io(nx, ny, B, dev):
+    """FP32 I/O through the lean grid kernel (rows staged as floats, FP64 arithmetic): against the FP64 kernel on the
+    float-rounded inputs, to output rounding.  Every n-tile split of m, ragged batches, y views at all four 4-byte phases
+    of a 16-byte boundary (the last one ending exactly at the end of its allocation: tail copies), shared field /
+    Dirichlet rows, conductivity input, the rho-only output, m > 32, residual_T and packed weights."""
+    from gpde_b200.VirtualObservables import PackedWeights
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 31 + ny, dev, load=False)
+    d = fom.dim_out
+    F = lambda t: torch.tensor(t, device=dev, dtype=torch.float32)
+    D = lambda t: t.double()
+    a32, y32, g32 = F(a), F(y), F(g)
+    assert plan.kernel_path(25, torch.float32) == 2 and plan.kernel_path(40, torch.float32) == 3
+    y_views = [y32]
+    for off in (1, 2, 3):
+        big = torch.zeros(B * d + off, dtype=torch.float32, device=dev)    # the view ends where the allocation ends
+        v = big[off:].view(B, d)
+        v.copy_(y32)
+        y_views.append(v)
+    tol = 2e-6
+    for m in (1, 8, 9, 16, 17, 24, 25, 32):
+        V32 = F(rng.normal(size=(d, m)))
+        r_ref = plan.residual(D(a32), D(y32), D(g32), D(V32)).cpu()
+        for yy in y_views:
+            assert rel_err(plan.residual(a32, yy, g32, V32).double().cpu(), r_ref) < tol, m
+        r_sh = plan.residual(a32[0], y32, g32[0], V32).double().cpu()
+        assert rel_err(r_sh, plan.residual(D(a32[0]), D(y32), D(g32[0]), D(V32)).cpu()) < tol, m
+        ea = torch.exp(D(a32)).float()
+        r_lin = plan.residual(ea, y32, None, V32, a_is_log=False).double().cpu()
+        assert rel_err(r_lin, plan.residual(D(ea), D(y32), None, D(V32), a_is_log=False).cpu()) < tol, m
+    V32 = F(rng.normal(size=(d, 25)))
+    pw = plan.pack_weights(V32, B)
+    assert isinstance(pw, PackedWeights)
+    assert torch.equal(plan.residual(a32, y32, g32, pw), plan.residual(a32, y32, g32, V32))
+    _, rho32 = plan.residual(a32, y32, g32, None)                                   # the fine residual alone
+    _, rho64 = plan.residual(D(a32), D(y32), D(g32), None)
+    _, rho_v1 = plan.variant(GPDE_VO_PATH="v1").residual(D(a32), D(y32), D(g32), None)
+    assert rel_err(rho64.cpu(), rho_v1.cpu()) < 1e-12
+    assert rho32.dtype == torch.float32 and rel_err(rho32.double().cpu(), rho64.cpu()) < tol
+    V40 = F(rng.normal(size=(d, 40)))                                                # rho kernel + FP64 contraction
+    assert rel_err(plan.residual(a32, y32, g32, V40).double().cpu(), plan.residual(D(a32), D(y32), D(g32), D(V40)).cpu()) < tol
+    for m in (5, 16, 25, 32):
+        Vm, sv = F(rng.normal(size=(d, m))), F(rng.normal(size=(B, m)))
+        q32 = plan.residual_T(a32, Vm, sv)
+        assert q32.dtype == torch.float32
+        assert rel_err(q32.double().cpu(), plan.residual_T(D(a32), D(Vm), D(sv)).cpu()) < tol, m
+
+
 def test_packed_weights_give_the_same_residual(dev):
     """gpde_vo_pack_weights_f64 + flags bit1: V packed once, many residual calls; bitwise equal to the call that packs
     V itself; meshes without a packed layout hand the matrix back."""
