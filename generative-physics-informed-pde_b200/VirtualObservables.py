@@ -42,6 +42,7 @@ class VoPlan(object):
         self._lib = _lib.load()
         self.device = _lib.require_cuda(device, "virtual observables")
         self._ctor = (physics, cell_to_input, n_inputs, load)
+        self.cell_to_input = None if cell_to_input is None else np.asarray(cell_to_input)
         mesh = physics.mesh
         if cell_to_input is None:
             cell_to_input, n_inputs = np.arange(mesh.num_cells), mesh.num_cells
@@ -435,7 +436,14 @@ class GaussianSketchingSampler(BaseSampler):
         self.m = N_aux
 
     def _sample(self):
-        return np.stack([np.random.normal(0, 1, self.qp.dim_out) for _ in range(self.m)], axis=1)
+        device = self.qp._device
+        if device is None or torch.device(device).type != "cuda":
+            return np.stack([np.random.normal(0, 1, self.qp.dim_out) for _ in range(self.m)], axis=1)
+        # drawn on the device (resample() runs at every VO update: no host loop, no H2D copy of d x m doubles); the
+        # device generator is seeded from numpy's global stream, so np.random.seed() still fixes the sequence
+        gen = torch.Generator(device=device)
+        gen.manual_seed(int(np.random.randint(0, 2 ** 31 - 1)))
+        return torch.randn(self.qp.dim_out, self.m, generator=gen, dtype=_F64, device=device)
 
 
 class CoarseGrainedResidualSampler(BaseSampler):
@@ -504,20 +512,24 @@ class ConcatenatedSamplers(BaseSampler):
 
 
 class FluxConstrainSampler(BaseSampler):
-    """Wraps a flux-balance constraint object (bottleneck/flux.py:43-158, built with FEniCS facet integrals at
-    setup -- SURVEY.md section 8 row f4, not part of this package): its reduced (Gamma, alpha) are taken as they
-    are, constant, learnable precision (VirtualObservables.py:323-349)."""
+    """Flux-balance constraints of the coarse cells (VirtualObservables.py:323-349): the reduced (Gamma, alpha) of a
+    FluxConstraintReducedOrderModel (gpde_b200/flux.py, the FEniCS-free bottleneck/flux.py:43-158) for this data point,
+    constant, learnable precision.  ``precomputed`` = this data point's (Gamma [N,d], alpha [N]) out of a batched device
+    assembly of the whole ensemble (QuerryEnsemble.FromQuerryPointEnsemble)."""
 
     is_constant = True
     provides_V = False
 
-    def __init__(self, qp, FluxConstrain):
+    def __init__(self, qp, FluxConstrain, precomputed=None):
         super().__init__(qp=qp)
         if not FluxConstrain.initialized:
             raise RuntimeError('Initialize flux-constrain first')
-        self._Gamma_fc, self._alpha_fc = FluxConstrain.assemble_reduced(np.exp(qp.x), qp.bc)
+        if precomputed is not None:
+            self._Gamma_fc, self._alpha_fc = precomputed
+        else:
+            self._Gamma_fc, self._alpha_fc = FluxConstrain.assemble_reduced(np.exp(qp.x), qp.bc)
 
-    m = property(lambda self: int(np.asarray(self._alpha_fc).size))
+    m = property(lambda self: int(self._alpha_fc.numel() if isinstance(self._alpha_fc, torch.Tensor) else np.asarray(self._alpha_fc).size))
     precision_mask = property(lambda self: np.ones(self.m))
 
     def sample(self):
@@ -623,17 +635,28 @@ class QuerryEnsemble(object):
         if W is None:
             raise NotImplementedError('need to provide W (as numpy array)')
         assert isinstance(W, np.ndarray) and W.shape[0] > W.shape[1]
-        if flux:
-            raise NotImplementedError('flux constraints need FEniCS (bottleneck/flux.py)')
         if N_rbf > 0:
             assert l_rbf is not None
         querries = []
         W_dev = _as_f64(W, device)      # ONE device copy of W shared by the samplers of all data points
-        for qp in QuerryPointEnsemble:
+        flux_pairs = None
+        if flux:
+            # test functions of the coarse cells' flux balances (VirtualObservables.py:514-517): the sparse pattern once,
+            # then (Gamma, alpha) of ALL data points in one device product instead of one FEniCS assembly per data point
+            from .flux import FluxConstraintReducedOrderModel
+            fluxconstr = FluxConstraintReducedOrderModel(physics)
+            fluxconstr.create_measures()
+            if torch.device(device).type == "cuda":
+                a_all = torch.exp(_as_f64(np.stack([qp.x for qp in QuerryPointEnsemble]), device))
+                flux_pairs = fluxconstr.assemble_reduced_batched(a_all, QuerryPointEnsemble.dirichlet_values(_F64, device), device)
+        for n_qp, qp in enumerate(QuerryPointEnsemble):
             qp._device = device
             parts = []
             if CGR:
                 parts.append(CoarseGrainedResidualSampler(qp, W_dev))
+            if flux:
+                parts.append(FluxConstrainSampler(qp, fluxconstr, precomputed=None if flux_pairs is None else
+                                                  (flux_pairs[0][n_qp], flux_pairs[1][n_qp])))
             if N_gaussian > 0:
                 parts.append(GaussianSketchingSampler(qp, N_gaussian))
             if N_rbf > 0:

@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libgpde_b200.so")
-SOURCES = ["rom.cu", "vo.cu", "prolong.cu"]
+SOURCES = ["rom.cu", "vo.cu", "prolong.cu", "fom_cg.cu"]
 HEADERS = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))) + \
           [os.path.join(os.path.dirname(HERE), "include", "gpde_b200.h")]
 

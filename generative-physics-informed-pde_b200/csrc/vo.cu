@@ -550,9 +550,9 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
 
 template <typename TV>
 static void grid2_pack(const Grid2Dev &G, const TV *V, int m, int NT, int NX, double *Vp, int n_sm, cudaStream_t st) {
-    const long long total = (long long)(G.ny + 1) * G.v_row_bytes / 8;
-    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)n_sm * 8);
-    vo_grid2_pack_kernel<TV><<<grid, 256, 0, st>>>(G, V, m, NT, NX, Vp);
+    const long long warps = (long long)(G.ny + 1) * 8;   // one warp per (node row, strip slot)
+    const unsigned grid = (unsigned)std::min<long long>((warps + 3) / 4, (long long)n_sm * 16);
+    vo_grid2_pack_kernel<TV><<<grid, 128, 0, st>>>(G, V, m, NT, NX, Vp);
 }
 
 // TA: conductivities, Dirichlet values and V; TY: y; TR: result (r, or the rho rows of the rho variant)

@@ -134,44 +134,43 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const TV *__restrict__ V, int m
     // programmatic dependent launch: the residual kernel may start its prologue (shared-memory setup, first a / y
     // stages) now; it waits for this grid (griddepcontrol.wait) before it touches the packed rows
     asm volatile("griddepcontrol.launch_dependents;");
+    // one warp per (node row t, strip q): it writes the strip's NT tiles (128 doubles each, 4 per lane, all loads
+    // independent), the extra column and -- from the values it has just seen -- the strip's mask word
     const int per_strip = 4 * NT * 32, per_row = G.v_row_bytes / 8, main = G.nstrips * per_strip;
     const int data = main + (NX ? G.nstrips * 16 : 0);     // doubles of a row before the masks
-    const long long total = (long long)(G.ny + 1) * per_row;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i / per_row);
-        int rem = (int)(i - (long long)t * per_row);
-        if (rem >= data) continue;                           // mask words: written below
-        int c, col;
-        if (rem < main) {
-            const int q = rem / per_strip;
-            rem -= q * per_strip;
-            const int h = rem & 1, lane = (rem >> 1) & 31, p = rem >> 6;
-            const int tt = p >> 1, jj = 2 * (p & 1) + h;
-            c = 16 * q + 4 * (lane & 3) + jj;
-            col = 8 * tt + (lane >> 2);
-        } else {
-            rem -= main;
-            c = rem;             // [q][k][j] = column 16 q + 4 k + j
-            col = 8 * NT;
-        }
-        Vp[i] = (c < G.ncol && col < m && (NX || col < 8 * NT)) ? (double)V[((long long)t * G.ncol + c) * m + col] : 0.0;
-    }
-    // masks: one warp per (node row, strip)
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const int mcols = min(m, 8 * NT + (NX ? 1 : 0));
     for (long long w = warp; w < (long long)(G.ny + 1) * 8; w += nwarps) {
         const int t = (int)(w >> 3), q = (int)(w & 7);
+        double *row = Vp + (long long)t * per_row;
         unsigned bits = 0;
         if (q < G.nstrips) {
-            for (int i = lane; i < 16 * mcols; i += 32) {
-                const int c = 16 * q + i / mcols, col = i % mcols;
-                if (c < G.ncol && V[((long long)t * G.ncol + c) * m + col] != (TV)0) bits |= col < 8 * NT ? 1u << (col >> 3) : 0x80u;
+            const TV *Vt = V + (long long)t * G.ncol * m;
+            for (int tt = 0; tt < NT; ++tt) {
+                double v[4];
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    const int e = it * 32 + lane;                       // [half ph][lane ln][h]
+                    const int h = e & 1, ln = (e >> 1) & 31, ph = e >> 6;
+                    const int c = 16 * q + 4 * (ln & 3) + 2 * ph + h, col = 8 * tt + (ln >> 2);
+                    v[it] = (c < G.ncol && col < m) ? (double)Vt[(long long)c * m + col] : 0.0;
+                }
+                bool nz = false;
+#pragma unroll
+                for (int it = 0; it < 4; ++it) {
+                    row[q * per_strip + tt * 128 + it * 32 + lane] = v[it];
+                    nz |= v[it] != 0.0;
+                }
+                if (__any_sync(0xffffffffu, nz)) bits |= 1u << tt;
+            }
+            if (NX) {
+                const int c = 16 * q + lane, col = 8 * NT;               // [k][j] = column 16 q + 4 k + j: lanes 0..15
+                const double v = (lane < 16 && c < G.ncol && col < m) ? (double)Vt[(long long)c * m + col] : 0.0;
+                if (lane < 16) row[main + q * 16 + lane] = v;
+                if (__any_sync(0xffffffffu, v != 0.0)) bits |= 0x80u;
             }
         }
-        bits = __reduce_or_sync(0xffffffffu, bits);
-        if (lane == 0) reinterpret_cast<unsigned *>(Vp + (long long)t * per_row + data)[q] = bits;
+        if (lane == 0) reinterpret_cast<unsigned *>(row + data)[q] = bits;
     }
 }
 

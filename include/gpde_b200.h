@@ -219,6 +219,21 @@ int gpde_vo_residual_T_f32(const gpde_vo_plan *plan, const float *a, int64_t a_s
                            const float *V, int m, const float *s, float *q, void *workspace,
                            int64_t B, gpde_stream_t stream);
 
+/* ---- fine-mesh label solves: batched preconditioned CG (setup-time replacement of the per-sample FEniCS / spsolve calls
+ * of physics/LinearElliptic.py:85-101, 120-133 in utils/data.py:96-99).  One iteration = one gpde_vo_residual_f64 call with
+ * y = p (rho output, flags bit0, no Dirichlet data: rho = K_ff(a) p for the whole batch) + one gpde_cg_step_f64 call.
+ * All arrays device, float64: rhs, Ax, x, r, p [B,d]; dinv [B or 1, d] (dinv_stride = d or 0) the inverse diagonal of
+ * K_ff(a_b); rz, stop2, rnorm2 [B] per-sample scalars owned by the caller.
+ *   init: r = rhs - Ax (Ax = NULL: x0 = 0), p = dinv r, rz = r.p, rnorm2 = r.r, stop2 = tol^2 rhs.rhs
+ *   step: alpha = rz / p.Ap; x += alpha p; r -= alpha Ap; z = dinv r; beta = r.z / rz; p = z + beta p; rz, rnorm2 updated;
+ *         samples with rnorm2 <= stop2 are frozen. */
+int gpde_cg_init_f64(const double *rhs, const double *Ax, const double *dinv, int64_t dinv_stride, double *r,
+                     double *p, double *rz, double *stop2, double *rnorm2, double tol, int d, int64_t B,
+                     int device, gpde_stream_t stream);
+int gpde_cg_step_f64(const double *Ap, const double *dinv, int64_t dinv_stride, double *x, double *r, double *p,
+                     double *rz, const double *stop2, double *rnorm2, int d, int64_t B, int device,
+                     gpde_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

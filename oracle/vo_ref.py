@@ -80,21 +80,6 @@ def update_vo_precision_beta(Gammas, alphas, means, varss, beta_0=1e-6):
     return 0.5 * beta + beta_0
 
 
-def energy_vo_update(K, f, prec, g, mean0, Vs, temperature=1.0):
-    """EnergyVirtualObservable.update (VirtualObservables.py:769-788): subspace Newton steps on
-    A = diag(prec) + K/T, b = f/T + prec*g with the supplied weighting matrices Vs (one per
-    iteration).  Returns (mean, vars)."""
-    invT = 1.0 / temperature
-    vars_ = 1 / (prec + invT * K.diagonal())
-    A = np.diag(prec) + invT * K
-    b = invT * f + prec * g
-    mean = mean0.copy()
-    for V in Vs:
-        Mm = np.array(V.T @ A @ V)
-        mean = mean - V @ np.linalg.solve(Mm, V.T @ np.array(A @ mean - b).flatten())
-    return mean, vars_
-
-
 class CsrAssembler(object):
     """Vectorised restatement of ``assemble_system`` for timing the CPU route fairly: the sparsity
     pattern of K_ff / K_fc is fixed by the mesh, so K.data = S @ a with a precomputed sparse S

@@ -158,8 +158,9 @@ def test_reference_style_construction_and_samplers(dev):
     for n in range(N):
         res = qe[n].Gamma @ ens.mean[n] - qe[n].alpha
         assert res.abs().max() < 1e-8
-    with pytest.raises(NotImplementedError):
-        VO.QuerryEnsemble.FromQuerryPointEnsemble(qpe, ph, True, True, 0, 0, dtype=torch.double, device=dev)
+    # flux constraints (VirtualObservables.py:514-527): one learnable-precision row per coarse cell after the CGR block
+    qe_flux = VO.QuerryEnsemble.FromQuerryPointEnsemble(qpe, ph, True, True, 0, 0, dtype=torch.double, device=dev)
+    assert qe_flux[0].m == ph['W'].shape[1] + ph['rom'].mesh.num_cells and qe_flux[0].V is None
 
 
 def test_pixel_input_plan_matches_cell_input_plan(dev):
@@ -632,3 +633,31 @@ def test_rbf_sampler_on_device_matches_host_evaluation(dev):
     assert isinstance(Vc, torch.Tensor) and Vc.shape == (ph['fom'].dim_out, 5) and cat.m == 5
     Gam, alp = cat.sample()
     assert Gam.shape == (5, ph['fom'].dim_out) and alp.shape == (5,)
+
+
+def test_gaussian_sketch_on_device(dev):
+    """GaussianSketchingSampler (VirtualObservables.py:230-258): query points on a CUDA device draw the i.i.d. N(0,1)
+    weighting vectors on the device; np.random.seed() still fixes the sequence; host query points keep the reference's
+    numpy stream draw for draw."""
+    from gpde_b200 import VirtualObservables as VO
+    g = load_golden("vo_2x2_8_nd")
+    ph, bce = _setup(g, dev)
+    qp_dev = VO.QuerryPoint(ph['fom'], g['in_X_DG'][0], bce[0], device=dev)
+    qp_host = VO.QuerryPoint(ph['fom'], g['in_X_DG'][0], bce[0])
+    d = ph['fom'].dim_out
+    np.random.seed(5)
+    V1 = VO.GaussianSketchingSampler(qp_dev, 64).sample_V()
+    V1b = VO.GaussianSketchingSampler(qp_dev, 64).sample_V()
+    np.random.seed(5)
+    V2 = VO.GaussianSketchingSampler(qp_dev, 64).sample_V()
+    assert isinstance(V1, torch.Tensor) and V1.is_cuda and V1.dtype == torch.double and V1.shape == (d, 64)
+    assert torch.equal(V1, V2) and not torch.equal(V1, V1b)
+    assert abs(float(V1.mean())) < 0.1 and abs(float(V1.std()) - 1.0) < 0.1
+    np.random.seed(5)
+    Vh = VO.GaussianSketchingSampler(qp_host, 3).sample_V()
+    np.random.seed(5)
+    ref = np.stack([np.random.normal(0, 1, d) for _ in range(3)], axis=1)      # the reference's loop, :243-246
+    assert isinstance(Vh, np.ndarray) and np.array_equal(Vh, ref)
+    s = VO.GaussianSketchingSampler(qp_dev, 4)
+    Gam, alp = s.sample()
+    assert Gam.shape == (4, d) and alp.shape == (4,) and s.fixed_precision
