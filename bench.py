@@ -440,12 +440,97 @@ def sub_record(torch, dist, dev, name, B_total, tdt, K, rank, world, peak, peak_
     return rec
 
 
+def svi_record(torch, dist, dev, K, rank, world, peak_unused=None):
+    """BASELINE config 5: the semi-supervised SVI ELBO step around the physics layer, data-parallel over the ranks
+    (owner-sharded per-sample tables, ONE flat NCCL all-reduce of the shared gradients), FP32 modules (the reference's model
+    dtype).  Every rank owns N_s = 128 supervised + N_vo = 128 virtual-observable data points and an unsupervised batch of
+    64 (weak scaling).  Times the eager step, the CUDA-graph replay of the whole step, the all-reduce alone and the batched
+    virtual-observable update; max over ranks."""
+    from gpde_b200 import svi
+    from gpde_b200.svi_workload import SviWorkload
+    wl = SviWorkload(dev, torch.float32, seed=100 + rank)
+    wl.build_virtual_observables()
+    wl.update_virtual_observables(N_mc=64, step=0)
+    dp = svi.DataParallelSVI(wl.shared_parameters(), wl.local_parameters(), wl.elbo, lr=1e-3, capturable=True)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    for _ in range(3):
+        dp.step()
+    t_eager = timed(dp.step, K)
+    t_ar = timed(dp.bucket.allreduce_, K) if world > 1 else 0.0
+    t_vo = timed(lambda: wl.update_virtual_observables(N_mc=64, step=1), max(2, K // 4))
+    mode = "cuda_graph"
+    try:
+        gs = svi.GraphedStep(dp)
+        t_graph = timed(gs.replay, K)
+    except Exception as exc:   # noqa: BLE001
+        sys.stderr.write("bench: cfg5 graph capture failed (%s)\n" % (exc,))
+        t_graph, mode = t_eager, "eager"
+    wl.g.rom.check()
+    elbo = float(dp.global_elbo().item())
+    if world > 1:
+        tt = torch.tensor([t_eager, t_graph, t_ar, t_vo], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_eager, t_graph, t_ar, t_vo = (float(x) for x in tt.tolist())
+    return {"workload": "cfg5", "desc": "semi-supervised SVI ELBO step (stand-in CNN encoder / decoder + ROM + VO term), data-parallel, "
+                                        "one flat NCCL all-reduce of the shared gradients", "dtype": "f32", "scaling": "weak",
+            "per_gpu": {"N_supervised": wl.N_s, "N_vo": wl.N_vo, "bs_unsupervised": wl.bs_u}, "n_gpus": world,
+            "value": world * wl.samples_per_step() / (t_graph * 1e-3), "unit": "data points/s through the SVI step",
+            "ms_per_step": t_graph, "launch_mode": mode, "ms_per_step_eager": t_eager, "steps": K,
+            "cgm_solves_per_s": world * wl.cgm_solves_per_step() / (t_graph * 1e-3),
+            "shared_parameters": dp.bucket.numel, "allreduce_bytes": dp.bucket.nbytes, "ms_allreduce_alone": t_ar,
+            "ms_vo_update_N_mc64": t_vo, "fused_log_likelihood": wl.fused, "elbo_sum_over_ranks": elbo,
+            "batchnorm": "none in the stand-in CNNs", "data": "synthetic, random-init weights"}
+
+
+def run_cfg5(args):
+    import torch
+    import torch.distributed as dist
+    import gpde_b200  # noqa: F401
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", "0"), ("WORLD_SIZE", "1"), ("LOCAL_RANK", "0")))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t0 = time.perf_counter()
+    rec = svi_record(torch, dist, dev, args.steps, rank, world)
+    t1 = time.perf_counter()
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        line = {"metric": METRIC, "value": rec["value"], "unit": rec["unit"], "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg5", "desc": rec["desc"]},
+                "components": rec, "gpu_launches": None, "clocks": sampler.summary(t0, t1) if sampler else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_b200(args):
     import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
     import gpde_b200  # noqa: F401
     from gpde_b200.workloads import Workload
+    if args.workload == "cfg5":
+        return run_cfg5(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -609,6 +694,7 @@ def run_b200(args):
             subs["cfg4_strong_b131072"] = sub_record(torch, dist, dev, "cfg4", 131072, torch.float64, Ks, rank, world, peak, peak_src, True)
             subs["cfg3_b16384"] = sub_record(torch, dist, dev, "cfg3", 16384, torch.float64, max(3, Ks // 2), rank, world, peak, peak_src, False)
             subs["cfg2_f32"] = sub_record(torch, dist, dev, "cfg2", 4096, torch.float32, Ks, rank, world, peak, peak_src, False)
+            subs["cfg5_svi_step"] = svi_record(torch, dist, dev, max(10, Ks), rank, world)
         except Exception as exc:   # noqa: BLE001 -- the headline record must survive a failing secondary record
             subs["error"] = "%s: %s" % (type(exc).__name__, exc)
     if sampler:
