@@ -36,6 +36,13 @@ class _RomPlan(object):
         _lib.check(lib.gpde_rom_plan_info(handle, info), "gpde_rom_plan_info")
         self.n, self.E, self.n_free, self.half_bandwidth, self.factor_doubles, self.n_contrib, self.lanes = \
             [int(v) for v in info[:7]]
+        # lanes == 2: windowed thread-per-sample kernels -- the forward call itself streams the factor through the stash
+        self.factor_required = self.lanes == 2
+
+    def factor_buffer(self, B, device):
+        """Opaque factor stash of a batch of B samples (layout is the kernels' business), or None when the plan keeps none."""
+        nbytes = int(self._lib.gpde_rom_factor_bytes(self.handle, int(B)))
+        return torch.empty(nbytes // 8, dtype=torch.float64, device=device) if nbytes else None
 
     def __del__(self):
         try:
@@ -50,7 +57,7 @@ def _launch_forward(plan, X, F, x_is_log, want_factor=True, info=None):
     lib, B = plan._lib, X.shape[0]
     sfx = _lib.suffix(X.dtype)
     u = torch.empty((B, plan.n), dtype=X.dtype, device=X.device)
-    factor = torch.empty((B, plan.factor_doubles), dtype=torch.float64, device=X.device) if want_factor else None
+    factor = plan.factor_buffer(B, X.device) if (want_factor or plan.factor_required) else None
     fn = getattr(lib, "gpde_rom_forward_" + sfx)
     dev = plan.device
     rc = fn(plan.handle, _lib.ptr(X, dev), int(bool(x_is_log)), _lib.ptr(F, dev), _lib.ptr(u, dev), _lib.ptr(factor, dev),

@@ -65,12 +65,16 @@ __device__ __forceinline__ double fast_rcp(double d) {
 }  // namespace gpde
 
 #include "rom_tps.cuh"
+#include "rom_tpw.cuh"
 
 struct gpde_rom_plan {
     gpde::RomDev dev;
     int device;
     int tps;                // 1: the thread-per-sample kernels (rom_tps.cuh) serve this plan (no factor stash)
     gpde::TpsAdjTab<gpde::TpsShape4x4> tps_tab;   // their tables, passed by value with every launch
+    int tpw;                // 1: the windowed thread-per-sample kernels (rom_tpw.cuh); the factor stash is sample-interleaved
+    gpde::TpwFwdTab<gpde::TpwShape8x8> tpw_fwd;
+    gpde::TpwAdjTab<gpde::TpwShape8x8> tpw_adj;
     int lanes;              // G
     int n_contrib;
     size_t smem_fwd, smem_adj;  // bytes per sample
@@ -416,6 +420,74 @@ static bool build_tps_tables(int n, int E, int nf, int hbw, const std::vector<in
     return true;
 }
 
+// Tables of the windowed thread-per-sample kernels (rom_tpw.cuh) for shape S; false if M does not fit: sizes, bandwidth,
+// more terms per entry than the shape provides, or a structural non-zero inside the band other than s = 1 and s = HBW.
+template <class S>
+static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<int> &free_dof, const std::vector<int> &bc_dof,
+                             const std::vector<unsigned char> &is_bc, const double *M, TpwFwdTab<S> &Ft, TpwAdjTab<S> &At) {
+    if (n != S::N || E != S::E || nf != S::NF || hbw != S::HBW) return false;
+    static_assert(S::E * kTpwPitch < 65536 && S::N * kTpwPitch < 65536, "column offsets are 16-bit");
+    auto Mat = [&](int i, int j, int e) { return M[((size_t)i * n + j) * E + e]; };
+    memset(&Ft, 0, sizeof(Ft));
+    memset(&At, 0, sizeof(At));
+    for (int i = 0; i < nf; ++i) {
+        Ft.free_dof[i] = At.free_dof[i] = (unsigned short)(free_dof[i] * kTpwPitch);
+        int cnt = 0;
+        for (int e = 0; e < E; ++e) {
+            const double v = Mat(free_dof[i], free_dof[i], e);
+            if (v == 0.0) continue;
+            if (cnt == S::TD) return false;
+            Ft.diag_coef[i * S::TD + cnt] = v;
+            Ft.diag_elem[i * S::TD + cnt] = (unsigned short)(e * kTpwPitch);
+            ++cnt;
+        }
+        for (int s = 1; s <= hbw && s <= i; ++s) {
+            cnt = 0;
+            for (int e = 0; e < E; ++e) {
+                const double v = Mat(free_dof[i], free_dof[i - s], e);
+                if (v == 0.0) continue;
+                if (s != 1 && s != hbw) return false;       // not the 5-point structure
+                if (cnt == S::TO) return false;
+                double *coef = s == 1 ? Ft.s1_coef : Ft.sh_coef;
+                unsigned short *elem = s == 1 ? Ft.s1_elem : Ft.sh_elem;
+                coef[i * S::TO + cnt] = v;
+                elem[i * S::TO + cnt] = (unsigned short)(e * kTpwPitch);
+                ++cnt;
+            }
+        }
+        cnt = 0;
+        for (size_t c = 0; c < bc_dof.size(); ++c)
+            for (int e = 0; e < E; ++e) {
+                const double v = Mat(free_dof[i], bc_dof[c], e);
+                if (v == 0.0) continue;
+                if (cnt == S::TR) return false;
+                const int k = i * S::TR + cnt;
+                Ft.rhs_coef[k] = At.rhs_coef[k] = v;
+                Ft.rhs_elem[k] = (unsigned short)(e * kTpwPitch);
+                At.rhs_elem[k] = (unsigned short)e;
+                Ft.rhs_dof[k] = At.rhs_dof[k] = (unsigned short)(bc_dof[c] * kTpwPitch);
+                ++cnt;
+            }
+    }
+    for (int e = 0; e < E; ++e) {
+        int cnt = 0;
+        for (int i = 0; i < n; ++i) {
+            if (is_bc[i]) continue;   // overwritten rows contribute nothing
+            for (int j = 0; j < n; ++j) {
+                const double v = Mat(i, j, e);
+                if (v == 0.0) continue;
+                if (cnt == S::TG) return false;
+                const int k = e * S::TG + cnt;
+                At.grad_coef[k] = v;
+                At.grad_i[k] = (unsigned short)(i * kTpwPitch);
+                At.grad_j[k] = (unsigned short)(j * kTpwPitch);
+                ++cnt;
+            }
+        }
+    }
+    return true;
+}
+
 template <typename T>
 static int track(gpde_rom_plan *pl, const T **dst, const std::vector<T> &src) {
     T *p = nullptr;
@@ -470,6 +542,16 @@ static int rom_forward(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
     }
+    if (pl->tpw && factor) {   // thread per sample, band streamed through a register window: the kernel itself streams the
+                               // factor through the stash (without one the cooperative kernels below serve the call)
+        using S = TpwShape8x8;
+        auto kern = rom_tpw_forward_kernel<T, S>;
+        constexpr size_t smem = tpw_smem_forward<S>();
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)((B + kTpwThreads - 1) / kTpwThreads), kTpwThreads, smem, st>>>(pl->tpw_fwd, X, x_is_log, F, u, factor, info, B);
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
     switch (pl->lanes) {
         case 8: return launch_forward<T, 8>(pl, X, x_is_log, F, u, factor, info, B, st);
         case 16: return launch_forward<T, 16>(pl, X, x_is_log, F, u, factor, info, B, st);
@@ -498,6 +580,22 @@ static int rom_adjoint(const gpde_rom_plan *pl, const T *X, int x_is_log, const 
             constexpr size_t smem = tps_smem_adjoint<S>(false);
             GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<grid, kTpsThreads, smem, st>>>(pl->tps_tab, X, x_is_log, u, gbar, gradX, gradF, B);
+        }
+        GPDE_CUDA_OK(cudaGetLastError());
+        return GPDE_OK;
+    }
+    if (pl->tpw && factor) {   // (no stash: the cooperative adjoint below re-factorises)
+        using S = TpwShape8x8;
+        const unsigned grid = (unsigned)((B + kTpwThreads - 1) / kTpwThreads);
+        constexpr size_t smem = tpw_smem_adjoint<S>();
+        if (gradF) {
+            auto kern = rom_tpw_adjoint_kernel<T, S, true>;
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kTpwThreads, smem, st>>>(pl->tpw_adj, X, x_is_log, u, factor, gbar, gradX, gradF, B);
+        } else {
+            auto kern = rom_tpw_adjoint_kernel<T, S, false>;
+            GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, kTpwThreads, smem, st>>>(pl->tpw_adj, X, x_is_log, u, factor, gbar, gradX, gradF, B);
         }
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
@@ -689,6 +787,8 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
         const char *e = getenv("GPDE_ROM_PATH");
         const bool want = !(e && strcmp(e, "coop") == 0);
         pl->tps = (want && build_tps_tables<TpsShape4x4>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, pl->tps_tab)) ? 1 : 0;
+        pl->tpw = (want && !pl->tps &&
+                   build_tpw_tables<TpwShape8x8>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, pl->tpw_fwd, pl->tpw_adj)) ? 1 : 0;
     }
     // per-sample scratch of the cooperative kernels; with 8 lanes per sample a 64-bit shared-memory wavefront serves two
     // samples, so the pitch is padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint
@@ -721,12 +821,18 @@ int gpde_rom_plan_destroy(gpde_rom_plan *pl) {
 int gpde_rom_plan_info(const gpde_rom_plan *pl, int64_t out[8]) {
     if (!pl || !out) return fail(GPDE_ERR_ARG, "rom_plan_info: null");
     out[0] = pl->dev.n; out[1] = pl->dev.E; out[2] = pl->dev.n_free; out[3] = pl->dev.hbw;
-    out[4] = pl->tps ? 0 : pl->dev.n_band; out[5] = pl->n_contrib; out[6] = pl->tps ? 1 : pl->lanes; out[7] = pl->device;
+    // [4] doubles of factor stash per sample (0: none; windowed kernels: per sample of a 128-sample block -- size the buffer
+    // with gpde_rom_factor_bytes); [6] lanes per sample: 1 = thread per sample (no stash), 2 = windowed thread per sample
+    // (the forward call itself needs the stash), 8/16/32 = cooperative kernels
+    out[4] = pl->tps ? 0 : (pl->tpw ? TpwShape8x8::NF * TpwShape8x8::W : pl->dev.n_band);
+    out[5] = pl->n_contrib; out[6] = pl->tps ? 1 : (pl->tpw ? 2 : pl->lanes); out[7] = pl->device;
     return GPDE_OK;
 }
 
 size_t gpde_rom_factor_bytes(const gpde_rom_plan *pl, int64_t B) {
     if (!pl || B < 0 || pl->tps) return 0;   // the thread-per-sample kernels keep no stash
+    if (pl->tpw)                              // sample-interleaved blocks of 128 samples
+        return sizeof(double) * tpw_stash_doubles_per_block<TpwShape8x8>() * (size_t)((B + kTpwThreads - 1) / kTpwThreads);
     return sizeof(double) * (size_t)pl->dev.n_band * (size_t)B;
 }
 

@@ -1,0 +1,354 @@
+// Coarse-grained model, one THREAD per sample with a SLIDING REGISTER WINDOW over the band.  Included by rom.cu.
+//
+// For coarse meshes whose banded LDL^T no longer fits the registers of one thread (the reference's 8x8 mesh of BASELINE
+// config 3: 63 free dofs, half bandwidth 7 -> 504 band entries), the thread-per-sample idea of rom_tps.cuh is kept and the
+// band is streamed through a window: at pivot k only rows k .. k+HBW of the band are live, W = HBW + 1 rows of W entries.
+//   * the window R[row mod W][s] = A[row][row - s] lives in registers; the pivot loop is rolled over blocks of W pivots and
+//     unrolled inside a block, so every register index is a compile-time constant and a row's slot is reused W pivots later;
+//   * row k + HBW is assembled from the sample's conductivity column (shared memory) just before pivot k touches it: the
+//     5-point structure of K_ff on the reference's meshes (the hypotenuse of a right triangle does not couple) leaves three
+//     structural entries per row -- diagonal, s = 1 and s = HBW -- everything in between is fill-in that starts at zero;
+//   * the forward substitution rides along in a window of W right-hand-side values; finished values go to the sample's
+//     column of F in shared memory (their slots are dead by then);
+//   * column k of the factor (1/d_k and the HBW unscaled entries below it) leaves the registers for the factor stash as soon
+//     as pivot k is done.  The stash is sample-interleaved ([block of 128 samples][pivot][entry][sample]): every store and
+//     every later load of a warp is 256 contiguous bytes.  The back substitution of the same kernel and both substitutions
+//     of the adjoint kernel stream it back (L2-resident within the kernel: 516 KB per CTA);
+//   * rows past the end of the matrix are phantom rows of zeros (tables padded with zero coefficients), pivots past the end
+//     are skipped by a uniform predicate: no per-entry bounds in the inner loops.
+// The cooperative kernels of rom.cu spent ~1000 warp-instructions per sample on table walks, a __syncwarp per pivot and
+// shared-memory round trips of the band (0.32 + 0.25 ms for 16384 samples of the 8x8 mesh); here a sample costs ~90
+// instructions per pivot of straight-line FP64 code.  Same maths: bottleneck/ROM.py:59-100 and its autograd.
+#pragma once
+#include <utility>
+
+#include "exp256.cuh"
+
+namespace gpde {
+
+constexpr int kTpwThreads = 128;
+constexpr int kTpwPitch = kTpwThreads + 1;   // doubles between consecutive rows of a per-thread column array
+constexpr int kTpwGradChunk = 32;            // gradient entries per round of the adjoint's output staging
+
+template <int NF_, int HBW_, int E_, int N_, int TO_, int TD_, int TR_, int TG_>
+struct TpwShape {
+    static constexpr int NF = NF_, HBW = HBW_, E = E_, N = N_, TO = TO_, TD = TD_, TR = TR_, TG = TG_;
+    static constexpr int W = HBW_ + 1;                 // window rows = entries per row
+    static constexpr int NB = (NF_ + W - 1) / W;       // blocks of W pivots
+    static constexpr int NFP = NB * W + HBW_;          // table rows incl. phantom rows
+    static_assert(HBW_ >= 2, "s = 1 and s = HBW must be different slots");
+};
+using TpwShape8x8 = TpwShape<63, 7, 128, 81, 2, 6, 2, 7>;
+
+// element / dof entries are column offsets (index * kTpwPitch); padding terms have coefficient 0 and offset 0
+template <class S>
+struct TpwFwdTab {
+    double diag_coef[S::NFP * S::TD];
+    double s1_coef[S::NFP * S::TO];     // A[i][i-1]
+    double sh_coef[S::NFP * S::TO];     // A[i][i-HBW]
+    double rhs_coef[S::NFP * S::TR];    // z_i = F[free_i] - sum_t rhs_coef * x[rhs_elem] * F[rhs_dof]
+    unsigned short diag_elem[S::NFP * S::TD], s1_elem[S::NFP * S::TO], sh_elem[S::NFP * S::TO];
+    unsigned short rhs_elem[S::NFP * S::TR], rhs_dof[S::NFP * S::TR];
+    unsigned short free_dof[S::NFP];
+};
+template <class S>
+struct TpwAdjTab {
+    double grad_coef[S::E * S::TG];                              // dL/dx_e = -sum_t grad_coef * lam[grad_i] * u[grad_j]
+    double rhs_coef[S::NF * S::TR];                              // couplings K_fc (gradient w.r.t. F only)
+    unsigned short grad_i[S::E * S::TG], grad_j[S::E * S::TG];   // dof columns (grad_i is a free dof)
+    unsigned short rhs_elem[S::NF * S::TR];                      // element INDEX (x is read from global memory there)
+    unsigned short rhs_dof[S::NF * S::TR];                       // dof column
+    unsigned short free_dof[S::NFP];
+};
+
+template <class S>
+__host__ __device__ constexpr size_t tpw_stash_doubles_per_block() {
+    return (size_t)S::NF * S::W * kTpwThreads;
+}
+
+// Rows [b0, b0+rows) x [0, WD) of a row-major [B, WD] array into per-thread columns col[j * pitch + row], CH coalesced
+// loads in flight per thread; rows past the batch get ``fill``.
+template <typename T, int WD, int CH>
+__device__ __forceinline__ void tpw_stage_in(const T *__restrict__ src, long long b0, int rows, double fill, double *col) {
+    const T *p = src + b0 * WD;
+    const int limit = rows * WD;
+#pragma unroll 1
+    for (int k0 = 0; k0 < WD; k0 += CH) {
+        T raw[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int i = threadIdx.x + (k0 + c) * kTpwThreads;
+            raw[c] = (k0 + c < WD && i < limit) ? p[i] : (T)fill;
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            if (k0 + c < WD) {
+                const int i = threadIdx.x + (k0 + c) * kTpwThreads;
+                const int row = i / WD, j = i - row * WD;
+                col[j * kTpwPitch + row] = (double)raw[c];
+            }
+        }
+    }
+}
+
+template <typename T, int WD>
+__device__ __forceinline__ void tpw_stage_out(T *__restrict__ dst, long long b0, int rows, const double *col) {
+    T *p = dst + b0 * WD;
+    const int limit = rows * WD;
+#pragma unroll 2
+    for (int i = threadIdx.x; i < limit; i += kTpwThreads) {
+        const int row = i / WD, j = i - row * WD;
+        p[i] = (T)col[j * kTpwPitch + row];
+    }
+}
+
+// x = exp(v) + 1e-8 in place (components.py:298) for this thread's column; GPDE_INFO_NONPOSITIVE_X if some x <= 1e-12
+template <int E>
+__device__ __forceinline__ int tpw_conductivities(double *x, int x_is_log, unsigned etab) {
+    int bad = 0;
+#pragma unroll 2
+    for (int e = 0; e < E; ++e) {
+        double v = x[e * kTpwPitch];
+        if (x_is_log) {
+            v = (exp256_in_range(v) ? exp_tab256c(v, etab) : exp(v)) + 1e-8;
+            x[e * kTpwPitch] = v;
+        }
+        if (!(v > 1e-12)) bad = GPDE_INFO_NONPOSITIVE_X;
+    }
+    return bad;
+}
+
+// Row r of K_ff(x) into window slot SLOT (entries s = 0 .. HBW) and its right-hand side into zw[SLOT]
+template <class S, int SLOT>
+__device__ __forceinline__ void tpw_enter_row(const TpwFwdTab<S> &tab, int r, const double *x, const double *f,
+                                              double (&R)[S::W][S::W], double (&zw)[S::W]) {
+    double d = 0.0, o1 = 0.0, oh = 0.0;
+#pragma unroll
+    for (int t = 0; t < S::TD; ++t) d = fma(tab.diag_coef[r * S::TD + t], x[tab.diag_elem[r * S::TD + t]], d);
+#pragma unroll
+    for (int t = 0; t < S::TO; ++t) {
+        o1 = fma(tab.s1_coef[r * S::TO + t], x[tab.s1_elem[r * S::TO + t]], o1);
+        oh = fma(tab.sh_coef[r * S::TO + t], x[tab.sh_elem[r * S::TO + t]], oh);
+    }
+    R[SLOT][0] = d;
+    R[SLOT][1] = o1;
+#pragma unroll
+    for (int s = 2; s < S::HBW; ++s) R[SLOT][s] = 0.0;
+    R[SLOT][S::HBW] = oh;
+    double acc = f[tab.free_dof[r]];
+#pragma unroll
+    for (int t = 0; t < S::TR; ++t) {
+        const int k = r * S::TR + t;
+        acc = fma(-tab.rhs_coef[k] * x[tab.rhs_elem[k]], f[tab.rhs_dof[k]], acc);
+    }
+    zw[SLOT] = acc;
+}
+
+// rows 0 .. HBW-1 of the window (row k + HBW enters at pivot k)
+template <class S, int... Js>
+__device__ __forceinline__ void tpw_prologue(std::integer_sequence<int, Js...>, const TpwFwdTab<S> &tab, const double *x,
+                                             const double *f, double (&R)[S::W][S::W], double (&zw)[S::W]) {
+    (tpw_enter_row<S, Js>(tab, Js, x, f, R, zw), ...);
+}
+
+// Pivot k = kb * W + J: bring in row k + HBW, eliminate column k from the window, advance the forward substitution,
+// flush column k of the factor to the stash.  J (= k mod W) fixes every register index at compile time.
+template <class S, int J>
+__device__ __forceinline__ void tpw_pivot(const TpwFwdTab<S> &tab, int kb, const double *x, double *f, double (&R)[S::W][S::W],
+                                          double (&zw)[S::W], double *__restrict__ st, int &bad) {
+    constexpr int W = S::W, HBW = S::HBW;
+    const int k = kb * W + J;
+    tpw_enter_row<S, (J + HBW) % W>(tab, k + HBW, x, f, R, zw);
+    if (k < S::NF) {
+        const double d = R[J][0];
+        if (!(d > 0.0)) bad |= GPDE_INFO_NOT_SPD;
+        const double invd = fast_rcp(d);
+        double *col = st + (size_t)k * W * kTpwThreads;
+        col[0] = invd;
+#pragma unroll
+        for (int si = 1; si <= HBW; ++si) {
+            const double c = R[(J + si) % W][si];
+            col[si * kTpwThreads] = c;
+            const double l = c * invd;
+#pragma unroll
+            for (int sj = 1; sj <= si; ++sj)
+                R[(J + si) % W][si - sj] = fma(-l, R[(J + sj) % W][sj], R[(J + si) % W][si - sj]);
+        }
+        const double wk = zw[J] * invd;
+#pragma unroll
+        for (int s = 1; s <= HBW; ++s) zw[(J + s) % W] = fma(-R[(J + s) % W][s], wk, zw[(J + s) % W]);
+        f[tab.free_dof[k]] = wk;
+    }
+}
+template <class S, int... Js>
+__device__ __forceinline__ void tpw_pivot_block(std::integer_sequence<int, Js...>, const TpwFwdTab<S> &tab, int kb, const double *x,
+                                                double *f, double (&R)[S::W][S::W], double (&zw)[S::W], double *__restrict__ st,
+                                                int &bad) {
+    (tpw_pivot<S, Js>(tab, kb, x, f, R, zw, st, bad), ...);
+}
+
+// L^T sol = w with the stashed factor; w and then sol live in column ``v`` at the free dofs
+template <class S>
+__device__ __forceinline__ void tpw_backward_subst(const double *__restrict__ st, const unsigned short *free_dof, double *v) {
+    constexpr int W = S::W, HBW = S::HBW, NF = S::NF, NB = S::NB;
+    double sw[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) sw[j] = 0.0;
+#pragma unroll 1
+    for (int kb = NB - 1; kb >= 0; --kb) {
+#pragma unroll
+        for (int j = W - 1; j >= 0; --j) {
+            const int k = kb * W + j;
+            if (k < NF) {
+                const double *col = st + (size_t)k * W * kTpwThreads;
+                double acc = 0.0;
+#pragma unroll
+                for (int s = 1; s <= HBW; ++s) acc = fma(col[s * kTpwThreads], sw[(j + s) % W], acc);
+                const double sol = fma(-col[0], acc, v[free_dof[k]]);
+                sw[j] = sol;
+                v[free_dof[k]] = sol;
+            }
+        }
+    }
+}
+
+// shared memory: [exp table 256][x: E columns][F -> u: N columns]
+template <typename T, class S>
+__global__ void __launch_bounds__(kTpwThreads, 1)
+rom_tpw_forward_kernel(const __grid_constant__ TpwFwdTab<S> tab, const T *__restrict__ X, int x_is_log,
+                       const T *__restrict__ F, T *__restrict__ u, double *__restrict__ stash, int *info, long long B) {
+    extern __shared__ __align__(16) double tpw_smem[];
+    constexpr int W = S::W, HBW = S::HBW, NB = S::NB;
+    double *etab = tpw_smem;
+    double *xs = etab + 256;
+    double *fs = xs + S::E * kTpwPitch;
+    const long long b0 = (long long)blockIdx.x * kTpwThreads;
+    const int rows = (int)min((long long)kTpwThreads, B - b0);
+    for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
+    tpw_stage_in<T, S::E, 16>(X, b0, rows, x_is_log ? 0.0 : 1.0, xs);
+    tpw_stage_in<T, S::N, 16>(F, b0, rows, 0.0, fs);
+    __syncthreads();
+    double *x = xs + threadIdx.x, *f = fs + threadIdx.x;
+    int bad = tpw_conductivities<S::E>(x, x_is_log, smem_u32_of(etab));
+    double *st = stash + (size_t)blockIdx.x * tpw_stash_doubles_per_block<S>() + threadIdx.x;
+    {
+        double R[W][W], zw[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            zw[j] = 0.0;
+#pragma unroll
+            for (int s = 0; s < W; ++s) R[j][s] = 0.0;
+        }
+        tpw_prologue<S>(std::make_integer_sequence<int, HBW>{}, tab, x, f, R, zw);
+#pragma unroll 1
+        for (int kb = 0; kb < NB; ++kb) tpw_pivot_block<S>(std::make_integer_sequence<int, W>{}, tab, kb, x, f, R, zw, st, bad);
+    }
+    tpw_backward_subst<S>(st, tab.free_dof, f);
+    if ((int)threadIdx.x >= rows) bad = 0;
+    if (bad && info) atomicOr(info, bad);
+    __syncthreads();
+    tpw_stage_out<T, S::N>(u, b0, rows, fs);
+}
+
+// shared memory: [exp table 256][gbar -> lambda: N columns][u: N columns][gradient chunk: kTpwGradChunk columns]
+template <typename T, class S, bool GRADF>
+__global__ void __launch_bounds__(kTpwThreads, 1)
+rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__restrict__ X, int x_is_log,
+                       const T *__restrict__ u, const double *__restrict__ stash, const T *__restrict__ gbar,
+                       T *__restrict__ gradX, T *__restrict__ gradF, long long B) {
+    extern __shared__ __align__(16) double tpw_smem[];
+    constexpr int W = S::W, HBW = S::HBW, NF = S::NF, NB = S::NB, EC = kTpwGradChunk;
+    static_assert(S::E % EC == 0, "gradient chunks");
+    double *etab = tpw_smem;
+    double *gs = etab + 256;
+    double *us = gs + S::N * kTpwPitch;
+    double *ds = us + S::N * kTpwPitch;
+    const long long b0 = (long long)blockIdx.x * kTpwThreads;
+    const int rows = (int)min((long long)kTpwThreads, B - b0);
+    for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
+    tpw_stage_in<T, S::N, 16>(gbar, b0, rows, 0.0, gs);
+    tpw_stage_in<T, S::N, 16>(u, b0, rows, 0.0, us);
+    __syncthreads();
+    double *g = gs + threadIdx.x;
+    const double *uu = us + threadIdx.x;
+    const double *st = stash + (size_t)blockIdx.x * tpw_stash_doubles_per_block<S>() + threadIdx.x;
+    {   // w = D^-1 L^-1 gbar_f, window of W values
+        double zw[W];
+#pragma unroll
+        for (int j = 0; j < HBW; ++j) zw[j] = g[tab.free_dof[j]];
+        zw[HBW] = 0.0;
+#pragma unroll 1
+        for (int kb = 0; kb < NB; ++kb) {
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+                const int k = kb * W + j;
+                zw[(j + HBW) % W] = g[tab.free_dof[k + HBW]];     // phantom rows read column 0: never used (their L entries are 0)
+                if (k < NF) {
+                    const double *col = st + (size_t)k * W * kTpwThreads;
+                    const double wk = zw[j] * col[0];
+#pragma unroll
+                    for (int s = 1; s <= HBW; ++s) zw[(j + s) % W] = fma(-col[s * kTpwThreads], wk, zw[(j + s) % W]);
+                    g[tab.free_dof[k]] = wk;
+                }
+            }
+        }
+    }
+    tpw_backward_subst<S>(st, tab.free_dof, g);
+    if (GRADF && (int)threadIdx.x < rows) {
+        // lambda on the constrained rows: gbar_c - sum_f K_cf lambda_f (x of the few boundary elements from global memory)
+        const T *Xb = X + (b0 + threadIdx.x) * S::E;
+#pragma unroll 1
+        for (int i = 0; i < NF; ++i) {
+            const double li = g[tab.free_dof[i]];
+#pragma unroll
+            for (int t = 0; t < S::TR; ++t) {
+                const int k = i * S::TR + t;
+                const double c = tab.rhs_coef[k];
+                if (c != 0.0) {
+                    double xv = (double)Xb[tab.rhs_elem[k]];
+                    if (x_is_log) xv = (exp256_in_range(xv) ? exp_tab256c(xv, smem_u32_of(etab)) : exp(xv)) + 1e-8;
+                    g[tab.rhs_dof[k]] = fma(-c * xv, li, g[tab.rhs_dof[k]]);
+                }
+            }
+        }
+    }
+    // dL/dX in rounds of EC elements: per-thread columns -> coalesced rows, chain rule through x = exp(X) + 1e-8 on the way out
+    double *dcol = ds + threadIdx.x;
+#pragma unroll 1
+    for (int c0 = 0; c0 < S::E; c0 += EC) {
+#pragma unroll 1
+        for (int e = 0; e < EC; ++e) {
+            double acc = 0.0;
+#pragma unroll
+            for (int t = 0; t < S::TG; ++t) {
+                const int k = (c0 + e) * S::TG + t;
+                acc = fma(tab.grad_coef[k] * g[tab.grad_i[k]], uu[tab.grad_j[k]], acc);
+            }
+            dcol[e * kTpwPitch] = -acc;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < rows * EC; i += kTpwThreads) {
+            const int row = i / EC, j = i - row * EC;
+            const long long at = (b0 + row) * S::E + c0 + j;
+            double v = ds[j * kTpwPitch + row];
+            if (x_is_log) {
+                const double xv = (double)X[at];
+                v *= exp256_in_range(xv) ? exp_tab256c(xv, smem_u32_of(etab)) : exp(xv);
+            }
+            gradX[at] = (T)v;
+        }
+        __syncthreads();
+    }
+    if (GRADF) tpw_stage_out<T, S::N>(gradF, b0, rows, gs);
+}
+
+template <class S>
+constexpr size_t tpw_smem_forward() {
+    return sizeof(double) * (256 + (size_t)(S::E + S::N) * kTpwPitch);
+}
+template <class S>
+constexpr size_t tpw_smem_adjoint() {
+    return sizeof(double) * (256 + (size_t)(2 * S::N + kTpwGradChunk) * kTpwPitch);
+}
+
+}  // namespace gpde

@@ -62,6 +62,8 @@ struct VoEnv {
     int grid_debug = 0;       // GPDE_GRID_DEBUG
     bool sync_staging = false;   // GPDE_VO_SYNC_STAGING
     bool expand_gemm = false;    // GPDE_VO_EXPAND=gemm
+    int gemm_splits = 0;         // GPDE_GEMM_SPLITS: parts of the contraction length (0 = automatic)
+    int grid2_split = 1;         // GPDE_GRID2_SPLIT: 0 = never cut the node rows over a cluster, 1 = automatic, n > 1 = force n
     VoEnv() {
         const char *e;
         if ((e = getenv("GPDE_GRID_R"))) grid_r = atoi(e);
@@ -73,6 +75,8 @@ struct VoEnv {
         if ((e = getenv("GPDE_GRID_DEBUG"))) grid_debug = atoi(e);
         sync_staging = getenv("GPDE_VO_SYNC_STAGING") != nullptr;
         if ((e = getenv("GPDE_VO_EXPAND"))) expand_gemm = strcmp(e, "gemm") == 0;
+        if ((e = getenv("GPDE_GEMM_SPLITS"))) gemm_splits = std::max(0, std::min(8, atoi(e)));
+        if ((e = getenv("GPDE_GRID2_SPLIT"))) grid2_split = std::max(0, std::min(8, atoi(e)));
     }
 };
 }  // namespace gpde
@@ -574,10 +578,21 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
     const int S = 8 * G.groups;
     double *Vp = (double *)workspace;
     if (!rho && !prepacked) grid2_pack(G, V, m, NT, NX, Vp, pl->n_sm, st);
-    const unsigned grid = (unsigned)((B + S - 1) / S);
+    const unsigned blocks = (unsigned)((B + S - 1) / S);
+    // small batches: the node rows of a sample block are cut over the CTAs of a thread-block cluster (SPLIT variant of the
+    // kernel) when the blocks alone would leave more than half of the SMs idle; every range gets at least two stages.
+    // The cluster size depends on the number of sample blocks only.  GPDE_GRID2_SPLIT=0 keeps one CTA per block.
+    int csize = 1;
+    if (!rho && std::is_same<TA, TY>::value && std::is_same<TA, TR>::value && pl->env.grid2_split) {
+        const int n_stages = G.ny / 2;
+        csize = std::min(std::min(8, n_stages / 2), pl->n_sm / (int)blocks);
+        if (pl->env.grid2_split > 1) csize = std::min(pl->env.grid2_split, n_stages / 2);   // forced size (tests)
+        if (csize < 2 || 2 * (size_t)G.stage_bytes < (size_t)(16 * 8 * 34 + S * 33) * sizeof(double)) csize = 1;
+    }
+    const unsigned grid = blocks * (unsigned)csize;
     // the residual kernel is launched as a programmatic dependent of the packing kernel (its prologue and first
     // a / y stages overlap the packing); GPDE_GRID2_PDL=0 keeps the plain stream order
-    const bool pdl = !rho && !prepacked && pl->env.grid2_pdl;
+    const bool pdl = !rho && !prepacked && pl->env.grid2_pdl && csize == 1;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -585,10 +600,17 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    if (csize > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)csize;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
+    cfg.numAttrs = (pdl || csize > 1) ? 1 : 0;
     const int m_arg = rho ? rho_pitch : m;
     // a_is_log is a template parameter: with the exp() path compiled in or out, each variant gets its own register
     // allocation (as a run-time branch the two paths cost each other 4-8 %, measured A/B)
@@ -600,7 +622,19 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
         GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
                                         (const double *)Vp, m_arg, r, B));                                       \
     }
-#define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV) GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, false)
+#define GPDE_LAUNCH_GRID2_SPLIT(NTV, NXV)                                                                        \
+    {                                                                                                            \
+        auto kern = a_is_log ? vo_grid2_kernel<NTV, NXV, false, false, true, TA, TY, TR, true>                   \
+                             : vo_grid2_kernel<NTV, NXV, false, false, false, TA, TY, TR, true>;                 \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        GPDE_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, G, a, a_stride, a_is_log, y, y_stride, g, g_stride,         \
+                                        (const double *)Vp, m_arg, r, B));                                       \
+    }
+#define GPDE_LAUNCH_GRID2(NTV, NXV, RHOV)                                                                        \
+    {                                                                                                            \
+        if (csize > 1) { if constexpr (!RHOV && same) GPDE_LAUNCH_GRID2_SPLIT(NTV, NXV) }                        \
+        else GPDE_LAUNCH_GRID2_YS(NTV, NXV, RHOV, false)                                                         \
+    }
     // instantiated type combinations: (T,T,T) every variant but the strided-y one for FP32; (float,float,double) the rho
     // variant only (rho rows for the FP64 contraction); (T,double,T) the strided-y rho variant only (residual_T)
     constexpr bool same = std::is_same<TA, TY>::value && std::is_same<TA, TR>::value;
@@ -624,6 +658,7 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
         return 0;
     }
 #undef GPDE_LAUNCH_GRID2
+#undef GPDE_LAUNCH_GRID2_SPLIT
 #undef GPDE_LAUNCH_GRID2_YS
     GPDE_CUDA_OK(cudaGetLastError());
     return 1;
@@ -831,17 +866,28 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
             vo_gemm_pack_kernel_t<T><<<grid, 256, 0, st>>>(V, d, m, Vp, dp, ldb);
         }
         dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
+        // tail of the tile grid on the SMs: parts of the contraction length with a deterministic reduction (vo_gemm.cuh)
+        const int splits = pl->env.gemm_splits > 0 ? pl->env.gemm_splits
+                                                   : gemm_splits((long long)grid.x * grid.y, pl->n_sm, dp / kGemmKC);
+        double *partial = splits > 1 ? Vp + (size_t)dp * ldb : nullptr;
+        grid.z = (unsigned)splits;
         const size_t smem = gemm_smem(bn);
         if (bn == 64) {
             auto kern = vo_gemm_kernel<64, T>;
             GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B);
+            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B, partial);
         } else {
             auto kern = vo_gemm_kernel<128, T>;
             GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B);
+            kern<<<grid, kGemmThreads, smem, st>>>(ws, dp, Vp, ldb, r, m, (long long)B, partial);
         }
         GPDE_CUDA_OK(cudaGetLastError());
+        if (splits > 1) {
+            const long long total = (long long)B * m;
+            const unsigned rgrid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 16);
+            vo_gemm_reduce_kernel<T><<<rgrid, 256, 0, st>>>(partial, splits, ldb, r, m, (long long)B);
+            GPDE_CUDA_OK(cudaGetLastError());
+        }
     }
     return GPDE_OK;
 }
@@ -941,7 +987,7 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
                 const size_t smem = gemm_smem(bn);
                 GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 dim3 grid((unsigned)((B + kGemmBM - 1) / kGemmBM), (unsigned)(ldb / bn));
-                kern<<<grid, kGemmThreads, smem, st>>>(Sp, mp, Vt, ldb, w, d, (long long)B);
+                kern<<<grid, kGemmThreads, smem, st>>>(Sp, mp, Vt, ldb, w, d, (long long)B, (double *)nullptr);
                 GPDE_CUDA_OK(cudaGetLastError());
             }
             }
@@ -1091,7 +1137,9 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
     if (!pl || B < 0) return 0;
     // version-1 kernels: K-padded rho [B][dp] + padded V [dp][ldb] (residual), V s [B][d] (residual_T)
     const size_t dp = (size_t)gemm_dp(pl->dev.d);
-    size_t need = sizeof(double) * (dp * (size_t)B + dp * (size_t)gemm_ldb(std::max(m, 1)));
+    // (+ up to 8 partial result tiles [B][ldb] of the split contraction)
+    size_t need = sizeof(double) * (dp * (size_t)B + dp * (size_t)gemm_ldb(std::max(m, 1)) +
+                                    8 * (size_t)B * (size_t)gemm_ldb(std::max(m, 1)));
     if (pl->grid.ok && m > 0) {   // residual_T on the grid path: padded s [B][mp], V^T [mp][ldb], w [B][d]
         const size_t mp = (size_t)gemm_dp(m), ldb = ((size_t)pl->dev.d + 127) / 128 * 128;
         need = std::max(need, sizeof(double) * ((size_t)B * mp + mp * ldb + (size_t)B * pl->dev.d));

@@ -14,6 +14,10 @@
 // pitches are = 4 (mod 16) doubles, which makes both fragment loads conflict-free.
 // (A 112-row tile on 7 warps, tried against the 256-tiles-on-148-SMs tail of config 3, is no faster: the FP64
 // tensor pipe is per scheduler, and 7 warps leave one scheduler with half the work -- measured, round 1.)
+// Tail: one CTA per SM, so T output tiles take ceil(T / #SM) tile-times (config 3: 256 tiles on 148 SMs = 2.0 for 1.73 of
+// work).  The contraction length can be cut into S equal parts (gridDim.z = S, partial tiles to a workspace, summed in part
+// order by vo_gemm_reduce_kernel: deterministic, the same split for every sample): ceil(S T / #SM) / S tile-times -- 1.75 at
+// S = 4 for config 3.  gemm_splits() picks S.
 #pragma once
 
 namespace gpde {
@@ -76,10 +80,26 @@ __global__ void vo_gemm_pack_transposed_kernel(const double *__restrict__ V, int
     }
 }
 
+// R[b][c] = sum_z P[z][b][c] (c < m), parts in ascending order
+template <typename To>
+__global__ void vo_gemm_reduce_kernel(const double *__restrict__ P, int splits, int ldp, To *__restrict__ R, int m, long long B) {
+    const long long total = B * m;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / m;
+        const int c = (int)(idx - b * m);
+        double v = 0.0;
+        for (int z = 0; z < splits; ++z) v += P[((long long)z * B + b) * ldp + c];
+        R[idx] = (To)v;
+    }
+}
+
+// ``partial`` != nullptr: gridDim.z parts of the contraction length; part z writes its [B][ldb] partial tile rows to
+// partial + z * B * ldb (all ldb columns) and R is left to vo_gemm_reduce_kernel
 template <int BN, typename To>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ Vp, int ldb, To *__restrict__ R, int m,
-               long long B) {
+               long long B, double *__restrict__ partial = nullptr) {
     constexpr int LdB = BN + 4;                    // doubles per B row in shared memory
     constexpr int NT = BN / 16;                    // 8-column DMMA tiles per warp
     constexpr int A_STAGE = kGemmBM * kGemmLdA, B_STAGE = kGemmKC * LdB;
@@ -89,7 +109,9 @@ vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ 
     const int wm = warp & 3, wn = warp >> 2;       // 4 x 2 warps
     const long long row0 = (long long)blockIdx.x * kGemmBM;
     const int col0 = blockIdx.y * BN;
-    const int nchunks = dp / kGemmKC;
+    const int all_chunks = dp / kGemmKC;
+    const int kc0 = (int)((long long)all_chunks * blockIdx.z / gridDim.z);            // this part's chunks [kc0, kc0 + nchunks)
+    const int nchunks = (int)((long long)all_chunks * (blockIdx.z + 1) / gridDim.z) - kc0;
 
     // cp.async assignments: A chunk = 128 rows x 8 pieces, B chunk = 16 rows x BN/2 pieces (16 bytes each)
     auto load_chunk = [&](int kc, int stage) {
@@ -100,13 +122,13 @@ vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ 
             const int rr = p >> 3, pc = p & 7;
             long long row = row0 + rr;
             if (row >= B) row = B - 1;
-            cp_async16(as + rr * kGemmLdA + 2 * pc, A + row * dp + (long long)kc * kGemmKC + 2 * pc);
+            cp_async16(as + rr * kGemmLdA + 2 * pc, A + row * dp + (long long)(kc0 + kc) * kGemmKC + 2 * pc);
         }
 #pragma unroll
         for (int i = 0; i < (kGemmKC * BN / 2) / kGemmThreads; ++i) {
             const int p = threadIdx.x + i * kGemmThreads;
             const int kr = p / (BN / 2), pc = p - kr * (BN / 2);
-            cp_async16(bs + kr * LdB + 2 * pc, Vp + ((long long)kc * kGemmKC + kr) * ldb + col0 + 2 * pc);
+            cp_async16(bs + kr * LdB + 2 * pc, Vp + ((long long)(kc0 + kc) * kGemmKC + kr) * ldb + col0 + 2 * pc);
         }
     };
 
@@ -152,6 +174,15 @@ vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ 
     for (int mt = 0; mt < 4; ++mt) {
         const long long row = row0 + wm * 32 + mt * 8 + (lane >> 2);
         if (row >= B) continue;
+        if (partial) {
+            double *prow = partial + ((long long)blockIdx.z * B + row) * ldb;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = col0 + wn * (BN / 2) + nt * 8 + 2 * (lane & 3);
+                *reinterpret_cast<double2 *>(prow + col) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+            }
+            continue;
+        }
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
             const int col = col0 + wn * (BN / 2) + nt * 8 + 2 * (lane & 3);
@@ -164,6 +195,18 @@ vo_gemm_kernel(const double *__restrict__ A, int dp, const double *__restrict__ 
 static inline int gemm_bn(int m) { return m <= 64 ? 64 : 128; }
 static inline int gemm_ldb(int m) { const int bn = gemm_bn(m); return (m + bn - 1) / bn * bn; }
 static inline int gemm_dp(int d) { return (d + kGemmKC - 1) / kGemmKC * kGemmKC; }
+// parts of the contraction length: the S in {1, 2, 4, 8} with the fewest tile-times ceil(S T / #SM) / S, ties to the smaller S;
+// a split must save at least 6 % (its partial tiles cost a write, a read and one more launch)
+static inline int gemm_splits(long long tiles, int n_sm, int nchunks) {
+    int best = 1;
+    double best_t = (double)((tiles + n_sm - 1) / n_sm);
+    for (int s = 2; s <= 8; s *= 2) {
+        if (nchunks < 64 * s) break;
+        const double t = (double)((tiles * s + n_sm - 1) / n_sm) / s;
+        if (t < 0.94 * best_t) { best = s; best_t = t; }
+    }
+    return best;
+}
 static inline size_t gemm_smem(int bn) {
     return sizeof(double) * (size_t)kGemmStages * ((size_t)kGemmBM * kGemmLdA + (size_t)kGemmKC * (bn + 4));
 }

@@ -203,7 +203,13 @@ __device__ __forceinline__ void grid2_contract(unsigned msk, double (&acc)[NT][2
     }
 }
 
-template <int NT, int NX, bool RHO, bool YS, bool ALOG, typename TA = double, typename TY = double, typename TR = double>
+// SPLIT (small batches, launched as thread-block clusters): the C CTAs of a cluster share one block of samples and cut the
+// node rows into C contiguous ranges of stages.  A range that does not start at the bottom first replays the stage before
+// it with the contraction switched off (that rebuilds the marching state: previous node row, previous pixel row, vertical
+// fluxes); each CTA reduces its strips as usual, the partial results meet in rank order through distributed shared memory
+// on rank 0.  The cut depends only on the number of sample blocks of the call, never on a sample's position in the batch.
+template <int NT, int NX, bool RHO, bool YS, bool ALOG, typename TA = double, typename TY = double, typename TR = double,
+          bool SPLIT = false>
 __global__ void __launch_bounds__(512, 1)
 vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_is_log,
                 const TY *__restrict__ y, long long y_stride_arg, const TA *__restrict__ g, long long g_stride,
@@ -231,7 +237,12 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const int s = lane >> 2, k = lane & 3;
     const int S = 8 * G.groups;
     const int sl = grp * 8 + s;
-    const long long cta_b0 = (long long)blockIdx.x * S;
+    unsigned crank = 0, csize = 1;                  // rank in the cluster and its size (SPLIT only)
+    if constexpr (SPLIT) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    }
+    const long long cta_b0 = (long long)(SPLIT ? blockIdx.x / csize : blockIdx.x) * S;
     const bool b_valid = cta_b0 + sl < B;
     const long long b = b_valid ? cta_b0 + sl : B - 1;
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
@@ -239,6 +250,12 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const long long y_stride = YS ? y_stride_arg : d;
     const int c0 = 16 * q + 4 * k;
     const int n_stages = ny >> 1;
+    // stages [ts_base, ts_base + n_local) of this CTA; with SPLIT the first one of ranks > 0 is the replayed stage
+    const int s_lo = SPLIT ? (int)((long long)n_stages * crank / csize) : 0;
+    const int s_hi = SPLIT ? (int)((long long)n_stages * (crank + 1) / csize) : n_stages;
+    const bool warm = SPLIT && crank > 0;
+    const int ts_base = warm ? s_lo - 1 : s_lo;
+    const int n_local = s_hi - ts_base;
     const int gthreads = 32 * G.nstrips;            // threads of one sample group (= 2 nx)
 
     // ---- zero the stages (halo reads past a sample's rows must see finite numbers), barriers, exp table
@@ -278,14 +295,15 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
 #pragma unroll
     for (int i = 0; i < NIY; ++i) nv += (cta_b0 + smp0 + SSY * i < B) ? 1 : 0;
     // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx elements (lowest address first)
-    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0a) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece_a;
     const long long a_adv = 2 * EA * G.sy, a_smp = SSA * a_stride * EA;
+    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0a) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece_a +
+                        (SPLIT ? ts_base * a_adv : 0);
     const unsigned a_dst = smp0a * G.a_pitch * EA + 16 * piece_a, a_dsmp = SSA * G.a_pitch * EA;
     // node rows 2 ts + 1, 2 ts + 2: 2 ncol elements starting on an element boundary; copied from the enclosing
     // 16-byte boundary.  The phase y_sig (in elements) is the same for the samples of a thread (they are 16 / E apart).
     // FP64: it is the same for all stages too (a stage advances by 16 ncol bytes); FP32: a stage advances by 8 ncol
     // bytes with ncol odd, so the phase alternates between y_sig and y_sig ^ 2 from stage to stage
-    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * y_stride + ncol);
+    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * y_stride + ncol + (SPLIT ? 2 * ts_base * ncol : 0));
     int y_sig = (int)(((unsigned long long)y_row1 / EY) & (16 / EY - 1));
     const char *y_src = y_row1 - EY * y_sig + 16 * piece;
     const long long y_adv = 2 * EY * ncol, y_smp = SSY * y_stride * EY;
@@ -336,8 +354,8 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             y_sig ^= 2;
         }
     };
-    issue_stage(0, 0);
-    if (n_stages > 1) issue_stage(1, 1);
+    issue_stage(ts_base, 0);
+    if (n_local > 1) issue_stage(ts_base + 1, 1);
 
     // packed V rows 2 ts, 2 ts + 1 -> V stage (thread 0 only; v_next = next stage to copy, into slot v_islot)
     // (thread 0's bookkeeping lives in shared memory: three registers less for every thread of the kernel)
@@ -347,15 +365,15 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         const unsigned bytes = (unsigned)v_bytes;
         int v_next = vst[0], v_islot = vst[1];
         mbar_arrive_expect_tx(full_v + v_islot, bytes);
-        bulk_g2s(v_base + (size_t)v_islot * v_bytes, reinterpret_cast<const char *>(Vp) + (size_t)(2 * v_next) * G.v_row_bytes,
-                 bytes, full_v + v_islot);
+        bulk_g2s(v_base + (size_t)v_islot * v_bytes,
+                 reinterpret_cast<const char *>(Vp) + (size_t)(2 * (ts_base + v_next)) * G.v_row_bytes, bytes, full_v + v_islot);
         ++v_next;
         if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) vst[2] = vst[2] ^ 1; }
         vst[0] = v_next; vst[1] = v_islot;
     };
     if (!RHO && tid == 0) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // the packing kernel's rows (no-op without a dependent launch)
-        while (vst[0] < G.nvs && vst[0] < n_stages) issue_v();
+        while (vst[0] < G.nvs && vst[0] < n_local) issue_v();
     }
 
     // ---- per-lane constants of the consumer
@@ -365,7 +383,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * y_stride + ncol) / EY) & (16 / EY - 1));
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
     const unsigned y_lane = G.y_off + (sl * G.y_pitch + (EY == 8 ? 2 * ((sl >> 1) & 1) + 2 : 4) + sig_b + c0) * EY;
-    const int y_lane_odd = EY == 4 ? 4 * ((sig_b ^ 2) - sig_b) : 0;   // FP32: odd stages sit at phase sig_b ^ 2
+    const int y_lane_odd = EY == 4 ? 4 * ((sig_b ^ 2) - sig_b) : 0;   // FP32: odd (global) stages sit at phase sig_b ^ 2
     const unsigned a_lane0 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? 0 : nx * EA);   // pixel row 2 ts
     const unsigned a_lane1 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? nx * EA : 0);   // pixel row 2 ts + 1
     const unsigned v_lane = (q * NP * 32 + lane) * 16;                       // inside a V stage
@@ -383,8 +401,12 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     for (int j = 0; j < 4; ++j) fvp[j] = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) ap[j] = 0.0;
-    // node row 0 straight from global memory
-    {
+    // node row 0 straight from global memory (a range that starts higher up gets its state from the replayed stage)
+    if (SPLIT && warm) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) uc[j] = 0.0;
+        ulc = urc = 0.0;
+    } else {
         const double g0 = gp ? (double)__ldg(gp) : 0.0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) uc[j] = (c0 + j < ncol) ? (double)__ldg(yb + c0 + j) : 0.0;
@@ -392,7 +414,8 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         urc = (c0 + 4 < ncol) ? (double)__ldg(yb + c0 + 4) : 0.0;
         if (is_right) uc[3] = g0;
     }
-    double gn0 = gp ? (double)__ldg(gp + 2) : 0.0, gn1 = gp ? (double)__ldg(gp + 4) : 0.0;   // Dirichlet values of node rows 1, 2
+    // Dirichlet values of the first stage's node rows 2 ts + 1, 2 ts + 2
+    double gn0 = gp ? (double)__ldg(gp + 2 * (2 * ts_base + 1)) : 0.0, gn1 = gp ? (double)__ldg(gp + 2 * (2 * ts_base + 2)) : 0.0;
 
     // one node row: new row (un, an) in, residual of the row below (uc between ap and an) out
     auto node_row = [&](const double (&un)[4], double unl, double unr, const double (&an)[5], unsigned v_addr,
@@ -454,16 +477,17 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
 
     int v_slot = 0;                  // V stage being consumed and the parity of its full barrier
     unsigned v_par = 0;
-    for (int ts = 0; ts < n_stages; ++ts) {
-        const int slot = ts & 1;
-        const unsigned par = (ts >> 1) & 1;
+    for (int lt = 0; lt < n_local; ++lt) {
+        const int ts = ts_base + lt;
+        const int slot = lt & 1;
+        const unsigned par = (lt >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
         const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
         if (!RHO && tid == 0) {
             // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
-            while (vst[0] < n_stages && vst[0] < ts + G.nvs) {
+            while (vst[0] < n_local && vst[0] < lt + G.nvs) {
                 if (!mbar_test(empty_v + vst[1], (unsigned)vst[2])) {
-                    if (vst[0] > ts) break;
+                    if (vst[0] > lt) break;
                     mbar_wait(empty_v + vst[1], (unsigned)vst[2]);
                 }
                 issue_v();
@@ -478,7 +502,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         }
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-            const unsigned ya = sb + y_lane + rr * row_bytes + (EY == 4 && slot ? y_lane_odd : 0);
+            const unsigned ya = sb + y_lane + rr * row_bytes + (EY == 4 && (SPLIT ? (ts & 1) : slot) ? y_lane_odd : 0);
             unsigned msk_rr = 0;
             if constexpr (!RHO) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(msk_rr) : "r"(vb + m_lane + rr * G.v_row_bytes));
             double un[4], unl, unr, an[5];
@@ -489,6 +513,17 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             const double gv = rr ? gn1 : gn0;
             if (is_left) unl = gv;
             if (is_right) un[3] = gv;
+            if (SPLIT && warm && lt == 0) {
+                // replayed stage: its first node row only becomes the "row below"; its second one runs with the contraction
+                // off (empty mask), which leaves the marching state as if the rows below had been processed
+                if (rr == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) uc[j] = un[j];
+                    ulc = unl; urc = unr;
+                    continue;
+                }
+                msk_rr = 0;
+            }
             const unsigned aa = sb + (rr ? a_lane1 : a_lane0);
             if constexpr (EA == 8) {
                 const double2 p0 = lds128(aa), p1 = lds128(aa + 16);
@@ -524,14 +559,14 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             if (!RHO) mbar_arrive(empty_v + v_slot);
         }
         if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
-        if (ts + 2 < n_stages) {
+        if (lt + 2 < n_local) {
             if (G.flags & 1) mbar_spin(my_empty + slot, par);
             else mbar_wait(my_empty + slot, par);
             issue_stage(ts + 2, slot);
         }
     }
-    // ---- last node row (ny): no pixel row above
-    {
+    // ---- last node row (ny): no pixel row above (SPLIT: the top range only)
+    if (!SPLIT || crank == csize - 1) {
         if (!RHO) asm volatile("griddepcontrol.wait;" ::: "memory");   // packed row ny is read with plain loads
         const double un[4] = {0.0, 0.0, 0.0, 0.0}, an[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
         node_row(un, 0.0, 0.0, an, 0u, 0u, 0u,
@@ -566,14 +601,47 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     }
     __syncthreads();
     constexpr int MC = NT * 8 + NX;
-    for (int idx = tid; idx < S * MC; idx += kThreads) {
-        const int si = idx / MC, col = idx - si * MC;
-        const long long bs = cta_b0 + si;
-        if (col < m && bs < B) {
+    if constexpr (SPLIT) {
+        // this range's partial result of the CTA's samples, behind ``red``; rank 0 adds the ranks' partials in rank order
+        double *part = red + (size_t)kWarps * 8 * NW;      // [S][MC]
+        for (int idx = tid; idx < S * MC; idx += kThreads) {
+            const int si = idx / MC, col = idx - si * MC;
             const int gi = si >> 3, ss = si & 7;
             double v = 0.0;
             for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * NW + col];
-            r[bs * m + col] = (TR)(G.scale * v);
+            part[idx] = v;
+        }
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (crank == 0) {
+            const unsigned part32 = smem_u32(part);
+            for (int idx = tid; idx < S * MC; idx += kThreads) {
+                const int si = idx / MC, col = idx - si * MC;
+                const long long bs = cta_b0 + si;
+                if (col < m && bs < B) {
+                    double v = 0.0;
+                    for (unsigned c = 0; c < csize; ++c) {
+                        unsigned remote;
+                        double pv;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(part32 + 8u * idx), "r"(c));
+                        asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(pv) : "r"(remote) : "memory");
+                        v += pv;
+                    }
+                    r[bs * m + col] = (TR)(G.scale * v);
+                }
+            }
+        }
+        // nobody leaves (and frees its shared memory) before rank 0 has read it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        for (int idx = tid; idx < S * MC; idx += kThreads) {
+            const int si = idx / MC, col = idx - si * MC;
+            const long long bs = cta_b0 + si;
+            if (col < m && bs < B) {
+                const int gi = si >> 3, ss = si & 7;
+                double v = 0.0;
+                for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * NW + col];
+                r[bs * m + col] = (TR)(G.scale * v);
+            }
         }
     }
 }

@@ -61,17 +61,20 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M_hos
 int gpde_rom_plan_destroy(gpde_rom_plan *plan);
 
 /* out[0]=n, [1]=E, [2]=n_free, [3]=half bandwidth, [4]=factor doubles per sample,
- * [5]=assembly contributions, [6]=lanes per sample (1 = thread-per-sample kernels), [7]=device */
+ * [5]=assembly contributions, [6]=lanes per sample (1 = thread-per-sample kernels without a stash, 2 = windowed
+ * thread-per-sample kernels: pass the stash to the forward call too, 8/16/32 = cooperative kernels), [7]=device */
 int gpde_rom_plan_info(const gpde_rom_plan *plan, int64_t out[8]);
 
-/* bytes of factor stash needed for a batch of B samples (always doubles) */
+/* bytes of factor stash needed for a batch of B samples (always doubles; the layout is the kernels' business: the
+ * windowed kernels interleave blocks of 128 samples, so size the buffer with this call, not with out[4] * B) */
 size_t gpde_rom_factor_bytes(const gpde_rom_plan *plan, int64_t B);
 
 /* Replaces ROM.__call__ (bottleneck/ROM.py:65-88)  [x_is_log = 0: X are conductivities]
  * and ReducedOrderModelOperator's exp(X)+1e-8 -> rom (components.py:298) [x_is_log = 1].
  *   X [B,E], F [B,n] (Dirichlet values already written at bc_dofs, BoundaryConditions.py:132-147)
  *   u [B,n]  solution incl. Dirichlet dofs
- *   factor   [gpde_rom_factor_bytes] banded LDL^T factor kept for the adjoint (may be NULL)
+ *   factor   [gpde_rom_factor_bytes] banded LDL^T factor kept for the adjoint (may be NULL; plans with lanes == 2 then
+ *            fall back to the slower cooperative kernels)
  *   info     device int32, OR-ed with GPDE_INFO_* (may be NULL)                              */
 int gpde_rom_forward_f64(const gpde_rom_plan *plan, const double *X, int x_is_log, const double *F,
                          double *u, double *factor, int *info, int64_t B, gpde_stream_t stream);

@@ -661,3 +661,53 @@ def test_gaussian_sketch_on_device(dev):
     s = VO.GaussianSketchingSampler(qp_dev, 4)
     Gam, alp = s.sample()
     assert Gam.shape == (4, d) and alp.shape == (4,) and s.fixed_precision
+
+
+@pytest.mark.parametrize("splits", [2, 4, 8])
+def test_split_contraction_matches_single_pass(splits, dev):
+    """m > 32: the FP64 tensor-core contraction cut into parts of the contraction length (tail of the tile grid on the SMs,
+    vo_gemm.cuh) with the deterministic in-order reduction == the single-pass contraction to rounding; ragged batch; FP32
+    I/O; repeated calls give bitwise the same numbers."""
+    plan, fom, a, y, g, rng = _grid_case(64, 16, "NDP", 150, 21, dev, load=False)
+    one, cut = plan.variant(GPDE_GEMM_SPLITS="1"), plan.variant(GPDE_GEMM_SPLITS=str(splits))
+    T = lambda t: torch.tensor(t, device=dev)
+    for m in (40, 100, 256):
+        V = T(rng.normal(size=(fom.dim_out, m)))
+        r1 = one.residual(T(a), T(y), T(g), V)
+        r2 = cut.residual(T(a), T(y), T(g), V)
+        assert rel_err(r2.cpu(), r1.cpu()) < 1e-13, m
+        assert torch.equal(r2, cut.residual(T(a), T(y), T(g), V))
+        r3 = cut.residual(T(a).float(), T(y).float(), T(g).float(), V.float())
+        assert r3.dtype == torch.float32 and rel_err(r3.double().cpu(), r1.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("nx,ny,B", [(32, 32, 64), (32, 32, 5), (64, 64, 37), (16, 8, 130), (128, 16, 19), (64, 4, 3), (16, 2, 9)])
+def test_small_batches_cut_the_node_rows_over_a_cluster(nx, ny, B, dev):
+    """Few sample blocks: the lean grid kernel runs as thread-block clusters whose CTAs each march a range of the node
+    rows (replaying the stage below their range) and meet through distributed shared memory (vo_grid2.cuh, SPLIT).
+    Against one CTA per block (GPDE_GRID2_SPLIT=0) to summation-order rounding: automatic and forced cluster sizes, every
+    n-tile split of m, FP64 and FP32 I/O (all phases of y), log and conductivity input, shared Dirichlet rows, packed
+    weights; the cut does not depend on the position in the batch (bitwise sample-permutation equivariance)."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 13 + ny + B, dev, load=False)
+    whole = plan.variant(GPDE_GRID2_SPLIT="0")
+    T = lambda t: torch.tensor(t, device=dev)
+    d = fom.dim_out
+    big = torch.zeros(B * d + 3, dtype=torch.float32, device=dev)
+    y32_off = big[3:].view(B, d)
+    y32_off.copy_(T(y).float())
+    variants = [plan] + [plan.variant(GPDE_GRID2_SPLIT=str(c)) for c in (2, 3, 8)]     # the library caps the size at stages / 2
+    for m in (1, 8, 9, 17, 25, 32):
+        V = T(rng.normal(size=(d, m)))
+        r0 = whole.residual(T(a), T(y), T(g), V)
+        r0_lin = whole.residual(torch.exp(T(a)), T(y), T(g[0]), V, a_is_log=False)
+        r0_32 = whole.residual(T(a).float(), y32_off, T(g).float(), V.float())
+        for p in variants:
+            assert rel_err(p.residual(T(a), T(y), T(g), V).cpu(), r0.cpu()) < 1e-12, m
+            assert rel_err(p.residual(torch.exp(T(a)), T(y), T(g[0]), V, a_is_log=False).cpu(), r0_lin.cpu()) < 1e-12, m
+            assert rel_err(p.residual(T(a).float(), y32_off, T(g).float(), V.float()).double().cpu(), r0_32.double().cpu()) < 2e-6, m
+    V = T(rng.normal(size=(d, 25)))
+    r = plan.residual(T(a), T(y), T(g), V)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0)).to(dev)
+    assert torch.equal(plan.residual(T(a)[perm], T(y)[perm], T(g)[perm], V), r[perm])
+    pw = plan.pack_weights(V, B)
+    assert torch.equal(plan.residual(T(a), T(y), T(g), pw), r)
