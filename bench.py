@@ -670,19 +670,26 @@ def run_b200(args):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(Ke):
-            step_e2e()
-        e1.record()
-        torch.cuda.synchronize()
-        e_ms = e0.elapsed_time(e1) / Ke
-        if world > 1:
-            tt = torch.tensor([e_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            e_ms = float(tt.item())
+        # three timed blocks of Ke steps; the MEDIAN block is reported and all three are listed: the copies share the host's
+        # memory system and PCIe root with whatever else runs on the box
+        blocks = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(Ke):
+                step_e2e()
+            e1.record()
+            torch.cuda.synchronize()
+            b_ms = e0.elapsed_time(e1) / Ke
+            if world > 1:
+                tt = torch.tensor([b_ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                b_ms = float(tt.item())
+            blocks.append(b_ms)
+        e_ms = sorted(blocks)[1]
         e2e = {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_in),
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e_ms, "steps": Ke, "chunks": nch,
+               "ms_per_step_blocks": blocks,
                "h2d_gbs_per_gpu": bytes_in / (e_ms * 1e-3) / 1e9, "cpu_affinity": affinity,
                "bound": "host-to-device copy (PCIe): compute is %.1f %% of the step" % (100.0 * ms_per_step / e_ms)}
 
