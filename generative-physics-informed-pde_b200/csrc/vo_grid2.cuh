@@ -392,6 +392,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const unsigned m_lane = G.v_row_bytes - kGrid2MaskBytes + 4 * q;
     const unsigned row_bytes = ncol * EY;
     const double rh = G.rh;
+    const bool rho_wide = RHO && !(m & 1) && !(reinterpret_cast<unsigned long long>(r) & 15ull);
 
     double acc[NT][2], accx = 0.0;
 #pragma unroll
@@ -436,9 +437,25 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         if constexpr (RHO) {
             if (b_valid) {
                 TR *dst = r + b * (long long)m + (long long)t_out * ncol + c0;
+                if (sizeof(TR) == 8 && rho_wide) {
+                    // even row pitch, 16-byte aligned rows: ncol is odd, so this lane's 4 values start on a 16-byte boundary
+                    // in even node rows and 8 bytes past one in odd rows -- 2 or 3 stores instead of 4
+                    double *dd = reinterpret_cast<double *>(dst);
+                    const double s0 = G.scale * Sv[0], s1 = G.scale * Sv[1], s2 = G.scale * Sv[2], s3 = G.scale * Sv[3];
+                    if (!(t_out & 1)) {
+                        *reinterpret_cast<double2 *>(dd) = make_double2(s0, s1);
+                        if (!is_right) *reinterpret_cast<double2 *>(dd + 2) = make_double2(s2, s3);
+                        else dd[2] = s2;
+                    } else {
+                        dd[0] = s0;
+                        *reinterpret_cast<double2 *>(dd + 1) = make_double2(s1, s2);
+                        if (!is_right) dd[3] = s3;
+                    }
+                } else {
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dst[j] = (TR)(G.scale * Sv[j]);
-                if (!is_right) dst[3] = (TR)(G.scale * Sv[3]);
+                    for (int j = 0; j < 3; ++j) dst[j] = (TR)(G.scale * Sv[j]);
+                    if (!is_right) dst[3] = (TR)(G.scale * Sv[3]);
+                }
             }
         } else {
             if (v_glob) {   // last node row: packed V row from global memory
