@@ -33,6 +33,25 @@ UNIT = "samples/s (1 CGM fwd+adjoint solve + 1 VO residual eval per sample)"
 FP64_PEAK_TFLOPS = 37.0   # DMMA/DFMA rate measured on this pool (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON record: everything libraries print there (NCCL's version banner, ...)
+    is sent to stderr for the whole run; ``emit`` writes the record to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,7 +188,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- clocks sampler
@@ -518,7 +537,7 @@ def run_cfg5(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg5", "desc": rec["desc"]},
                 "components": rec, "gpu_launches": None, "clocks": sampler.summary(t0, t1) if sampler else None}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -751,13 +770,14 @@ def run_b200(args):
                       "points) on the first %d samples of the batch" % (n, ref.n),
             "vo_evals_per_s_assemble_each_step": 1.0 / ref.vo_assemble(min(ref.n, 32)),
             "vo_evals_per_s_vectorised_cached_K": 1.0 / ref.vo_vectorised()}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
