@@ -96,18 +96,28 @@ prolong_loglik_rows_kernel(ProlongDev P, const T *__restrict__ u, const T *__res
         inv = exp(-lsi);
     }
     const int lane = threadIdx.x & 31;
-    for (int sidx = 0; sidx < nb; ++sidx) {
-        double term = 0.0;
-        if (live) {
-            double mu = 0.0;
-            for (int t = t0; t < t1; ++t) mu = fma(P.val[t], us[sidx * P.n + P.col[t]], mu);
-            const double e = (pld(Y + (b0 + sidx) * P.d + i) - mu) * inv;
-            term = fma(e, e, 2.0 * lsi + kLog2Pi);
-            gl += fma(e, e, -1.0);
-        }
+    // 8 samples at a time: their Y values are fetched together (one global round trip per 8 samples, not one per sample:
+    // small batches have too few CTAs to hide it), then reduced over the warp's rows
+    for (int s0 = 0; s0 < nb; s0 += 8) {
+        double yv[8];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
-        if (lane == 0) atomicAdd(Ls + sidx, term);
+        for (int w8 = 0; w8 < 8; ++w8) yv[w8] = (live && s0 + w8 < nb) ? pld(Y + (b0 + s0 + w8) * P.d + i) : 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < 8; ++w8) {
+            const int sidx = s0 + w8;
+            if (sidx >= nb) break;
+            double term = 0.0;
+            if (live) {
+                double mu = 0.0;
+                for (int t = t0; t < t1; ++t) mu = fma(P.val[t], us[sidx * P.n + P.col[t]], mu);
+                const double e = (yv[w8] - mu) * inv;
+                term = fma(e, e, 2.0 * lsi + kLog2Pi);
+                gl += fma(e, e, -1.0);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+            if (lane == 0) atomicAdd(Ls + sidx, term);
+        }
     }
     if (live && gls) atomicAdd(gls + i, gl);
     __syncthreads();

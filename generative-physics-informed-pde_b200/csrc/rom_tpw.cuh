@@ -95,7 +95,7 @@ template <typename T, int WD>
 __device__ __forceinline__ void tpw_stage_out(T *__restrict__ dst, long long b0, int rows, const double *col) {
     T *p = dst + b0 * WD;
     const int limit = rows * WD;
-#pragma unroll 2
+#pragma unroll 4
     for (int i = threadIdx.x; i < limit; i += kTpwThreads) {
         const int row = i / WD, j = i - row * WD;
         p[i] = (T)col[j * kTpwPitch + row];
@@ -106,8 +106,8 @@ __device__ __forceinline__ void tpw_stage_out(T *__restrict__ dst, long long b0,
 template <int E>
 __device__ __forceinline__ int tpw_conductivities(double *x, int x_is_log, unsigned etab) {
     int bad = 0;
-#pragma unroll 2
-    for (int e = 0; e < E; ++e) {
+#pragma unroll 8
+    for (int e = 0; e < E; ++e) {      // 8 independent exp chains in flight (one warp per scheduler: nothing else hides them)
         double v = x[e * kTpwPitch];
         if (x_is_log) {
             v = (exp256_in_range(v) ? exp_tab256c(v, etab) : exp(v)) + 1e-8;
@@ -225,8 +225,9 @@ rom_tpw_forward_kernel(const __grid_constant__ TpwFwdTab<S> tab, const T *__rest
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
     const int rows = (int)min((long long)kTpwThreads, B - b0);
     for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
-    tpw_stage_in<T, S::E, 16>(X, b0, rows, x_is_log ? 0.0 : 1.0, xs);
-    tpw_stage_in<T, S::N, 16>(F, b0, rows, 0.0, fs);
+    // (64 coalesced loads in flight per thread: the staging is a chain of DRAM round trips, one per chunk)
+    tpw_stage_in<T, S::E, 64>(X, b0, rows, x_is_log ? 0.0 : 1.0, xs);
+    tpw_stage_in<T, S::N, 41>(F, b0, rows, 0.0, fs);
     __syncthreads();
     double *x = xs + threadIdx.x, *f = fs + threadIdx.x;
     int bad = tpw_conductivities<S::E>(x, x_is_log, smem_u32_of(etab));
@@ -266,8 +267,8 @@ rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__rest
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
     const int rows = (int)min((long long)kTpwThreads, B - b0);
     for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
-    tpw_stage_in<T, S::N, 16>(gbar, b0, rows, 0.0, gs);
-    tpw_stage_in<T, S::N, 16>(u, b0, rows, 0.0, us);
+    tpw_stage_in<T, S::N, 41>(gbar, b0, rows, 0.0, gs);
+    tpw_stage_in<T, S::N, 41>(u, b0, rows, 0.0, us);
     __syncthreads();
     double *g = gs + threadIdx.x;
     const double *uu = us + threadIdx.x;
@@ -327,15 +328,27 @@ rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__rest
             dcol[e * kTpwPitch] = -acc;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < rows * EC; i += kTpwThreads) {
-            const int row = i / EC, j = i - row * EC;
-            const long long at = (b0 + row) * S::E + c0 + j;
-            double v = ds[j * kTpwPitch + row];
-            if (x_is_log) {
-                const double xv = (double)X[at];
-                v *= exp256_in_range(xv) ? exp_tab256c(xv, smem_u32_of(etab)) : exp(xv);
+        // EC entries per thread and round (fewer in the last CTA); the conductivity inputs of 8 entries are fetched together:
+        // one global round trip per 8 entries instead of one per entry
+#pragma unroll 1
+        for (int it0 = 0; it0 < EC; it0 += 8) {
+            double xv[8];
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) {
+                const int i = threadIdx.x + (it0 + w8) * kTpwThreads;
+                const int row = i / EC, j = i - row * EC;
+                xv[w8] = (x_is_log && i < rows * EC) ? (double)X[(b0 + row) * S::E + c0 + j] : 0.0;
             }
-            gradX[at] = (T)v;
+#pragma unroll
+            for (int w8 = 0; w8 < 8; ++w8) {
+                const int i = threadIdx.x + (it0 + w8) * kTpwThreads;
+                if (i < rows * EC) {
+                    const int row = i / EC, j = i - row * EC;
+                    double v = ds[j * kTpwPitch + row];
+                    if (x_is_log) v *= exp256_in_range(xv[w8]) ? exp_tab256c(xv[w8], smem_u32_of(etab)) : exp(xv[w8]);
+                    gradX[(b0 + row) * S::E + c0 + j] = (T)v;
+                }
+            }
         }
         __syncthreads();
     }

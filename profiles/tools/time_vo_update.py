@@ -27,3 +27,13 @@ ms_c, _ = t(lambda: (wl.vo_mean.copy_(wl.VO.mean), wl.vo_logsigma.copy_(wl.VO.lo
 ms_all, _ = t(lambda: wl.update_virtual_observables(N_mc=64, step=1))
 print("VO update N_vo=%d N_mc=%d: sample %.3f | predictive moments %.3f | resample %.3f | precision %.3f | update (incl. precision) %.3f | "
       "copy out %.3f | whole %.3f ms" % (wl.N_vo, N_mc, ms_s, ms_m, ms_r, ms_p, ms_u, ms_c, ms_all))
+
+if "--profile" in sys.argv:
+    import cProfile, pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(5):
+        wl.update_virtual_observables(N_mc=64, step=1)
+    torch.cuda.synchronize()
+    pr.disable()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(25)
