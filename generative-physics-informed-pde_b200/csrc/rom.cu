@@ -73,8 +73,8 @@ struct gpde_rom_plan {
     int tps;                // 1: the thread-per-sample kernels (rom_tps.cuh) serve this plan (no factor stash)
     gpde::TpsAdjTab<gpde::TpsShape4x4> tps_tab;   // their tables, passed by value with every launch
     int tpw;                // 1: the windowed thread-per-sample kernels (rom_tpw.cuh); the factor stash is sample-interleaved
-    gpde::TpwFwdTab<gpde::TpwShape8x8> tpw_fwd;
-    gpde::TpwAdjTab<gpde::TpwShape8x8> tpw_adj;
+    const gpde::TpwFwdTab<gpde::TpwShape8x8> *tpw_fwd;   // their tables, in device memory (each CTA copies them to shared memory)
+    const gpde::TpwAdjTab<gpde::TpwShape8x8> *tpw_adj;
     int lanes;              // G
     int n_contrib;
     size_t smem_fwd, smem_adj;  // bytes per sample
@@ -431,14 +431,15 @@ static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<in
     memset(&Ft, 0, sizeof(Ft));
     memset(&At, 0, sizeof(At));
     for (int i = 0; i < nf; ++i) {
-        Ft.free_dof[i] = At.free_dof[i] = (unsigned short)(free_dof[i] * kTpwPitch);
+        TpwRow<S> &R = Ft.row[i];
+        R.free_dof = At.free_dof[i] = (unsigned short)(free_dof[i] * kTpwPitch);
         int cnt = 0;
         for (int e = 0; e < E; ++e) {
             const double v = Mat(free_dof[i], free_dof[i], e);
             if (v == 0.0) continue;
             if (cnt == S::TD) return false;
-            Ft.diag_coef[i * S::TD + cnt] = v;
-            Ft.diag_elem[i * S::TD + cnt] = (unsigned short)(e * kTpwPitch);
+            R.diag_coef[cnt] = v;
+            R.diag_elem[cnt] = (unsigned short)(e * kTpwPitch);
             ++cnt;
         }
         for (int s = 1; s <= hbw && s <= i; ++s) {
@@ -448,10 +449,10 @@ static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<in
                 if (v == 0.0) continue;
                 if (s != 1 && s != hbw) return false;       // not the 5-point structure
                 if (cnt == S::TO) return false;
-                double *coef = s == 1 ? Ft.s1_coef : Ft.sh_coef;
-                unsigned short *elem = s == 1 ? Ft.s1_elem : Ft.sh_elem;
-                coef[i * S::TO + cnt] = v;
-                elem[i * S::TO + cnt] = (unsigned short)(e * kTpwPitch);
+                double *coef = s == 1 ? R.s1_coef : R.sh_coef;
+                unsigned short *elem = s == 1 ? R.s1_elem : R.sh_elem;
+                coef[cnt] = v;
+                elem[cnt] = (unsigned short)(e * kTpwPitch);
                 ++cnt;
             }
         }
@@ -462,10 +463,10 @@ static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<in
                 if (v == 0.0) continue;
                 if (cnt == S::TR) return false;
                 const int k = i * S::TR + cnt;
-                Ft.rhs_coef[k] = At.rhs_coef[k] = v;
-                Ft.rhs_elem[k] = (unsigned short)(e * kTpwPitch);
+                R.rhs_coef[cnt] = At.rhs_coef[k] = v;
+                R.rhs_elem[cnt] = (unsigned short)(e * kTpwPitch);
                 At.rhs_elem[k] = (unsigned short)e;
-                Ft.rhs_dof[k] = At.rhs_dof[k] = (unsigned short)(bc_dof[c] * kTpwPitch);
+                R.rhs_dof[cnt] = At.rhs_dof[k] = (unsigned short)(bc_dof[c] * kTpwPitch);
                 ++cnt;
             }
     }
@@ -787,8 +788,22 @@ int gpde_rom_plan_create(gpde_rom_plan **plan, int n, int E, const double *M, co
         const char *e = getenv("GPDE_ROM_PATH");
         const bool want = !(e && strcmp(e, "coop") == 0);
         pl->tps = (want && build_tps_tables<TpsShape4x4>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, pl->tps_tab)) ? 1 : 0;
-        pl->tpw = (want && !pl->tps &&
-                   build_tpw_tables<TpwShape8x8>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, pl->tpw_fwd, pl->tpw_adj)) ? 1 : 0;
+        pl->tpw = 0;
+        pl->tpw_fwd = nullptr;
+        pl->tpw_adj = nullptr;
+        if (want && !pl->tps) {
+            std::vector<TpwFwdTab<TpwShape8x8>> ft(1);
+            std::vector<TpwAdjTab<TpwShape8x8>> at(1);
+            if (build_tpw_tables<TpwShape8x8>(n, E, nf, hbw, free_dof, bc_dof, is_bc, M, ft[0], at[0])) {
+                int rc2 = track(pl, &pl->tpw_fwd, ft);
+                if (rc2 == GPDE_OK) rc2 = track(pl, &pl->tpw_adj, at);
+                if (rc2 != GPDE_OK) {
+                    gpde_rom_plan_destroy(pl);
+                    return rc2;
+                }
+                pl->tpw = 1;
+            }
+        }
     }
     // per-sample scratch of the cooperative kernels; with 8 lanes per sample a 64-bit shared-memory wavefront serves two
     // samples, so the pitch is padded to 8 (mod 16) doubles: the two samples' unit-stride accesses then fall on disjoint

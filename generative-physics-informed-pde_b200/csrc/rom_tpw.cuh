@@ -40,25 +40,33 @@ struct TpwShape {
 };
 using TpwShape8x8 = TpwShape<63, 7, 128, 81, 2, 6, 2, 7>;
 
+// One record per band row, everything the row needs in one place (the pivot loop indexes the table with a run-time row:
+// as separate arrays in the constant bank every row entry cost ~10 cold constant-cache misses -- the tables are copied to
+// SHARED memory once per CTA instead and read there with uniform addresses).
 // element / dof entries are column offsets (index * kTpwPitch); padding terms have coefficient 0 and offset 0
 template <class S>
+struct TpwRow {
+    double diag_coef[S::TD];
+    double s1_coef[S::TO];      // A[i][i-1]
+    double sh_coef[S::TO];      // A[i][i-HBW]
+    double rhs_coef[S::TR];     // z_i = F[free_i] - sum_t rhs_coef * x[rhs_elem] * F[rhs_dof]
+    unsigned short diag_elem[S::TD], s1_elem[S::TO], sh_elem[S::TO], rhs_elem[S::TR], rhs_dof[S::TR];
+    unsigned short free_dof, pad[(8 - (S::TD + 2 * S::TO + 2 * S::TR + 1) % 8) % 8];
+};
+template <class S>
 struct TpwFwdTab {
-    double diag_coef[S::NFP * S::TD];
-    double s1_coef[S::NFP * S::TO];     // A[i][i-1]
-    double sh_coef[S::NFP * S::TO];     // A[i][i-HBW]
-    double rhs_coef[S::NFP * S::TR];    // z_i = F[free_i] - sum_t rhs_coef * x[rhs_elem] * F[rhs_dof]
-    unsigned short diag_elem[S::NFP * S::TD], s1_elem[S::NFP * S::TO], sh_elem[S::NFP * S::TO];
-    unsigned short rhs_elem[S::NFP * S::TR], rhs_dof[S::NFP * S::TR];
-    unsigned short free_dof[S::NFP];
+    TpwRow<S> row[S::NFP];
+    __device__ __forceinline__ int free_of(int k) const { return row[k].free_dof; }
 };
 template <class S>
 struct TpwAdjTab {
     double grad_coef[S::E * S::TG];                              // dL/dx_e = -sum_t grad_coef * lam[grad_i] * u[grad_j]
     double rhs_coef[S::NF * S::TR];                              // couplings K_fc (gradient w.r.t. F only)
     unsigned short grad_i[S::E * S::TG], grad_j[S::E * S::TG];   // dof columns (grad_i is a free dof)
-    unsigned short rhs_elem[S::NF * S::TR];                      // element INDEX (x is read from global memory there)
-    unsigned short rhs_dof[S::NF * S::TR];                       // dof column
-    unsigned short free_dof[S::NFP];
+    unsigned short rhs_elem[(S::NF * S::TR + 7) / 8 * 8];        // element INDEX (x is read from global memory there)
+    unsigned short rhs_dof[(S::NF * S::TR + 7) / 8 * 8];         // dof column
+    unsigned short free_dof[(S::NFP + 7) / 8 * 8];
+    __device__ __forceinline__ int free_of(int k) const { return free_dof[k]; }
 };
 
 template <class S>
@@ -122,25 +130,23 @@ __device__ __forceinline__ int tpw_conductivities(double *x, int x_is_log, unsig
 template <class S, int SLOT>
 __device__ __forceinline__ void tpw_enter_row(const TpwFwdTab<S> &tab, int r, const double *x, const double *f,
                                               double (&R)[S::W][S::W], double (&zw)[S::W]) {
+    const TpwRow<S> &row = tab.row[r];
     double d = 0.0, o1 = 0.0, oh = 0.0;
 #pragma unroll
-    for (int t = 0; t < S::TD; ++t) d = fma(tab.diag_coef[r * S::TD + t], x[tab.diag_elem[r * S::TD + t]], d);
+    for (int t = 0; t < S::TD; ++t) d = fma(row.diag_coef[t], x[row.diag_elem[t]], d);
 #pragma unroll
     for (int t = 0; t < S::TO; ++t) {
-        o1 = fma(tab.s1_coef[r * S::TO + t], x[tab.s1_elem[r * S::TO + t]], o1);
-        oh = fma(tab.sh_coef[r * S::TO + t], x[tab.sh_elem[r * S::TO + t]], oh);
+        o1 = fma(row.s1_coef[t], x[row.s1_elem[t]], o1);
+        oh = fma(row.sh_coef[t], x[row.sh_elem[t]], oh);
     }
     R[SLOT][0] = d;
     R[SLOT][1] = o1;
 #pragma unroll
     for (int s = 2; s < S::HBW; ++s) R[SLOT][s] = 0.0;
     R[SLOT][S::HBW] = oh;
-    double acc = f[tab.free_dof[r]];
+    double acc = f[row.free_dof];
 #pragma unroll
-    for (int t = 0; t < S::TR; ++t) {
-        const int k = r * S::TR + t;
-        acc = fma(-tab.rhs_coef[k] * x[tab.rhs_elem[k]], f[tab.rhs_dof[k]], acc);
-    }
+    for (int t = 0; t < S::TR; ++t) acc = fma(-row.rhs_coef[t] * x[row.rhs_elem[t]], f[row.rhs_dof[t]], acc);
     zw[SLOT] = acc;
 }
 
@@ -177,7 +183,7 @@ __device__ __forceinline__ void tpw_pivot(const TpwFwdTab<S> &tab, int kb, const
         const double wk = zw[J] * invd;
 #pragma unroll
         for (int s = 1; s <= HBW; ++s) zw[(J + s) % W] = fma(-R[(J + s) % W][s], wk, zw[(J + s) % W]);
-        f[tab.free_dof[k]] = wk;
+        f[tab.row[k].free_dof] = wk;
     }
 }
 template <class S, int... Js>
@@ -188,8 +194,8 @@ __device__ __forceinline__ void tpw_pivot_block(std::integer_sequence<int, Js...
 }
 
 // L^T sol = w with the stashed factor; w and then sol live in column ``v`` at the free dofs
-template <class S>
-__device__ __forceinline__ void tpw_backward_subst(const double *__restrict__ st, const unsigned short *free_dof, double *v) {
+template <class S, class Tab>
+__device__ __forceinline__ void tpw_backward_subst(const double *__restrict__ st, const Tab &tab, double *v) {
     constexpr int W = S::W, HBW = S::HBW, NF = S::NF, NB = S::NB;
     double sw[W];
 #pragma unroll
@@ -204,24 +210,36 @@ __device__ __forceinline__ void tpw_backward_subst(const double *__restrict__ st
                 double acc = 0.0;
 #pragma unroll
                 for (int s = 1; s <= HBW; ++s) acc = fma(col[s * kTpwThreads], sw[(j + s) % W], acc);
-                const double sol = fma(-col[0], acc, v[free_dof[k]]);
+                const int at = tab.free_of(k);
+                const double sol = fma(-col[0], acc, v[at]);
                 sw[j] = sol;
-                v[free_dof[k]] = sol;
+                v[at] = sol;
             }
         }
     }
 }
 
-// shared memory: [exp table 256][x: E columns][F -> u: N columns]
+// 16-byte copy of a plan table into shared memory (all threads)
+template <class Tab>
+__device__ __forceinline__ void tpw_table_to_smem(const Tab *__restrict__ src, Tab *dst) {
+    static_assert(sizeof(Tab) % 16 == 0, "tables are copied in 16-byte pieces");
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (int i = threadIdx.x; i < (int)(sizeof(Tab) / 16); i += kTpwThreads) d4[i] = s4[i];
+}
+
+// shared memory: [row table][exp table 256][x: E columns][F -> u: N columns]
 template <typename T, class S>
 __global__ void __launch_bounds__(kTpwThreads, 1)
-rom_tpw_forward_kernel(const __grid_constant__ TpwFwdTab<S> tab, const T *__restrict__ X, int x_is_log,
+rom_tpw_forward_kernel(const TpwFwdTab<S> *__restrict__ tab_g, const T *__restrict__ X, int x_is_log,
                        const T *__restrict__ F, T *__restrict__ u, double *__restrict__ stash, int *info, long long B) {
     extern __shared__ __align__(16) double tpw_smem[];
     constexpr int W = S::W, HBW = S::HBW, NB = S::NB;
-    double *etab = tpw_smem;
+    TpwFwdTab<S> &tab = *reinterpret_cast<TpwFwdTab<S> *>(tpw_smem);
+    double *etab = tpw_smem + sizeof(TpwFwdTab<S>) / sizeof(double);
     double *xs = etab + 256;
     double *fs = xs + S::E * kTpwPitch;
+    tpw_table_to_smem(tab_g, &tab);
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
     const int rows = (int)min((long long)kTpwThreads, B - b0);
     for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
@@ -244,25 +262,27 @@ rom_tpw_forward_kernel(const __grid_constant__ TpwFwdTab<S> tab, const T *__rest
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) tpw_pivot_block<S>(std::make_integer_sequence<int, W>{}, tab, kb, x, f, R, zw, st, bad);
     }
-    tpw_backward_subst<S>(st, tab.free_dof, f);
+    tpw_backward_subst<S>(st, tab, f);
     if ((int)threadIdx.x >= rows) bad = 0;
     if (bad && info) atomicOr(info, bad);
     __syncthreads();
     tpw_stage_out<T, S::N>(u, b0, rows, fs);
 }
 
-// shared memory: [exp table 256][gbar -> lambda: N columns][u: N columns][gradient chunk: kTpwGradChunk columns]
+// shared memory: [tables][exp table 256][gbar -> lambda: N columns][u: N columns][gradient chunk: kTpwGradChunk columns]
 template <typename T, class S, bool GRADF>
 __global__ void __launch_bounds__(kTpwThreads, 1)
-rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__restrict__ X, int x_is_log,
+rom_tpw_adjoint_kernel(const TpwAdjTab<S> *__restrict__ tab_g, const T *__restrict__ X, int x_is_log,
                        const T *__restrict__ u, const double *__restrict__ stash, const T *__restrict__ gbar,
                        T *__restrict__ gradX, T *__restrict__ gradF, long long B) {
     extern __shared__ __align__(16) double tpw_smem[];
     constexpr int W = S::W, HBW = S::HBW, NF = S::NF, NB = S::NB, EC = kTpwGradChunk;
     static_assert(S::E % EC == 0, "gradient chunks");
-    double *etab = tpw_smem;
+    TpwAdjTab<S> &tab = *reinterpret_cast<TpwAdjTab<S> *>(tpw_smem);
+    double *etab = tpw_smem + sizeof(TpwAdjTab<S>) / sizeof(double);
     double *gs = etab + 256;
     double *us = gs + S::N * kTpwPitch;
+    tpw_table_to_smem(tab_g, &tab);
     double *ds = us + S::N * kTpwPitch;
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
     const int rows = (int)min((long long)kTpwThreads, B - b0);
@@ -294,7 +314,7 @@ rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__rest
             }
         }
     }
-    tpw_backward_subst<S>(st, tab.free_dof, g);
+    tpw_backward_subst<S>(st, tab, g);
     if (GRADF && (int)threadIdx.x < rows) {
         // lambda on the constrained rows: gbar_c - sum_f K_cf lambda_f (x of the few boundary elements from global memory)
         const T *Xb = X + (b0 + threadIdx.x) * S::E;
@@ -357,11 +377,11 @@ rom_tpw_adjoint_kernel(const __grid_constant__ TpwAdjTab<S> tab, const T *__rest
 
 template <class S>
 constexpr size_t tpw_smem_forward() {
-    return sizeof(double) * (256 + (size_t)(S::E + S::N) * kTpwPitch);
+    return sizeof(TpwFwdTab<S>) + sizeof(double) * (256 + (size_t)(S::E + S::N) * kTpwPitch);
 }
 template <class S>
 constexpr size_t tpw_smem_adjoint() {
-    return sizeof(double) * (256 + (size_t)(2 * S::N + kTpwGradChunk) * kTpwPitch);
+    return sizeof(TpwAdjTab<S>) + sizeof(double) * (256 + (size_t)(2 * S::N + kTpwGradChunk) * kTpwPitch);
 }
 
 }  // namespace gpde
