@@ -76,10 +76,14 @@ __host__ __device__ constexpr size_t tpw_stash_doubles_per_block() {
 
 // Rows [b0, b0+rows) x [0, WD) of a row-major [B, WD] array into per-thread columns col[j * pitch + row], CH coalesced
 // loads in flight per thread; rows past the batch get ``fill``.
-template <typename T, int WD, int CH>
-__device__ __forceinline__ void tpw_stage_in(const T *__restrict__ src, long long b0, int rows, double fill, double *col) {
+// COND: the values are conductivities -- x = exp(v) + 1e-8 (components.py:298) applied on the way in when x_is_log, and
+// GPDE_INFO_NONPOSITIVE_X returned if some x <= 1e-12 (ROM.py:74-76); CH independent exp chains per thread.
+template <typename T, int WD, int CH, bool COND = false>
+__device__ __forceinline__ int tpw_stage_in(const T *__restrict__ src, long long b0, int rows, double fill, double *col,
+                                            int x_is_log = 0, unsigned etab = 0) {
     const T *p = src + b0 * WD;
     const int limit = rows * WD;
+    int bad = 0;
 #pragma unroll 1
     for (int k0 = 0; k0 < WD; k0 += CH) {
         T raw[CH];
@@ -93,10 +97,16 @@ __device__ __forceinline__ void tpw_stage_in(const T *__restrict__ src, long lon
             if (k0 + c < WD) {
                 const int i = threadIdx.x + (k0 + c) * kTpwThreads;
                 const int row = i / WD, j = i - row * WD;
-                col[j * kTpwPitch + row] = (double)raw[c];
+                double v = (double)raw[c];
+                if (COND) {
+                    if (x_is_log) v = (exp256_in_range(v) ? exp_tab256c(v, etab) : exp(v)) + 1e-8;
+                    if (!(v > 1e-12)) bad = GPDE_INFO_NONPOSITIVE_X;
+                }
+                col[j * kTpwPitch + row] = v;
             }
         }
     }
+    return bad;
 }
 
 template <typename T, int WD>
@@ -193,28 +203,43 @@ __device__ __forceinline__ void tpw_pivot_block(std::integer_sequence<int, Js...
     (tpw_pivot<S, Js>(tab, kb, x, f, R, zw, st, bad), ...);
 }
 
-// L^T sol = w with the stashed factor; w and then sol live in column ``v`` at the free dofs
+// Column k of the stashed factor (W entries) into registers; columns past the matrix read as zeros
+template <class S>
+__device__ __forceinline__ void tpw_load_column(const double *__restrict__ st, int k, double (&c)[S::W]) {
+    const double *col = st + (size_t)k * S::W * kTpwThreads;
+    const bool in = k >= 0 && k < S::NF;
+#pragma unroll
+    for (int s = 0; s < S::W; ++s) c[s] = in ? col[s * kTpwThreads] : 0.0;
+}
+
+// L^T sol = w with the stashed factor; w and then sol live in column ``v`` at the free dofs.  A rotating register buffer
+// holds the next W factor columns: as soon as a column has been used, the one W pivots further on is fetched into its slot,
+// so every load is W pivots of dependent arithmetic ahead of its use: with one warp per scheduler nothing else hides the
+// L2 / HBM latency (36 % of the forward kernel's samples sat on these loads before)
 template <class S, class Tab>
 __device__ __forceinline__ void tpw_backward_subst(const double *__restrict__ st, const Tab &tab, double *v) {
     constexpr int W = S::W, HBW = S::HBW, NF = S::NF, NB = S::NB;
-    double sw[W];
+    double sw[W], cur[W][W];
 #pragma unroll
-    for (int j = 0; j < W; ++j) sw[j] = 0.0;
+    for (int j = 0; j < W; ++j) {
+        sw[j] = 0.0;
+        tpw_load_column<S>(st, (NB - 1) * W + j, cur[j]);
+    }
 #pragma unroll 1
     for (int kb = NB - 1; kb >= 0; --kb) {
 #pragma unroll
         for (int j = W - 1; j >= 0; --j) {
             const int k = kb * W + j;
             if (k < NF) {
-                const double *col = st + (size_t)k * W * kTpwThreads;
                 double acc = 0.0;
 #pragma unroll
-                for (int s = 1; s <= HBW; ++s) acc = fma(col[s * kTpwThreads], sw[(j + s) % W], acc);
+                for (int s = 1; s <= HBW; ++s) acc = fma(cur[j][s], sw[(j + s) % W], acc);
                 const int at = tab.free_of(k);
-                const double sol = fma(-col[0], acc, v[at]);
+                const double sol = fma(-cur[j][0], acc, v[at]);
                 sw[j] = sol;
                 v[at] = sol;
             }
+            tpw_load_column<S>(st, k - W, cur[j]);
         }
     }
 }
@@ -243,12 +268,13 @@ rom_tpw_forward_kernel(const TpwFwdTab<S> *__restrict__ tab_g, const T *__restri
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
     const int rows = (int)min((long long)kTpwThreads, B - b0);
     for (int i = threadIdx.x; i < 256; i += kTpwThreads) etab[i] = kExp256Tab[i];
-    // (64 coalesced loads in flight per thread: the staging is a chain of DRAM round trips, one per chunk)
-    tpw_stage_in<T, S::E, 64>(X, b0, rows, x_is_log ? 0.0 : 1.0, xs);
+    __syncthreads();      // the exp table is used while staging
+    // (32 coalesced loads in flight per thread: the staging is a chain of DRAM round trips, one per chunk; the conductivities
+    // get their exp() on the way in -- 32 independent chains per thread instead of a second pass over shared memory)
+    int bad = tpw_stage_in<T, S::E, 32, true>(X, b0, rows, x_is_log ? 0.0 : 1.0, xs, x_is_log, smem_u32_of(etab));
     tpw_stage_in<T, S::N, 41>(F, b0, rows, 0.0, fs);
     __syncthreads();
     double *x = xs + threadIdx.x, *f = fs + threadIdx.x;
-    int bad = tpw_conductivities<S::E>(x, x_is_log, smem_u32_of(etab));
     double *st = stash + (size_t)blockIdx.x * tpw_stash_doubles_per_block<S>() + threadIdx.x;
     {
         double R[W][W], zw[W];
@@ -263,7 +289,8 @@ rom_tpw_forward_kernel(const TpwFwdTab<S> *__restrict__ tab_g, const T *__restri
         for (int kb = 0; kb < NB; ++kb) tpw_pivot_block<S>(std::make_integer_sequence<int, W>{}, tab, kb, x, f, R, zw, st, bad);
     }
     tpw_backward_subst<S>(st, tab, f);
-    if ((int)threadIdx.x >= rows) bad = 0;
+    // (the staging flags belong to whatever rows a thread copied, the factor flag to its own sample: rows past the batch
+    // were filled with harmless values, so every flag raised is a real one)
     if (bad && info) atomicOr(info, bad);
     __syncthreads();
     tpw_stage_out<T, S::N>(u, b0, rows, fs);
@@ -293,11 +320,13 @@ rom_tpw_adjoint_kernel(const TpwAdjTab<S> *__restrict__ tab_g, const T *__restri
     double *g = gs + threadIdx.x;
     const double *uu = us + threadIdx.x;
     const double *st = stash + (size_t)blockIdx.x * tpw_stash_doubles_per_block<S>() + threadIdx.x;
-    {   // w = D^-1 L^-1 gbar_f, window of W values
-        double zw[W];
+    {   // w = D^-1 L^-1 gbar_f, window of W values; the next block's factor columns are fetched ahead of the chain
+        double zw[W], cur[W][W];
 #pragma unroll
         for (int j = 0; j < HBW; ++j) zw[j] = g[tab.free_dof[j]];
         zw[HBW] = 0.0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) tpw_load_column<S>(st, j, cur[j]);
 #pragma unroll 1
         for (int kb = 0; kb < NB; ++kb) {
 #pragma unroll
@@ -305,12 +334,12 @@ rom_tpw_adjoint_kernel(const TpwAdjTab<S> *__restrict__ tab_g, const T *__restri
                 const int k = kb * W + j;
                 zw[(j + HBW) % W] = g[tab.free_dof[k + HBW]];     // phantom rows read column 0: never used (their L entries are 0)
                 if (k < NF) {
-                    const double *col = st + (size_t)k * W * kTpwThreads;
-                    const double wk = zw[j] * col[0];
+                    const double wk = zw[j] * cur[j][0];
 #pragma unroll
-                    for (int s = 1; s <= HBW; ++s) zw[(j + s) % W] = fma(-col[s * kTpwThreads], wk, zw[(j + s) % W]);
+                    for (int s = 1; s <= HBW; ++s) zw[(j + s) % W] = fma(-cur[j][s], wk, zw[(j + s) % W]);
                     g[tab.free_dof[k]] = wk;
                 }
+                tpw_load_column<S>(st, k + W, cur[j]);
             }
         }
     }
