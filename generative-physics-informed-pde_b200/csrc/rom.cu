@@ -426,7 +426,7 @@ template <class S>
 static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<int> &free_dof, const std::vector<int> &bc_dof,
                              const std::vector<unsigned char> &is_bc, const double *M, TpwFwdTab<S> &Ft, TpwAdjTab<S> &At) {
     if (n != S::N || E != S::E || nf != S::NF || hbw != S::HBW) return false;
-    static_assert(S::E * kTpwPitch < 65536 && S::N * kTpwPitch < 65536, "column offsets are 16-bit");
+    static_assert(S::E * kTpwPitch < 65536 && (S::N + 1) * kTpwPitch < 65536, "column offsets are 16-bit");
     auto Mat = [&](int i, int j, int e) { return M[((size_t)i * n + j) * E + e]; };
     memset(&Ft, 0, sizeof(Ft));
     memset(&At, 0, sizeof(At));
@@ -470,18 +470,38 @@ static bool build_tpw_tables(int n, int E, int nf, int hbw, const std::vector<in
                 ++cnt;
             }
     }
+    // gradient in edge form (rom_tpw.cuh): every element matrix must be symmetric with zero row sums
     for (int e = 0; e < E; ++e) {
-        int cnt = 0;
+        std::vector<int> verts;
         for (int i = 0; i < n; ++i) {
-            if (is_bc[i]) continue;   // overwritten rows contribute nothing
-            for (int j = 0; j < n; ++j) {
-                const double v = Mat(i, j, e);
-                if (v == 0.0) continue;
-                if (cnt == S::TG) return false;
-                const int k = e * S::TG + cnt;
-                At.grad_coef[k] = v;
-                At.grad_i[k] = (unsigned short)(i * kTpwPitch);
-                At.grad_j[k] = (unsigned short)(j * kTpwPitch);
+            bool used = false;
+            for (int j = 0; j < n; ++j)
+                if (Mat(i, j, e) != 0.0 || Mat(j, i, e) != 0.0) used = true;
+            if (used) verts.push_back(i);
+        }
+        double scale = 0.0;
+        for (int i : verts)
+            for (int j : verts) scale = std::max(scale, std::fabs(Mat(i, j, e)));
+        const double tol = 1e-12 * scale;
+        int cnt = 0;
+        for (size_t a = 0; a < verts.size(); ++a) {
+            double rs = 0.0;
+            for (size_t b = 0; b < verts.size(); ++b) {
+                rs += Mat(verts[a], verts[b], e);
+                if (std::fabs(Mat(verts[a], verts[b], e) - Mat(verts[b], verts[a], e)) > tol) return false;
+            }
+            if (std::fabs(rs) > 1e-9 * scale) return false;
+            for (size_t b = a + 1; b < verts.size(); ++b) {
+                const double w = -Mat(verts[a], verts[b], e);
+                if (w == 0.0) continue;
+                if (cnt == kTpwEdges) return false;
+                const int k = e * kTpwEdges + cnt;
+                At.edge_w[k] = w;
+                const int va = verts[a], vb = verts[b];
+                At.lam_a[k] = (unsigned short)((is_bc[va] ? n : va) * kTpwPitch);     // column n of the lambda array holds zeros
+                At.lam_b[k] = (unsigned short)((is_bc[vb] ? n : vb) * kTpwPitch);
+                At.u_a[k] = (unsigned short)(va * kTpwPitch);
+                At.u_b[k] = (unsigned short)(vb * kTpwPitch);
                 ++cnt;
             }
         }

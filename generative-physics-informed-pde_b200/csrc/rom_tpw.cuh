@@ -58,11 +58,20 @@ struct TpwFwdTab {
     TpwRow<S> row[S::NFP];
     __device__ __forceinline__ int free_of(int k) const { return row[k].free_dof; }
 };
+// Gradient in EDGE form: a symmetric element matrix with zero row sums is K_e = sum over its edges (a,b) of
+// w_ab (e_a - e_b)(e_a - e_b)^T with w_ab = -K_e[a][b], so
+//     dL/dx_e = - lam~^T K_e u = - sum_edges w_ab (lam~_a - lam~_b)(u_a - u_b),   lam~ = lam on free dofs, 0 on constrained ones
+// (rows of constrained dofs were overwritten and contribute nothing).  2 edges of a right triangle carry a
+// weight (the hypotenuse does not couple): 4 values, 2 subtractions, a multiplication and an FMA per edge instead of the 7
+// coefficient terms with 14 values of the entry-by-entry form (the gradient loop was 42 % of the adjoint kernel's samples).
+// lam offsets of constrained dofs point to a column of zeros.
+constexpr int kTpwEdges = 3;
 template <class S>
 struct TpwAdjTab {
-    double grad_coef[S::E * S::TG];                              // dL/dx_e = -sum_t grad_coef * lam[grad_i] * u[grad_j]
+    double edge_w[S::E * kTpwEdges];
     double rhs_coef[S::NF * S::TR];                              // couplings K_fc (gradient w.r.t. F only)
-    unsigned short grad_i[S::E * S::TG], grad_j[S::E * S::TG];   // dof columns (grad_i is a free dof)
+    unsigned short lam_a[S::E * kTpwEdges], lam_b[S::E * kTpwEdges];   // lambda columns of the edge's ends (zero column if constrained)
+    unsigned short u_a[S::E * kTpwEdges], u_b[S::E * kTpwEdges];       // u columns of the edge's ends
     unsigned short rhs_elem[(S::NF * S::TR + 7) / 8 * 8];        // element INDEX (x is read from global memory there)
     unsigned short rhs_dof[(S::NF * S::TR + 7) / 8 * 8];         // dof column
     unsigned short free_dof[(S::NFP + 7) / 8 * 8];
@@ -307,8 +316,9 @@ rom_tpw_adjoint_kernel(const TpwAdjTab<S> *__restrict__ tab_g, const T *__restri
     static_assert(S::E % EC == 0, "gradient chunks");
     TpwAdjTab<S> &tab = *reinterpret_cast<TpwAdjTab<S> *>(tpw_smem);
     double *etab = tpw_smem + sizeof(TpwAdjTab<S>) / sizeof(double);
-    double *gs = etab + 256;
-    double *us = gs + S::N * kTpwPitch;
+    double *gs = etab + 256;                        // N columns + one column of zeros (lambda~ of constrained dofs)
+    double *us = gs + (S::N + 1) * kTpwPitch;
+    gs[S::N * kTpwPitch + threadIdx.x] = 0.0;
     tpw_table_to_smem(tab_g, &tab);
     double *ds = us + S::N * kTpwPitch;
     const long long b0 = (long long)blockIdx.x * kTpwThreads;
@@ -366,37 +376,37 @@ rom_tpw_adjoint_kernel(const TpwAdjTab<S> *__restrict__ tab_g, const T *__restri
     double *dcol = ds + threadIdx.x;
 #pragma unroll 1
     for (int c0 = 0; c0 < S::E; c0 += EC) {
-#pragma unroll 1
+        // the conductivity inputs this thread will need for the round's output (entries threadIdx.x + 128 it of the CTA's
+        // [rows][EC] block) are requested first: they arrive while the round's gradient entries are computed
+        T xv[EC];
+#pragma unroll
+        for (int it = 0; it < EC; ++it) {
+            const int i = threadIdx.x + it * kTpwThreads;
+            const int row = i / EC, j = i - row * EC;
+            xv[it] = (x_is_log && i < rows * EC) ? X[(b0 + row) * S::E + c0 + j] : (T)0;
+        }
+#pragma unroll 2
         for (int e = 0; e < EC; ++e) {
             double acc = 0.0;
 #pragma unroll
-            for (int t = 0; t < S::TG; ++t) {
-                const int k = (c0 + e) * S::TG + t;
-                acc = fma(tab.grad_coef[k] * g[tab.grad_i[k]], uu[tab.grad_j[k]], acc);
+            for (int t = 0; t < kTpwEdges; ++t) {
+                const int k = (c0 + e) * kTpwEdges + t;
+                acc = fma(tab.edge_w[k] * (g[tab.lam_a[k]] - g[tab.lam_b[k]]), uu[tab.u_a[k]] - uu[tab.u_b[k]], acc);
             }
             dcol[e * kTpwPitch] = -acc;
         }
         __syncthreads();
-        // EC entries per thread and round (fewer in the last CTA); the conductivity inputs of 8 entries are fetched together:
-        // one global round trip per 8 entries instead of one per entry
-#pragma unroll 1
-        for (int it0 = 0; it0 < EC; it0 += 8) {
-            double xv[8];
 #pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) {
-                const int i = threadIdx.x + (it0 + w8) * kTpwThreads;
+        for (int it = 0; it < EC; ++it) {
+            const int i = threadIdx.x + it * kTpwThreads;
+            if (i < rows * EC) {
                 const int row = i / EC, j = i - row * EC;
-                xv[w8] = (x_is_log && i < rows * EC) ? (double)X[(b0 + row) * S::E + c0 + j] : 0.0;
-            }
-#pragma unroll
-            for (int w8 = 0; w8 < 8; ++w8) {
-                const int i = threadIdx.x + (it0 + w8) * kTpwThreads;
-                if (i < rows * EC) {
-                    const int row = i / EC, j = i - row * EC;
-                    double v = ds[j * kTpwPitch + row];
-                    if (x_is_log) v *= exp256_in_range(xv[w8]) ? exp_tab256c(xv[w8], smem_u32_of(etab)) : exp(xv[w8]);
-                    gradX[(b0 + row) * S::E + c0 + j] = (T)v;
+                double v = ds[j * kTpwPitch + row];
+                if (x_is_log) {
+                    const double xd = (double)xv[it];
+                    v *= exp256_in_range(xd) ? exp_tab256c(xd, smem_u32_of(etab)) : exp(xd);
                 }
+                gradX[(b0 + row) * S::E + c0 + j] = (T)v;
             }
         }
         __syncthreads();
@@ -410,7 +420,7 @@ constexpr size_t tpw_smem_forward() {
 }
 template <class S>
 constexpr size_t tpw_smem_adjoint() {
-    return sizeof(TpwAdjTab<S>) + sizeof(double) * (256 + (size_t)(2 * S::N + kTpwGradChunk) * kTpwPitch);
+    return sizeof(TpwAdjTab<S>) + sizeof(double) * (256 + (size_t)(2 * S::N + 1 + kTpwGradChunk) * kTpwPitch);
 }
 
 }  // namespace gpde
