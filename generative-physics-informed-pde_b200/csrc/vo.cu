@@ -46,6 +46,7 @@ constexpr int kVoThreads = 256;
 #include "vo_grid2.cuh"
 #include "vo_expand.cuh"
 #include "vo_gemm.cuh"
+#include "vo_gridgemm.cuh"
 #include "vo_posterior.cuh"
 
 namespace gpde {
@@ -64,6 +65,7 @@ struct VoEnv {
     bool expand_gemm = false;    // GPDE_VO_EXPAND=gemm
     int gemm_splits = 0;         // GPDE_GEMM_SPLITS: parts of the contraction length (0 = automatic)
     int grid2_split = 1;         // GPDE_GRID2_SPLIT: 0 = never cut the node rows over a cluster, 1 = automatic, n > 1 = force n
+    bool gridgemm = true;        // GPDE_VO_GRIDGEMM=0: rho through HBM + vo_gemm_kernel instead of the one-kernel route (m > 32)
     VoEnv() {
         const char *e;
         if ((e = getenv("GPDE_GRID_R"))) grid_r = atoi(e);
@@ -77,6 +79,7 @@ struct VoEnv {
         if ((e = getenv("GPDE_VO_EXPAND"))) expand_gemm = strcmp(e, "gemm") == 0;
         if ((e = getenv("GPDE_GEMM_SPLITS"))) gemm_splits = std::max(0, std::min(8, atoi(e)));
         if ((e = getenv("GPDE_GRID2_SPLIT"))) grid2_split = std::max(0, std::min(8, atoi(e)));
+        if ((e = getenv("GPDE_VO_GRIDGEMM"))) gridgemm = atoi(e) != 0;
     }
 };
 }  // namespace gpde
@@ -791,6 +794,66 @@ static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride
     return GPDE_OK;
 }
 
+// Many weighting functions on the reference's pixel meshes: rho produced inside the contraction kernel (vo_gridgemm.cuh).
+// Returns 1 if it served the call, 0 if the two-kernel route should, < 0 on error.
+static bool gridgemm_setup(const gpde_vo_plan *pl, int m, int sub_f, int elem, GGDev &G, int &bn, size_t &smem) {
+    Grid2Dev G2;
+    int nt2, nx2;
+    size_t smem2;
+    if (!pl->env.gridgemm || m <= 32 || !use_grid(pl) || !grid2_setup(pl, 0, true, sub_f, G2, nt2, nx2, smem2, elem, elem)) return false;
+    memset(&G, 0, sizeof(G));
+    G.nx = G2.nx; G.ny = G2.ny; G.ncol = G2.ncol; G.nstrips = G2.nstrips;
+    G.in0 = G2.in0; G.sy = G2.sy; G.rh = G2.rh; G.scale = G2.scale;
+    bn = m <= 128 ? 128 : 256;
+    G.ctiles = (m + bn - 1) / bn;
+    for (G.stages_b = 4; G.stages_b >= 2; --G.stages_b)
+        if ((smem = gg_smem_bytes(bn, G.stages_b, elem)) <= 227 * 1024) return true;
+    return false;
+}
+static size_t gridgemm_workspace_bytes(const gpde_vo_plan *pl, long long B, int m) {
+    GGDev G;
+    int bn;
+    size_t smem;
+    if (!gridgemm_setup(pl, m, 0, 8, G, bn, smem)) return 0;
+    return gg_packed_bytes(bn, G.ctiles, G.nstrips * (G.ny + 1)) + 16 + sizeof(double) * 8 * (size_t)B * G.ctiles * bn;
+}
+template <typename T>
+static int launch_gridgemm(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *y, const T *g,
+                           long long g_stride, const T *V, int m, T *r, void *workspace, int sub_f, long long B,
+                           cudaStream_t st) {
+    GGDev G;
+    int bn;
+    size_t smem;
+    if (((uintptr_t)workspace & 15) || !gridgemm_setup(pl, m, sub_f, (int)sizeof(T), G, bn, smem)) return 0;
+    const int chunks = G.nstrips * (G.ny + 1);
+    double *Vp = (double *)workspace;
+    const long long tiles = (B + kGGBM - 1) / kGGBM * G.ctiles;
+    int splits = pl->env.gemm_splits > 0 ? pl->env.gemm_splits : gemm_splits(tiles, pl->n_sm, chunks);
+    splits = std::max(1, std::min(splits, G.nstrips));
+    const int ldp = G.ctiles * bn;
+    double *partial = splits > 1 ? (double *)(((uintptr_t)Vp + gg_packed_bytes(bn, G.ctiles, chunks) + 15) & ~(uintptr_t)15) : nullptr;
+    const dim3 grid((unsigned)((B + kGGBM - 1) / kGGBM), (unsigned)G.ctiles, (unsigned)splits);
+    const unsigned pgrid = (unsigned)std::min<long long>(((long long)G.ctiles * chunks + 7) / 8, (long long)pl->n_sm * 8);
+#define GPDE_LAUNCH_GG(BNV, ALOGV)                                                                                \
+    {                                                                                                             \
+        vo_gridgemm_pack_kernel<BNV, T><<<pgrid, 256, 0, st>>>(G, V, m, Vp);                                      \
+        auto kern = vo_gridgemm_kernel<BNV, ALOGV, T, T>;                                                         \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        kern<<<grid, kGGThreads, smem, st>>>(G, a, a_stride, y, g, g_stride, Vp, r, m, ldp, B, partial);          \
+    }
+    if (bn == 128) { if (a_is_log) GPDE_LAUNCH_GG(128, true) else GPDE_LAUNCH_GG(128, false) }
+    else           { if (a_is_log) GPDE_LAUNCH_GG(256, true) else GPDE_LAUNCH_GG(256, false) }
+#undef GPDE_LAUNCH_GG
+    GPDE_CUDA_OK(cudaGetLastError());
+    if (splits > 1) {
+        const long long total = B * m;
+        const unsigned rgrid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 16);
+        vo_gemm_reduce_kernel<T><<<rgrid, 256, 0, st>>>(partial, splits, ldp, r, m, B);
+        GPDE_CUDA_OK(cudaGetLastError());
+    }
+    return 1;
+}
+
 template <typename T>
 static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int a_is_log, const T *y, const T *g,
                        int64_t g_stride, const T *V, int m, T *r, T *rho, void *workspace, int flags, int64_t B,
@@ -839,6 +902,11 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
 #undef GPDE_LAUNCH_FUSED
         GPDE_CUDA_OK(cudaGetLastError());
         return GPDE_OK;
+    }
+    if (m > 32 && !rho && use_grid(pl)) {   // many weighting functions on a pixel mesh: one kernel, rho never leaves the SM
+        const int rc = launch_gridgemm<T>(pl, a, (long long)a_stride, a_is_log, y, g, (long long)g_stride, V, m, r, workspace,
+                                          (flags & 1) ? 0 : 1, (long long)B, st);
+        if (rc != 0) return rc < 0 ? rc : GPDE_OK;
     }
     // version 1: rho -> K-padded workspace, then the FP64 tensor-core contraction (vo_gemm.cuh)
     const int d = pl->dev.d, dp = gemm_dp(d);
@@ -1144,6 +1212,7 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
         const size_t mp = (size_t)gemm_dp(m), ldb = ((size_t)pl->dev.d + 127) / 128 * 128;
         need = std::max(need, sizeof(double) * ((size_t)B * mp + mp * ldb + (size_t)B * pl->dev.d));
     }
+    if (m > 32) need = std::max(need, gridgemm_workspace_bytes(pl, (long long)B, m));
     if (pl->grid.ok && m > 0 && m <= 32)   // packed V (+ the per-row tile masks of the lean kernel)
         need = std::max(need, grid_packed_bytes(pl->grid, 4) + (size_t)(pl->grid.ny + 1) * kGrid2MaskBytes);
     return need;

@@ -1,0 +1,367 @@
+// Structured-grid virtual-observable residual for MANY weighting functions (m > 64), one kernel (sm_100a).
+// Included by vo.cu after vo_grid2.cuh and vo_gemm.cuh.
+//
+//   r[b,:] = V^T (K_fom(a_b) u~_b - f)_free        (VirtualObservables.py:61-69, 662, 990)
+//
+// vo_grid2_kernel<rho> + vo_gemm_kernel move the fine residual rho [B,d] through HBM (2.1 GB written and read at BASELINE
+// config 3: ~1.1 of 5.5 ms).  Here the CTA that contracts a tile of 64 samples with V also PRODUCES the tile's rho values,
+// 16 nodes of one node row at a time, straight into the A operand of the contraction in shared memory:
+//   * the contraction index runs strip-major: strip q (16 node columns), node rows bottom to top inside the strip; a chunk
+//     = the 16 nodes (q, t) -- V is re-packed in this order, one chunk = one contiguous stage image [16][BN + 4] with the
+//     chunk's tile mask in the padding, fetched by ONE bulk copy (TMA engine) two chunks ahead;
+//   * four producer warps, one per scheduler (32 samples x 8 node columns each, lane = sample), march up the strip with
+//     their own window of node rows of y and pixel rows of a in shared memory (cp.async one step ahead, 8 lanes per sample
+//     row segment; Dirichlet columns come from g the same way), form the flux-form residual of the row (same expressions
+//     and order as vo_grid2.cuh) and write their quarter of the 64 x 16 tile K-major;
+//   * eight consumer warps (2 x 4, warp tile 32 x BN/4, n-tiles interleaved over the warps) run DMMA.8x8x4 out of the
+//     two rings; an n-tile whose 16 x 8 block of V is all zero in this chunk is skipped (exact: it drops products with 0
+//     -- the coarse-grained-residual columns W, VirtualObservables.py:297-321, are P1 hat functions: 1-3 of their 10
+//     n-tiles are non-zero in a chunk);
+//   * roles get their registers by setmaxnreg (consumers 200, producers / loader 96: 384 x 168 registers are allocated at launch); full / empty mbarriers per stage.
+// The contraction length is cut over gridDim.z by whole strips (partial tiles + vo_gemm_reduce_kernel, deterministic).
+#pragma once
+
+namespace gpde {
+
+constexpr int kGGBM = 64;                 // samples per CTA
+constexpr int kGGKC = 16;                 // nodes per chunk
+constexpr int kGGThreads = 384;           // 8 consumer warps + 4 producer warps
+constexpr int kGGStagesA = 2;
+constexpr int kGGLdA = kGGBM + 4;         // doubles per k row of the rho tile (= 4 mod 16: conflict-free fragment loads)
+// a producer warp's window: 3 slots of 10 y columns (8 nodes + halo), 3 slots of 9 pixel columns, one slot of zeros (the
+// rows outside the mesh); a column holds the warp's 32 samples at pitch 34 (FP64) / 36 (FP32) elements: the copies of a
+// quarter-warp per sample and the reads of a lane per sample are both conflict-free
+constexpr int kGGYC = 10, kGGAC = 9, kGGWinCols = 3 * kGGYC + 3 * kGGAC + kGGYC;
+static inline __host__ __device__ constexpr int gg_win_pitch(int elem) { return elem == 8 ? 34 : 36; }
+
+struct GGDev {
+    int nx, ny, ncol, nstrips;
+    long long in0, sy;       // conductivity entry of pixel (cx, cy) = in0 + cy * sy + cx
+    double rh, scale;
+    int ctiles;              // column tiles of BN
+    int stages_b;            // V stages in the ring
+};
+
+static inline size_t gg_smem_bytes(int bn, int stages_b, int elem) {
+    return (size_t)stages_b * sizeof(double) * kGGKC * (bn + 4) + (size_t)kGGStagesA * sizeof(double) * kGGKC * kGGLdA +
+           (size_t)4 * elem * gg_win_pitch(elem) * kGGWinCols + 16 +
+           sizeof(unsigned long long) * (2 * kGGStagesA + 2 * 8) + 256 * sizeof(double);
+}
+static inline size_t gg_packed_bytes(int bn, int ctiles, int chunks) {
+    return (size_t)ctiles * chunks * sizeof(double) * kGGKC * (bn + 4);
+}
+
+// V[d,m] row-major -> [column tile][chunk (q, t)][k < 16][BN + 4]; row k of chunk (q, t) = node row t, free column 16 q + k
+// (zero past the last free column and past column m); the 4 padding doubles of row 0 hold the chunk's tile mask
+// (bit j <=> the 16 x 8 block of columns 8 j .. 8 j + 7 has a non-zero entry), the other padding is zero.
+template <int BN, typename TV>
+__global__ void vo_gridgemm_pack_kernel(GGDev G, const TV *__restrict__ V, int m, double *__restrict__ Vp) {
+    constexpr int LdB = BN + 4, SEG = BN / 32;
+    const int chunks = G.nstrips * (G.ny + 1);
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp; w < (long long)G.ctiles * chunks; w += nwarps) {
+        const int ct = (int)(w / chunks), ch = (int)(w - (long long)ct * chunks);
+        const int q = ch / (G.ny + 1), t = ch - q * (G.ny + 1);
+        double *dst = Vp + (size_t)w * kGGKC * LdB;
+        unsigned nz[SEG];
+#pragma unroll
+        for (int sg = 0; sg < SEG; ++sg) nz[sg] = 0;
+        for (int k = 0; k < kGGKC; ++k) {
+            const int c = 16 * q + k;
+            const TV *src = V + ((long long)t * G.ncol + c) * m;
+#pragma unroll
+            for (int sg = 0; sg < SEG; ++sg) {
+                const int col = ct * BN + sg * 32 + lane;
+                const double v = (c < G.ncol && col < m) ? (double)src[col] : 0.0;
+                dst[k * LdB + sg * 32 + lane] = v;
+                nz[sg] |= (v != 0.0) ? 1u : 0u;
+            }
+            if (lane < 4 && k > 0) dst[k * LdB + BN + lane] = 0.0;
+        }
+        unsigned mask = 0;
+#pragma unroll
+        for (int sg = 0; sg < SEG; ++sg) {
+            const unsigned bal = __ballot_sync(0xffffffffu, nz[sg] != 0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if ((bal >> (8 * u)) & 0xffu) mask |= 1u << (sg * 4 + u);
+        }
+        if (lane == 0) {
+            unsigned *mw = reinterpret_cast<unsigned *>(dst + BN);
+            mw[0] = mask;
+            for (int i = 1; i < 8; ++i) mw[i] = 0;
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ void gg_cp_async_elem(unsigned dst, const T *src);
+template <> __device__ __forceinline__ void gg_cp_async_elem<double>(unsigned dst, const double *src) { cp_async8_u32(dst, src); }
+template <> __device__ __forceinline__ void gg_cp_async_elem<float>(unsigned dst, const float *src) { cp_async4_u32(dst, src); }
+template <typename T> __device__ __forceinline__ void gg_sts_elem(unsigned dst, double v);
+template <> __device__ __forceinline__ void gg_sts_elem<double>(unsigned dst, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(dst), "d"(v) : "memory");
+}
+template <> __device__ __forceinline__ void gg_sts_elem<float>(unsigned dst, double v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"((float)v) : "memory");
+}
+
+// grid: (sample tiles of 64, column tiles of BN, parts of the contraction length = groups of whole strips)
+template <int BN, bool ALOG, typename T, typename TR>
+__global__ void __launch_bounds__(kGGThreads, 1)
+vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T *__restrict__ y, const T *__restrict__ g,
+                   long long g_stride, const double *__restrict__ Vp, TR *__restrict__ R, int m, int ldp, long long B,
+                   double *__restrict__ partial) {
+    constexpr int LdB = BN + 4, NT = BN / 32;     // n-tiles per consumer warp (4 warps along N, interleaved)
+    constexpr int A_STAGE = kGGKC * kGGLdA, B_STAGE = kGGKC * LdB;
+    constexpr int E = (int)sizeof(T), P = E == 8 ? 34 : 36;
+    constexpr int WIN_BYTES = kGGWinCols * P * E;                 // one producer warp's window
+    extern __shared__ __align__(128) unsigned char gg_smem[];
+    const int SB = G.stages_b;
+    double *Bs = reinterpret_cast<double *>(gg_smem);
+    double *As = Bs + (size_t)SB * B_STAGE;
+    unsigned char *win = reinterpret_cast<unsigned char *>(As + kGGStagesA * A_STAGE);
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(win + 4 * WIN_BYTES) + 15) & ~(uintptr_t)15);
+    unsigned long long *fullA = bars, *emptyA = bars + kGGStagesA, *fullB = bars + 2 * kGGStagesA, *emptyB = fullB + 8;
+    double *tab = reinterpret_cast<double *>(emptyB + 8);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long row0 = (long long)blockIdx.x * kGGBM;
+    const int rows_per_strip = G.ny + 1;
+    const int q_lo = (int)((long long)G.nstrips * blockIdx.z / gridDim.z), q_hi = (int)((long long)G.nstrips * (blockIdx.z + 1) / gridDim.z);
+    const int n_chunks = (q_hi - q_lo) * rows_per_strip;
+    const long long chunk0 = (long long)blockIdx.y * G.nstrips * rows_per_strip + (long long)q_lo * rows_per_strip;
+
+    // ---- setup: windows zeroed (rows outside the mesh and the slots of samples past the batch read as 0), barriers, exp table
+    {
+        unsigned *w32 = reinterpret_cast<unsigned *>(win);
+        for (int i = tid; i < (4 * WIN_BYTES) >> 2; i += kGGThreads) w32[i] = 0u;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kGGStagesA; ++i) { mbar_init(fullA + i, 128); mbar_init(emptyA + i, 8); }
+        for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (ALOG && tid < 256) tab[tid] = kExp256Tab[tid];
+    __syncthreads();
+
+    if (warp < 8) {
+        // =================================================== consumers: DMMA out of the two rings
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        const int wm = warp & 1, wn = warp >> 1;
+        const int gq = lane >> 2, tq = lane & 3;
+        double acc[4][NT][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        const unsigned as0 = smem_u32(As) + 8u * (tq * kGGLdA + wm * 32 + gq);      // + stage, + ks * 4 * LdA, + mt * 8
+        const unsigned bs0 = smem_u32(Bs) + 8u * (tq * LdB + wn * 8 + gq);          // + stage, + ks * 4 * LdB, + nt * 32
+        const unsigned mk0 = smem_u32(Bs) + 8u * BN;
+        int sa = 0, sb = 0;
+        unsigned pa = 0, pb = 0;
+        for (int kc = 0; kc < n_chunks; ++kc) {
+            mbar_wait(fullB + sb, pb);
+            mbar_wait(fullA + sa, pa);
+            const unsigned ab = as0 + sa * (A_STAGE * 8), bb = bs0 + sb * (B_STAGE * 8);
+            unsigned mask;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mask) : "r"(mk0 + sb * (B_STAGE * 8)));
+            double af[4][4];
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) af[ks][mt] = lds64(ab + 8u * (ks * 4 * kGGLdA + mt * 8));
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                if ((mask >> (wn + 4 * nt)) & 1u) {
+                    double bf[4];
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) bf[ks] = lds64(bb + 8u * (ks * 4 * LdB + nt * 32));
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+                        for (int mt = 0; mt < 4; ++mt) dmma884(acc[mt][nt][0], acc[mt][nt][1], af[ks][mt], bf[ks]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(emptyA + sa); mbar_arrive(emptyB + sb); }
+            if (++sa == kGGStagesA) { sa = 0; pa ^= 1; }
+            if (++sb == SB) { sb = 0; pb ^= 1; }
+        }
+        // epilogue: lane holds C[row = lane / 4][cols 2 (lane % 4), + 1] of every 8 x 8 tile
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+            const long long row = row0 + wm * 32 + mt * 8 + gq;
+            if (row >= B) continue;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const int col = blockIdx.y * BN + (wn + 4 * nt) * 8 + 2 * tq;
+                if (partial) {
+                    *reinterpret_cast<double2 *>(partial + ((long long)blockIdx.z * B + row) * ldp + col) =
+                        make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+                } else {
+                    if (col < m) R[row * m + col] = (TR)acc[mt][nt][0];
+                    if (col + 1 < m) R[row * m + col + 1] = (TR)acc[mt][nt][1];
+                }
+            }
+        }
+        return;
+    }
+
+    // ======================================================= producers: rho of 32 samples x 8 nodes per warp and step
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    const int pw = warp - 8, sh = pw >> 1, ch = pw & 1;     // sample half, column half of the strip
+    const int ncol = G.ncol, ny = G.ny, nx = G.nx;
+    const long long d = (long long)ncol * (ny + 1);
+    const int nvw = (int)max(0ll, min(32ll, B - row0 - sh * 32));    // valid samples of this warp
+    const unsigned wb = smem_u32(win) + pw * WIN_BYTES, tab32 = smem_u32(tab);
+    const unsigned zero_b = wb + (unsigned)((3 * kGGYC + 3 * kGGAC) * P + lane) * E;
+    // copies: quarter-warp lq takes samples 4 i + lq (i < 8), lane lc of it the window column lc (< 8); window columns 8 (9)
+    // of sample ``lane`` by that lane
+    const int lq = lane >> 3, lc = lane & 7;
+    const long long b_l = row0 + sh * 32 + lq, b_own = row0 + sh * 32 + lane;
+    const char *py = nullptr, *px = nullptr, *pa = nullptr, *pax = nullptr;
+    unsigned py_adv = 0, py_smp = 0, px_adv = 0, pa_smp = (unsigned)(4 * a_stride * E);
+    const long long pa_adv = G.sy * E;
+    bool py_on = false, px_on = false, px_zero = false, px2_on = false, pax_on = false, right = false;
+    auto set_strip = [&](int q) {   // sources of the strip's rows 0
+        right = 16 * q + 16 >= nx;
+        const int c = 16 * q + 8 * ch - 1 + lc;             // free column behind window column lc
+        if (c >= 0) {
+            py = reinterpret_cast<const char *>(y + b_l * d + c); py_adv = (unsigned)(ncol * E); py_smp = (unsigned)(4 * d * E); py_on = true;
+        } else {                                            // left Dirichlet column: g[2 t]
+            py = reinterpret_cast<const char *>(g + b_l * g_stride); py_adv = 2 * E; py_smp = (unsigned)(4 * g_stride * E); py_on = g != nullptr;
+        }
+        if (ch == 1 && right) {                             // right Dirichlet column: g[2 t + 1]; nothing behind it
+            px = reinterpret_cast<const char *>(g + b_own * g_stride + 1); px_adv = 2 * E;
+            px_on = g != nullptr; px_zero = g == nullptr; px2_on = false;
+        } else {
+            px = reinterpret_cast<const char *>(y + b_own * d + 16 * q + 8 * ch + 7); px_adv = (unsigned)(ncol * E);
+            px_on = px2_on = true; px_zero = false;
+        }
+        pa = reinterpret_cast<const char *>(a + b_l * a_stride + G.in0 + 16 * q + 8 * ch + lc);
+        pax = reinterpret_cast<const char *>(a + b_own * a_stride + G.in0 + 16 * q + 8 * ch + 8);
+        pax_on = !(ch == 1 && right);
+    };
+    auto load_y_row = [&](int slot) {   // next node row of the strip -> y slot
+        const unsigned dst = wb + (unsigned)((slot * kGGYC + lc) * P + lq) * E;
+        if (py_on) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (4 * i + lq < nvw) gg_cp_async_elem<T>(dst + 4 * i * E, reinterpret_cast<const T *>(py + (size_t)i * py_smp));
+        }
+        const unsigned dx = wb + (unsigned)((slot * kGGYC + 8) * P + lane) * E;
+        if (lane < nvw) {
+            if (px_on) gg_cp_async_elem<T>(dx, reinterpret_cast<const T *>(px));
+            if (px_zero) gg_sts_elem<T>(dx, 0.0);
+            if (px2_on) gg_cp_async_elem<T>(dx + P * E, reinterpret_cast<const T *>(px + E));
+        }
+        py += py_adv; px += px_adv;
+    };
+    auto load_a_row = [&](int slot) {   // next pixel row of the strip -> a slot
+        const unsigned dst = wb + (unsigned)((3 * kGGYC + slot * kGGAC + lc) * P + lq) * E;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (4 * i + lq < nvw) gg_cp_async_elem<T>(dst + 4 * i * E, reinterpret_cast<const T *>(pa + (size_t)i * pa_smp));
+        if (pax_on && lane < nvw)
+            gg_cp_async_elem<T>(wb + (unsigned)((3 * kGGYC + slot * kGGAC + 8) * P + lane) * E, reinterpret_cast<const T *>(pax));
+        pa += pa_adv; pax += pa_adv;
+    };
+    auto ld = [&](unsigned base, int col) -> double { return lds_elem<T>(base + (unsigned)(col * P * E)); };
+
+    // slots: at a step, ycs holds the node row t, ycs + 1 the row above, ycs + 2 takes row t + 2; aas holds pixel row t,
+    // aas - 1 the row below, aas + 1 takes row t + 1 (all mod 3, advancing by one per step -- across strip boundaries too)
+    int ycs = 0, aas = 0;
+    set_strip(q_lo);
+    load_y_row(0);
+    load_y_row(1);
+    load_a_row(0);
+    cp_async_commit();
+    const unsigned vbytes = (unsigned)(B_STAGE * 8);
+    if (pw == 0 && lane == 0) {         // packed V: chunks 0 and 1 (the ring is empty)
+        for (int v = 0; v < 2 && v < n_chunks; ++v) {
+            mbar_arrive_expect_tx(fullB + v, vbytes);
+            bulk_g2s(Bs + (size_t)v * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + v);
+        }
+    }
+
+    double fvp[8];
+    int sa = 0, kcl = 0;
+    unsigned pe = 1;                    // waiting on the "previous" phase of a fresh barrier returns at once
+    const double rh = G.rh, scale = G.scale;
+    for (int q = q_lo; q < q_hi; ++q) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) fvp[j] = 0.0;
+        for (int t = 0; t <= ny; ++t, ++kcl) {
+            const int y1 = ycs == 2 ? 0 : ycs + 1, y2 = ycs == 0 ? 2 : ycs - 1;      // ycs + 1, ycs + 2 (mod 3)
+            const int a1 = aas == 2 ? 0 : aas + 1, am = aas == 0 ? 2 : aas - 1;      // aas + 1, aas - 1 (mod 3)
+            // ---- next step's rows (every lane has left the slots they replace: they were last read a step ago)
+            __syncwarp();
+            if (t < ny) {
+                if (t + 2 <= ny) load_y_row(y2);
+                if (t + 1 < ny) load_a_row(a1);
+            } else if (q + 1 < q_hi) {
+                set_strip(q + 1);
+                load_y_row(y1);
+                load_y_row(y2);
+                load_a_row(a1);
+            }
+            cp_async_commit();
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            mbar_wait(emptyA + sa, pe);
+            if (pw == 0) {              // packed V two chunks ahead: its slot was released with the rho stage just waited for
+                const int v = kcl + 2;
+                if (v < n_chunks) {
+                    const int vs = v % SB;
+                    if (v >= SB) mbar_wait(emptyB + vs, (unsigned)((v / SB) - 1) & 1u);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(fullB + vs, vbytes);
+                        bulk_g2s(Bs + (size_t)vs * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + vs);
+                    }
+                }
+            }
+            // ---- this step: node row t between pixel rows t - 1 (below) and t (above)
+            const bool has_b = t > 0, has_a = t < ny;
+            const bool was_right = (t == ny && q + 1 < q_hi) ? (16 * q + 16 >= nx) : right;   // set_strip(q + 1) ran above
+            const unsigned yc_b = wb + (unsigned)(ycs * kGGYC * P + lane) * E;
+            const unsigned ya_b = has_a ? wb + (unsigned)(y1 * kGGYC * P + lane) * E : zero_b;
+            const unsigned ab_b = has_b ? wb + (unsigned)((3 * kGGYC + am * kGGAC) * P + lane) * E : zero_b;
+            const unsigned aa_b = has_a ? wb + (unsigned)((3 * kGGYC + aas * kGGAC) * P + lane) * E : zero_b;
+            const unsigned a_dst = smem_u32(As) + 8u * (sa * A_STAGE + (8 * ch) * kGGLdA + sh * 32 + lane);
+            double ul = ld(yc_b, 0), uc = ld(yc_b, 1);
+            double aBj = ld(ab_b, 0), aAj = ld(aa_b, 0);
+            if constexpr (ALOG) {
+                if (has_a) {
+                    aAj = exp256_in_range(aAj) ? exp_tab256c(aAj, tab32) : exp(aAj);
+                    gg_sts_elem<T>(aa_b, aAj);
+                }
+            }
+            double fh_l = (aBj + aAj) * (uc - ul);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const double ur = ld(yc_b, j + 2), aBn = ld(ab_b, j + 1), un = ld(ya_b, j + 1);
+                double aAn = ld(aa_b, j + 1);
+                if constexpr (ALOG) {
+                    if (has_a) {
+                        aAn = exp256_in_range(aAn) ? exp_tab256c(aAn, tab32) : exp(aAn);
+                        gg_sts_elem<T>(aa_b + (unsigned)((j + 1) * P * E), aAn);
+                    }
+                }
+                const double fh_r = (aBn + aAn) * (ur - uc);
+                const double fv = (aAj + aAn) * (un - uc);
+                double Sv = fma(rh, fh_r - fh_l, fv - fvp[j]);
+                fvp[j] = fv;
+                if (j == 7 && ch == 1 && was_right) Sv = 0.0;
+                asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_dst + 8u * (j * kGGLdA)), "d"(scale * Sv) : "memory");
+                fh_l = fh_r; aBj = aBn; aAj = aAn; ul = uc; uc = ur;
+            }
+            mbar_arrive(fullA + sa);
+            if (++sa == kGGStagesA) { sa = 0; pe ^= 1; }
+            ycs = y1; aas = a1;
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+}  // namespace gpde
