@@ -806,7 +806,7 @@ static bool gridgemm_setup(const gpde_vo_plan *pl, int m, int sub_f, int elem, G
     G.in0 = G2.in0; G.sy = G2.sy; G.rh = G2.rh; G.scale = G2.scale;
     bn = m <= 128 ? 128 : 256;
     G.ctiles = (m + bn - 1) / bn;
-    for (G.stages_b = 4; G.stages_b >= 2; --G.stages_b)
+    for (G.stages_b = 4; G.stages_b >= 3; --G.stages_b)
         if ((smem = gg_smem_bytes(bn, G.stages_b, elem)) <= 227 * 1024) return true;
     return false;
 }

@@ -8,7 +8,7 @@
 // 16 nodes of one node row at a time, straight into the A operand of the contraction in shared memory:
 //   * the contraction index runs strip-major: strip q (16 node columns), node rows bottom to top inside the strip; a chunk
 //     = the 16 nodes (q, t) -- V is re-packed in this order, one chunk = one contiguous stage image [16][BN + 4] with the
-//     chunk's tile mask in the padding, fetched by ONE bulk copy (TMA engine) two chunks ahead;
+//     chunk's tile mask in the padding, fetched by ONE bulk copy (TMA engine) two chunks ahead (ring of 4);
 //   * four producer warps, one per scheduler (32 samples x 8 node columns each, lane = sample), march up the strip with
 //     their own window of node rows of y and pixel rows of a in shared memory (cp.async one step ahead, 8 lanes per sample
 //     row segment; Dirichlet columns come from g the same way), form the flux-form residual of the row (same expressions
@@ -26,12 +26,12 @@ namespace gpde {
 constexpr int kGGBM = 64;                 // samples per CTA
 constexpr int kGGKC = 16;                 // nodes per chunk
 constexpr int kGGThreads = 384;           // 8 consumer warps + 4 producer warps
-constexpr int kGGStagesA = 2;
+constexpr int kGGStagesA = 3;
 constexpr int kGGLdA = kGGBM + 4;         // doubles per k row of the rho tile (= 4 mod 16: conflict-free fragment loads)
-// a producer warp's window: 3 slots of 10 y columns (8 nodes + halo), 3 slots of 9 pixel columns, one slot of zeros (the
-// rows outside the mesh); a column holds the warp's 32 samples at pitch 34 (FP64) / 36 (FP32) elements: the copies of a
-// quarter-warp per sample and the reads of a lane per sample are both conflict-free
-constexpr int kGGYC = 10, kGGAC = 9, kGGWinCols = 3 * kGGYC + 3 * kGGAC + kGGYC;
+// a producer warp's window: 3 slots of 10 y columns (8 nodes + halo), 3 slots of 9 pixel columns; one slot of zeros (the
+// rows outside the mesh) is shared by the four warps; a column holds the warp's 32 samples at pitch 34 (FP64) / 36 (FP32)
+// elements: the copies of a quarter-warp per sample and the reads of a lane per sample are both conflict-free
+constexpr int kGGYC = 10, kGGAC = 9, kGGWinCols = 3 * kGGYC + 3 * kGGAC;
 static inline __host__ __device__ constexpr int gg_win_pitch(int elem) { return elem == 8 ? 34 : 36; }
 
 struct GGDev {
@@ -44,7 +44,7 @@ struct GGDev {
 
 static inline size_t gg_smem_bytes(int bn, int stages_b, int elem) {
     return (size_t)stages_b * sizeof(double) * kGGKC * (bn + 4) + (size_t)kGGStagesA * sizeof(double) * kGGKC * kGGLdA +
-           (size_t)4 * elem * gg_win_pitch(elem) * kGGWinCols + 16 +
+           (size_t)elem * gg_win_pitch(elem) * (4 * kGGWinCols + kGGYC) + 16 +
            sizeof(unsigned long long) * (2 * kGGStagesA + 2 * 8) + 256 * sizeof(double);
 }
 static inline size_t gg_packed_bytes(int bn, int ctiles, int chunks) {
@@ -121,7 +121,8 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     double *Bs = reinterpret_cast<double *>(gg_smem);
     double *As = Bs + (size_t)SB * B_STAGE;
     unsigned char *win = reinterpret_cast<unsigned char *>(As + kGGStagesA * A_STAGE);
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(win + 4 * WIN_BYTES) + 15) & ~(uintptr_t)15);
+    constexpr int WIN_ALL = 4 * WIN_BYTES + kGGYC * P * E;      // + the shared slot of zeros
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(win + WIN_ALL) + 15) & ~(uintptr_t)15);
     unsigned long long *fullA = bars, *emptyA = bars + kGGStagesA, *fullB = bars + 2 * kGGStagesA, *emptyB = fullB + 8;
     double *tab = reinterpret_cast<double *>(emptyB + 8);
 
@@ -135,7 +136,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     // ---- setup: windows zeroed (rows outside the mesh and the slots of samples past the batch read as 0), barriers, exp table
     {
         unsigned *w32 = reinterpret_cast<unsigned *>(win);
-        for (int i = tid; i < (4 * WIN_BYTES) >> 2; i += kGGThreads) w32[i] = 0u;
+        for (int i = tid; i < WIN_ALL >> 2; i += kGGThreads) w32[i] = 0u;
     }
     if (tid == 0) {
         for (int i = 0; i < kGGStagesA; ++i) { mbar_init(fullA + i, 128); mbar_init(emptyA + i, 8); }
@@ -147,7 +148,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
 
     if (warp < 8) {
         // =================================================== consumers: DMMA out of the two rings
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         const int wm = warp & 1, wn = warp >> 1;
         const int gq = lane >> 2, tq = lane & 3;
         double acc[4][NT][2];
@@ -160,7 +161,28 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
         const unsigned mk0 = smem_u32(Bs) + 8u * BN;
         int sa = 0, sb = 0;
         unsigned pa = 0, pb = 0;
+        // packed V: one bulk copy per chunk, issued by warp 0 two chunks ahead into the slot of the chunk every warp left two
+        // iterations ago (SB = 4: no waiting in practice; the producers never touch this ring)
+        const unsigned vbytes = (unsigned)(B_STAGE * 8);
+        int vs = 2 % SB;
+        unsigned vpar = 1;               // parity of the slot's previous use; "1" on a fresh barrier returns at once
+        if (warp == 0 && lane == 0) {
+            for (int v = 0; v < 2 && v < n_chunks; ++v) {
+                mbar_arrive_expect_tx(fullB + v, vbytes);
+                bulk_g2s(Bs + (size_t)v * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + v);
+            }
+        }
         for (int kc = 0; kc < n_chunks; ++kc) {
+            if (warp == 0) {
+                if (kc + 2 < n_chunks) {
+                    mbar_wait(emptyB + vs, vpar);
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(fullB + vs, vbytes);
+                        bulk_g2s(Bs + (size_t)vs * B_STAGE, Vp + (size_t)(chunk0 + kc + 2) * B_STAGE, vbytes, fullB + vs);
+                    }
+                }
+                if (++vs == SB) { vs = 0; vpar ^= 1; }
+            }
             mbar_wait(fullB + sb, pb);
             mbar_wait(fullA + sa, pa);
             const unsigned ab = as0 + sa * (A_STAGE * 8), bb = bs0 + sb * (B_STAGE * 8);
@@ -209,63 +231,69 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     }
 
     // ======================================================= producers: rho of 32 samples x 8 nodes per warp and step
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
     const int pw = warp - 8, sh = pw >> 1, ch = pw & 1;     // sample half, column half of the strip
     const int ncol = G.ncol, ny = G.ny, nx = G.nx;
     const long long d = (long long)ncol * (ny + 1);
     const int nvw = (int)max(0ll, min(32ll, B - row0 - sh * 32));    // valid samples of this warp
     const unsigned wb = smem_u32(win) + pw * WIN_BYTES, tab32 = smem_u32(tab);
-    const unsigned zero_b = wb + (unsigned)((3 * kGGYC + 3 * kGGAC) * P + lane) * E;
+    const unsigned zero_b = smem_u32(win) + 4 * WIN_BYTES + lane * E;
     // copies: quarter-warp lq takes samples 4 i + lq (i < 8), lane lc of it the window column lc (< 8); window columns 8 (9)
-    // of sample ``lane`` by that lane
+    // of sample ``lane``, and the Dirichlet values g[2 t], g[2 t + 1] of the mesh's first / last column, by that lane.
+    // Sources are 32-bit byte offsets from the first sample of this warp (the launcher checks that they fit).
     const int lq = lane >> 3, lc = lane & 7;
-    const long long b_l = row0 + sh * 32 + lq, b_own = row0 + sh * 32 + lane;
-    const char *py = nullptr, *px = nullptr, *pa = nullptr, *pax = nullptr;
-    unsigned py_adv = 0, py_smp = 0, px_adv = 0, pa_smp = (unsigned)(4 * a_stride * E);
-    const long long pa_adv = G.sy * E;
-    bool py_on = false, px_on = false, px_zero = false, px2_on = false, pax_on = false, right = false;
-    auto set_strip = [&](int q) {   // sources of the strip's rows 0
-        right = 16 * q + 16 >= nx;
-        const int c = 16 * q + 8 * ch - 1 + lc;             // free column behind window column lc
-        if (c >= 0) {
-            py = reinterpret_cast<const char *>(y + b_l * d + c); py_adv = (unsigned)(ncol * E); py_smp = (unsigned)(4 * d * E); py_on = true;
-        } else {                                            // left Dirichlet column: g[2 t]
-            py = reinterpret_cast<const char *>(g + b_l * g_stride); py_adv = 2 * E; py_smp = (unsigned)(4 * g_stride * E); py_on = g != nullptr;
-        }
-        if (ch == 1 && right) {                             // right Dirichlet column: g[2 t + 1]; nothing behind it
-            px = reinterpret_cast<const char *>(g + b_own * g_stride + 1); px_adv = 2 * E;
-            px_on = g != nullptr; px_zero = g == nullptr; px2_on = false;
-        } else {
-            px = reinterpret_cast<const char *>(y + b_own * d + 16 * q + 8 * ch + 7); px_adv = (unsigned)(ncol * E);
-            px_on = px2_on = true; px_zero = false;
-        }
-        pa = reinterpret_cast<const char *>(a + b_l * a_stride + G.in0 + 16 * q + 8 * ch + lc);
-        pax = reinterpret_cast<const char *>(a + b_own * a_stride + G.in0 + 16 * q + 8 * ch + 8);
-        pax_on = !(ch == 1 && right);
+    const char *y_w = reinterpret_cast<const char *>(y + (row0 + sh * 32) * d);
+    const char *a_w = reinterpret_cast<const char *>(a + (row0 + sh * 32) * a_stride + G.in0);
+    const char *g_w = reinterpret_cast<const char *>(g ? g + (row0 + sh * 32) * g_stride : nullptr);
+    const unsigned y_smp = (unsigned)(4 * d * E), a_smp = (unsigned)(4 * a_stride * E);
+    const unsigned y_adv = (unsigned)(ncol * E);
+    const int a_adv = (int)(G.sy * E);
+    unsigned oy = 0, ox = 0, og = 0;    // next node row: main copy of this lane, column 8 of the lane's sample, Dirichlet pair
+    int oa = 0, oax = 0;                // next pixel row
+    bool left = false, right = false;   // the warp's first / last node column is a Dirichlet column
+    auto set_strip = [&](int q) {       // sources of the strip's rows 0
+        left = q == 0 && ch == 0;
+        right = ch == 1 && 16 * q + 16 >= nx;
+        const int c = 16 * q + 8 * ch - 1;                   // free column behind window column 0
+        oy = (unsigned)((lq * d + c + lc) * E);
+        ox = (unsigned)((lane * d + c + 8) * E);
+        og = (unsigned)(lane * g_stride * E);
+        oa = (int)((lq * a_stride + 16 * q + 8 * ch + lc) * E);
+        oax = (int)((lane * a_stride + 16 * q + 8 * ch + 8) * E);
     };
     auto load_y_row = [&](int slot) {   // next node row of the strip -> y slot
         const unsigned dst = wb + (unsigned)((slot * kGGYC + lc) * P + lq) * E;
-        if (py_on) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (4 * i + lq < nvw) gg_cp_async_elem<T>(dst + 4 * i * E, reinterpret_cast<const T *>(py + (size_t)i * py_smp));
+        if (!(left && lc == 0)) {
+            // (rolled on purpose: unrolled, the eight per-sample base addresses become loop invariants that do not fit the
+            // producers' register budget)
+            const char *src = y_w + oy;
+#pragma unroll 1
+            for (int i = 0; i < 4 * 8; i += 4, src += y_smp)
+                if (i + lq < nvw) gg_cp_async_elem<T>(dst + i * E, reinterpret_cast<const T *>(src));
         }
         const unsigned dx = wb + (unsigned)((slot * kGGYC + 8) * P + lane) * E;
         if (lane < nvw) {
-            if (px_on) gg_cp_async_elem<T>(dx, reinterpret_cast<const T *>(px));
-            if (px_zero) gg_sts_elem<T>(dx, 0.0);
-            if (px2_on) gg_cp_async_elem<T>(dx + P * E, reinterpret_cast<const T *>(px + E));
+            if (!right) {
+                gg_cp_async_elem<T>(dx, reinterpret_cast<const T *>(y_w + ox));
+                gg_cp_async_elem<T>(dx + P * E, reinterpret_cast<const T *>(y_w + ox + E));
+            } else if (g_w) {
+                gg_cp_async_elem<T>(dx, reinterpret_cast<const T *>(g_w + og + E));
+            } else {
+                gg_sts_elem<T>(dx, 0.0);
+            }
+            if (left && g_w) gg_cp_async_elem<T>(wb + (unsigned)((slot * kGGYC) * P + lane) * E, reinterpret_cast<const T *>(g_w + og));
         }
-        py += py_adv; px += px_adv;
+        oy += y_adv; ox += y_adv; og += 2 * E;
     };
     auto load_a_row = [&](int slot) {   // next pixel row of the strip -> a slot
         const unsigned dst = wb + (unsigned)((3 * kGGYC + slot * kGGAC + lc) * P + lq) * E;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-            if (4 * i + lq < nvw) gg_cp_async_elem<T>(dst + 4 * i * E, reinterpret_cast<const T *>(pa + (size_t)i * pa_smp));
-        if (pax_on && lane < nvw)
-            gg_cp_async_elem<T>(wb + (unsigned)((3 * kGGYC + slot * kGGAC + 8) * P + lane) * E, reinterpret_cast<const T *>(pax));
-        pa += pa_adv; pax += pa_adv;
+        const char *src = a_w + oa;
+#pragma unroll 1
+        for (int i = 0; i < 4 * 8; i += 4, src += a_smp)
+            if (i + lq < nvw) gg_cp_async_elem<T>(dst + i * E, reinterpret_cast<const T *>(src));
+        if (!right && lane < nvw)
+            gg_cp_async_elem<T>(wb + (unsigned)((3 * kGGYC + slot * kGGAC + 8) * P + lane) * E, reinterpret_cast<const T *>(a_w + oax));
+        oa += a_adv; oax += a_adv;
     };
     auto ld = [&](unsigned base, int col) -> double { return lds_elem<T>(base + (unsigned)(col * P * E)); };
 
@@ -277,14 +305,6 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     load_y_row(1);
     load_a_row(0);
     cp_async_commit();
-    const unsigned vbytes = (unsigned)(B_STAGE * 8);
-    if (pw == 0 && lane == 0) {         // packed V: chunks 0 and 1 (the ring is empty)
-        for (int v = 0; v < 2 && v < n_chunks; ++v) {
-            mbar_arrive_expect_tx(fullB + v, vbytes);
-            bulk_g2s(Bs + (size_t)v * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + v);
-        }
-    }
-
     double fvp[8];
     int sa = 0, kcl = 0;
     unsigned pe = 1;                    // waiting on the "previous" phase of a fresh barrier returns at once
@@ -310,20 +330,9 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
             asm volatile("cp.async.wait_group 1;" ::: "memory");
             __syncwarp();
             mbar_wait(emptyA + sa, pe);
-            if (pw == 0) {              // packed V two chunks ahead: its slot was released with the rho stage just waited for
-                const int v = kcl + 2;
-                if (v < n_chunks) {
-                    const int vs = v % SB;
-                    if (v >= SB) mbar_wait(emptyB + vs, (unsigned)((v / SB) - 1) & 1u);
-                    if (lane == 0) {
-                        mbar_arrive_expect_tx(fullB + vs, vbytes);
-                        bulk_g2s(Bs + (size_t)vs * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + vs);
-                    }
-                }
-            }
             // ---- this step: node row t between pixel rows t - 1 (below) and t (above)
             const bool has_b = t > 0, has_a = t < ny;
-            const bool was_right = (t == ny && q + 1 < q_hi) ? (16 * q + 16 >= nx) : right;   // set_strip(q + 1) ran above
+            const bool was_right = ch == 1 && 16 * q + 16 >= nx;
             const unsigned yc_b = wb + (unsigned)(ycs * kGGYC * P + lane) * E;
             const unsigned ya_b = has_a ? wb + (unsigned)(y1 * kGGYC * P + lane) * E : zero_b;
             const unsigned ab_b = has_b ? wb + (unsigned)((3 * kGGYC + am * kGGAC) * P + lane) * E : zero_b;
@@ -352,7 +361,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
                 const double fv = (aAj + aAn) * (un - uc);
                 double Sv = fma(rh, fh_r - fh_l, fv - fvp[j]);
                 fvp[j] = fv;
-                if (j == 7 && ch == 1 && was_right) Sv = 0.0;
+                if (j == 7 && was_right) Sv = 0.0;
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_dst + 8u * (j * kGGLdA)), "d"(scale * Sv) : "memory");
                 fh_l = fh_r; aBj = aBn; aAj = aAn; ul = uc; uc = ur;
             }
