@@ -796,7 +796,7 @@ static int launch_matvec(const gpde_vo_plan *pl, const Ta *a, long long a_stride
 
 // Many weighting functions on the reference's pixel meshes: rho produced inside the contraction kernel (vo_gridgemm.cuh).
 // Returns 1 if it served the call, 0 if the two-kernel route should, < 0 on error.
-static bool gridgemm_setup(const gpde_vo_plan *pl, int m, int sub_f, int elem, GGDev &G, int &bn, size_t &smem) {
+static bool gridgemm_setup(const gpde_vo_plan *pl, int m, int sub_f, int elem, GGDev &G, int &bn, int &nw, size_t &smem) {
     Grid2Dev G2;
     int nt2, nx2;
     size_t smem2;
@@ -806,15 +806,16 @@ static bool gridgemm_setup(const gpde_vo_plan *pl, int m, int sub_f, int elem, G
     G.in0 = G2.in0; G.sy = G2.sy; G.rh = G2.rh; G.scale = G2.scale;
     bn = m <= 128 ? 128 : 256;
     G.ctiles = (m + bn - 1) / bn;
+    nw = 8;   // node columns per producer warp: 4 producer warps (8 warps of 4 columns measured slower: 4.46 vs 4.26 ms at config 3)
     for (G.stages_b = 4; G.stages_b >= 3; --G.stages_b)
-        if ((smem = gg_smem_bytes(bn, G.stages_b, elem)) <= 227 * 1024) return true;
+        if ((smem = gg_smem_bytes(bn, G.stages_b, elem, nw)) <= 227 * 1024) return true;
     return false;
 }
 static size_t gridgemm_workspace_bytes(const gpde_vo_plan *pl, long long B, int m) {
     GGDev G;
-    int bn;
+    int bn, nw;
     size_t smem;
-    if (!gridgemm_setup(pl, m, 0, 8, G, bn, smem)) return 0;
+    if (!gridgemm_setup(pl, m, 0, 8, G, bn, nw, smem)) return 0;
     return gg_packed_bytes(bn, G.ctiles, G.nstrips * (G.ny + 1)) + 16 + sizeof(double) * 8 * (size_t)B * G.ctiles * bn;
 }
 template <typename T>
@@ -822,9 +823,12 @@ static int launch_gridgemm(const gpde_vo_plan *pl, const T *a, long long a_strid
                            long long g_stride, const T *V, int m, T *r, void *workspace, int sub_f, long long B,
                            cudaStream_t st) {
     GGDev G;
-    int bn;
+    int bn, nw;
     size_t smem;
-    if (((uintptr_t)workspace & 15) || !gridgemm_setup(pl, m, sub_f, (int)sizeof(T), G, bn, smem)) return 0;
+    if (((uintptr_t)workspace & 15) || !gridgemm_setup(pl, m, sub_f, (int)sizeof(T), G, bn, nw, smem)) return 0;
+    // the producers address a warp's 32 samples by 32-bit byte offsets
+    const long long span = 32 * std::max<long long>(std::max<long long>(pl->dev.d, a_stride), g_stride) + 2 * (long long)pl->dev.d;
+    if (span * (long long)sizeof(T) >= (1ll << 31)) return 0;
     const int chunks = G.nstrips * (G.ny + 1);
     double *Vp = (double *)workspace;
     const long long tiles = (B + kGGBM - 1) / kGGBM * G.ctiles;
@@ -834,16 +838,18 @@ static int launch_gridgemm(const gpde_vo_plan *pl, const T *a, long long a_strid
     double *partial = splits > 1 ? (double *)(((uintptr_t)Vp + gg_packed_bytes(bn, G.ctiles, chunks) + 15) & ~(uintptr_t)15) : nullptr;
     const dim3 grid((unsigned)((B + kGGBM - 1) / kGGBM), (unsigned)G.ctiles, (unsigned)splits);
     const unsigned pgrid = (unsigned)std::min<long long>(((long long)G.ctiles * chunks + 7) / 8, (long long)pl->n_sm * 8);
-#define GPDE_LAUNCH_GG(BNV, ALOGV)                                                                                \
+#define GPDE_LAUNCH_GG3(BNV, NWV, ALOGV)                                                                          \
     {                                                                                                             \
         vo_gridgemm_pack_kernel<BNV, T><<<pgrid, 256, 0, st>>>(G, V, m, Vp);                                      \
-        auto kern = vo_gridgemm_kernel<BNV, ALOGV, T, T>;                                                         \
+        auto kern = vo_gridgemm_kernel<BNV, NWV, ALOGV, T, T>;                                                    \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
-        kern<<<grid, kGGThreads, smem, st>>>(G, a, a_stride, y, g, g_stride, Vp, r, m, ldp, B, partial);          \
+        kern<<<grid, gg_threads(NWV), smem, st>>>(G, a, a_stride, y, g, g_stride, Vp, r, m, ldp, B, partial);     \
     }
+#define GPDE_LAUNCH_GG(BNV, ALOGV) GPDE_LAUNCH_GG3(BNV, 8, ALOGV)
     if (bn == 128) { if (a_is_log) GPDE_LAUNCH_GG(128, true) else GPDE_LAUNCH_GG(128, false) }
     else           { if (a_is_log) GPDE_LAUNCH_GG(256, true) else GPDE_LAUNCH_GG(256, false) }
 #undef GPDE_LAUNCH_GG
+#undef GPDE_LAUNCH_GG3
     GPDE_CUDA_OK(cudaGetLastError());
     if (splits > 1) {
         const long long total = B * m;

@@ -25,14 +25,15 @@ namespace gpde {
 
 constexpr int kGGBM = 64;                 // samples per CTA
 constexpr int kGGKC = 16;                 // nodes per chunk
-constexpr int kGGThreads = 384;           // 8 consumer warps + 4 producer warps
+// 8 consumer warps + 2 * (16 / NW) producer warps, NW = node columns per producer warp (8 or 4)
+static inline __host__ __device__ constexpr int gg_threads(int nw) { return 256 + 64 * (16 / nw); }
 constexpr int kGGStagesA = 3;
 constexpr int kGGLdA = kGGBM + 4;         // doubles per k row of the rho tile (= 4 mod 16: conflict-free fragment loads)
-// a producer warp's window: 3 slots of 10 y columns (8 nodes + halo), 3 slots of 9 pixel columns; one slot of zeros (the
-// rows outside the mesh) is shared by the four warps; a column holds the warp's 32 samples at pitch 34 (FP64) / 36 (FP32)
-// elements: the copies of a quarter-warp per sample and the reads of a lane per sample are both conflict-free
-constexpr int kGGYC = 10, kGGAC = 9, kGGWinCols = 3 * kGGYC + 3 * kGGAC;
-static inline __host__ __device__ constexpr int gg_win_pitch(int elem) { return elem == 8 ? 34 : 36; }
+// a producer warp's window: 3 slots of NW + 2 y columns (its nodes + halo), 3 slots of NW + 1 pixel columns; one slot of
+// zeros (the rows outside the mesh) is shared by the warps; a column holds the warp's 32 samples at a pitch that makes both
+// the copies (NW lanes per sample row segment) and the reads (a lane per sample) conflict-free
+static inline __host__ __device__ constexpr int gg_win_cols(int nw) { return 3 * (nw + 2) + 3 * (nw + 1); }
+static inline __host__ __device__ constexpr int gg_win_pitch(int elem, int nw) { return 32 + (elem == 8 ? 16 : 32) / nw; }
 
 struct GGDev {
     int nx, ny, ncol, nstrips;
@@ -42,9 +43,9 @@ struct GGDev {
     int stages_b;            // V stages in the ring
 };
 
-static inline size_t gg_smem_bytes(int bn, int stages_b, int elem) {
+static inline size_t gg_smem_bytes(int bn, int stages_b, int elem, int nw) {
     return (size_t)stages_b * sizeof(double) * kGGKC * (bn + 4) + (size_t)kGGStagesA * sizeof(double) * kGGKC * kGGLdA +
-           (size_t)elem * gg_win_pitch(elem) * (4 * kGGWinCols + kGGYC) + 16 +
+           (size_t)elem * gg_win_pitch(elem, nw) * (2 * (16 / nw) * gg_win_cols(nw) + nw + 2) + 16 +
            sizeof(unsigned long long) * (2 * kGGStagesA + 2 * 8) + 256 * sizeof(double);
 }
 static inline size_t gg_packed_bytes(int bn, int ctiles, int chunks) {
@@ -107,21 +108,24 @@ template <> __device__ __forceinline__ void gg_sts_elem<float>(unsigned dst, dou
 }
 
 // grid: (sample tiles of 64, column tiles of BN, parts of the contraction length = groups of whole strips)
-template <int BN, bool ALOG, typename T, typename TR>
-__global__ void __launch_bounds__(kGGThreads, 1)
+template <int BN, int NW, bool ALOG, typename T, typename TR>
+__global__ void __launch_bounds__(gg_threads(NW), 1)
 vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T *__restrict__ y, const T *__restrict__ g,
                    long long g_stride, const double *__restrict__ Vp, TR *__restrict__ R, int m, int ldp, long long B,
                    double *__restrict__ partial) {
     constexpr int LdB = BN + 4, NT = BN / 32;     // n-tiles per consumer warp (4 warps along N, interleaved)
     constexpr int A_STAGE = kGGKC * kGGLdA, B_STAGE = kGGKC * LdB;
-    constexpr int E = (int)sizeof(T), P = E == 8 ? 34 : 36;
-    constexpr int WIN_BYTES = kGGWinCols * P * E;                 // one producer warp's window
+    constexpr int E = (int)sizeof(T), P = gg_win_pitch(E, NW);
+    constexpr int CG = 16 / NW, NPROD = 2 * CG;                 // column groups of a strip; producer warps
+    constexpr int YC = NW + 2, AC = NW + 1;                     // window columns per slot
+    constexpr int kThreads = gg_threads(NW);
+    constexpr int WIN_BYTES = gg_win_cols(NW) * P * E;          // one producer warp's window
     extern __shared__ __align__(128) unsigned char gg_smem[];
     const int SB = G.stages_b;
     double *Bs = reinterpret_cast<double *>(gg_smem);
     double *As = Bs + (size_t)SB * B_STAGE;
     unsigned char *win = reinterpret_cast<unsigned char *>(As + kGGStagesA * A_STAGE);
-    constexpr int WIN_ALL = 4 * WIN_BYTES + kGGYC * P * E;      // + the shared slot of zeros
+    constexpr int WIN_ALL = NPROD * WIN_BYTES + YC * P * E;      // + the shared slot of zeros
     unsigned long long *bars = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(win + WIN_ALL) + 15) & ~(uintptr_t)15);
     unsigned long long *fullA = bars, *emptyA = bars + kGGStagesA, *fullB = bars + 2 * kGGStagesA, *emptyB = fullB + 8;
     double *tab = reinterpret_cast<double *>(emptyB + 8);
@@ -136,10 +140,10 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     // ---- setup: windows zeroed (rows outside the mesh and the slots of samples past the batch read as 0), barriers, exp table
     {
         unsigned *w32 = reinterpret_cast<unsigned *>(win);
-        for (int i = tid; i < WIN_ALL >> 2; i += kGGThreads) w32[i] = 0u;
+        for (int i = tid; i < WIN_ALL >> 2; i += kThreads) w32[i] = 0u;
     }
     if (tid == 0) {
-        for (int i = 0; i < kGGStagesA; ++i) { mbar_init(fullA + i, 128); mbar_init(emptyA + i, 8); }
+        for (int i = 0; i < kGGStagesA; ++i) { mbar_init(fullA + i, 32 * NPROD); mbar_init(emptyA + i, 8); }
         for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -148,7 +152,9 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
 
     if (warp < 8) {
         // =================================================== consumers: DMMA out of the two rings
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+        // registers: 384 x 168 (NW = 8) / 512 x 128 (NW = 4) are allocated at launch and re-divided between the roles
+        if constexpr (NW == 8) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
         const int wm = warp & 1, wn = warp >> 1;
         const int gq = lane >> 2, tq = lane & 3;
         double acc[4][NT][2];
@@ -164,24 +170,24 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
         // packed V: one bulk copy per chunk, issued by warp 0 two chunks ahead into the slot of the chunk every warp left two
         // iterations ago (SB = 4: no waiting in practice; the producers never touch this ring)
         const unsigned vbytes = (unsigned)(B_STAGE * 8);
-        int vs = 2 % SB;
-        unsigned vpar = 1;               // parity of the slot's previous use; "1" on a fresh barrier returns at once
+        const int LA = SB - 2;           // chunks ahead: the slot of chunk kc + LA last held chunk kc - 2
+        int vs = LA, vwrap = 0;          // slot of the next chunk to fetch; how often the ring has wrapped
         if (warp == 0 && lane == 0) {
-            for (int v = 0; v < 2 && v < n_chunks; ++v) {
+            for (int v = 0; v < LA && v < n_chunks; ++v) {
                 mbar_arrive_expect_tx(fullB + v, vbytes);
                 bulk_g2s(Bs + (size_t)v * B_STAGE, Vp + (size_t)(chunk0 + v) * B_STAGE, vbytes, fullB + v);
             }
         }
         for (int kc = 0; kc < n_chunks; ++kc) {
             if (warp == 0) {
-                if (kc + 2 < n_chunks) {
-                    mbar_wait(emptyB + vs, vpar);
+                if (kc + LA < n_chunks) {
+                    if (vwrap > 0) mbar_wait(emptyB + vs, (unsigned)(vwrap - 1) & 1u);
                     if (lane == 0) {
                         mbar_arrive_expect_tx(fullB + vs, vbytes);
-                        bulk_g2s(Bs + (size_t)vs * B_STAGE, Vp + (size_t)(chunk0 + kc + 2) * B_STAGE, vbytes, fullB + vs);
+                        bulk_g2s(Bs + (size_t)vs * B_STAGE, Vp + (size_t)(chunk0 + kc + LA) * B_STAGE, vbytes, fullB + vs);
                     }
                 }
-                if (++vs == SB) { vs = 0; vpar ^= 1; }
+                if (++vs == SB) { vs = 0; ++vwrap; }
             }
             mbar_wait(fullB + sb, pb);
             mbar_wait(fullA + sa, pa);
@@ -231,21 +237,24 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     }
 
     // ======================================================= producers: rho of 32 samples x 8 nodes per warp and step
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
-    const int pw = warp - 8, sh = pw >> 1, ch = pw & 1;     // sample half, column half of the strip
+    if constexpr (NW == 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 112;");
+    else asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    const int pw = warp - 8, sh = pw / CG, ch = pw % CG;    // sample half, column group of the strip
     const int ncol = G.ncol, ny = G.ny, nx = G.nx;
     const long long d = (long long)ncol * (ny + 1);
     const int nvw = (int)max(0ll, min(32ll, B - row0 - sh * 32));    // valid samples of this warp
     const unsigned wb = smem_u32(win) + pw * WIN_BYTES, tab32 = smem_u32(tab);
-    const unsigned zero_b = smem_u32(win) + 4 * WIN_BYTES + lane * E;
-    // copies: quarter-warp lq takes samples 4 i + lq (i < 8), lane lc of it the window column lc (< 8); window columns 8 (9)
-    // of sample ``lane``, and the Dirichlet values g[2 t], g[2 t + 1] of the mesh's first / last column, by that lane.
+    const unsigned zero_b = smem_u32(win) + NPROD * WIN_BYTES + lane * E;
+    // copies: NW lanes per sample: lane group lq takes samples SPI i + lq (i < NW), lane lc of it the window column lc (< NW);
+    // window columns NW (NW + 1) of sample ``lane``, and the Dirichlet values g[2 t], g[2 t + 1] of the mesh's first / last
+    // column, by that lane.
     // Sources are 32-bit byte offsets from the first sample of this warp (the launcher checks that they fit).
-    const int lq = lane >> 3, lc = lane & 7;
+    constexpr int SPI = 32 / NW;        // samples per copy instruction
+    const int lq = lane / NW, lc = lane % NW;
     const char *y_w = reinterpret_cast<const char *>(y + (row0 + sh * 32) * d);
     const char *a_w = reinterpret_cast<const char *>(a + (row0 + sh * 32) * a_stride + G.in0);
     const char *g_w = reinterpret_cast<const char *>(g ? g + (row0 + sh * 32) * g_stride : nullptr);
-    const unsigned y_smp = (unsigned)(4 * d * E), a_smp = (unsigned)(4 * a_stride * E);
+    const unsigned y_smp = (unsigned)(SPI * d * E), a_smp = (unsigned)(SPI * a_stride * E);
     const unsigned y_adv = (unsigned)(ncol * E);
     const int a_adv = (int)(G.sy * E);
     unsigned oy = 0, ox = 0, og = 0;    // next node row: main copy of this lane, column 8 of the lane's sample, Dirichlet pair
@@ -253,25 +262,25 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     bool left = false, right = false;   // the warp's first / last node column is a Dirichlet column
     auto set_strip = [&](int q) {       // sources of the strip's rows 0
         left = q == 0 && ch == 0;
-        right = ch == 1 && 16 * q + 16 >= nx;
-        const int c = 16 * q + 8 * ch - 1;                   // free column behind window column 0
+        right = ch == CG - 1 && 16 * q + 16 >= nx;
+        const int c = 16 * q + NW * ch - 1;                   // free column behind window column 0
         oy = (unsigned)((lq * d + c + lc) * E);
-        ox = (unsigned)((lane * d + c + 8) * E);
+        ox = (unsigned)((lane * d + c + NW) * E);
         og = (unsigned)(lane * g_stride * E);
-        oa = (int)((lq * a_stride + 16 * q + 8 * ch + lc) * E);
-        oax = (int)((lane * a_stride + 16 * q + 8 * ch + 8) * E);
+        oa = (int)((lq * a_stride + 16 * q + NW * ch + lc) * E);
+        oax = (int)((lane * a_stride + 16 * q + NW * ch + NW) * E);
     };
     auto load_y_row = [&](int slot) {   // next node row of the strip -> y slot
-        const unsigned dst = wb + (unsigned)((slot * kGGYC + lc) * P + lq) * E;
+        const unsigned dst = wb + (unsigned)((slot * YC + lc) * P + lq) * E;
         if (!(left && lc == 0)) {
             // (rolled on purpose: unrolled, the eight per-sample base addresses become loop invariants that do not fit the
             // producers' register budget)
             const char *src = y_w + oy;
 #pragma unroll 1
-            for (int i = 0; i < 4 * 8; i += 4, src += y_smp)
+            for (int i = 0; i < 32; i += SPI, src += y_smp)
                 if (i + lq < nvw) gg_cp_async_elem<T>(dst + i * E, reinterpret_cast<const T *>(src));
         }
-        const unsigned dx = wb + (unsigned)((slot * kGGYC + 8) * P + lane) * E;
+        const unsigned dx = wb + (unsigned)((slot * YC + NW) * P + lane) * E;
         if (lane < nvw) {
             if (!right) {
                 gg_cp_async_elem<T>(dx, reinterpret_cast<const T *>(y_w + ox));
@@ -281,18 +290,18 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
             } else {
                 gg_sts_elem<T>(dx, 0.0);
             }
-            if (left && g_w) gg_cp_async_elem<T>(wb + (unsigned)((slot * kGGYC) * P + lane) * E, reinterpret_cast<const T *>(g_w + og));
+            if (left && g_w) gg_cp_async_elem<T>(wb + (unsigned)((slot * YC) * P + lane) * E, reinterpret_cast<const T *>(g_w + og));
         }
         oy += y_adv; ox += y_adv; og += 2 * E;
     };
     auto load_a_row = [&](int slot) {   // next pixel row of the strip -> a slot
-        const unsigned dst = wb + (unsigned)((3 * kGGYC + slot * kGGAC + lc) * P + lq) * E;
+        const unsigned dst = wb + (unsigned)((3 * YC + slot * AC + lc) * P + lq) * E;
         const char *src = a_w + oa;
 #pragma unroll 1
-        for (int i = 0; i < 4 * 8; i += 4, src += a_smp)
+        for (int i = 0; i < 32; i += SPI, src += a_smp)
             if (i + lq < nvw) gg_cp_async_elem<T>(dst + i * E, reinterpret_cast<const T *>(src));
         if (!right && lane < nvw)
-            gg_cp_async_elem<T>(wb + (unsigned)((3 * kGGYC + slot * kGGAC + 8) * P + lane) * E, reinterpret_cast<const T *>(a_w + oax));
+            gg_cp_async_elem<T>(wb + (unsigned)((3 * YC + slot * AC + NW) * P + lane) * E, reinterpret_cast<const T *>(a_w + oax));
         oa += a_adv; oax += a_adv;
     };
     auto ld = [&](unsigned base, int col) -> double { return lds_elem<T>(base + (unsigned)(col * P * E)); };
@@ -305,13 +314,13 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     load_y_row(1);
     load_a_row(0);
     cp_async_commit();
-    double fvp[8];
+    double fvp[NW];
     int sa = 0, kcl = 0;
     unsigned pe = 1;                    // waiting on the "previous" phase of a fresh barrier returns at once
     const double rh = G.rh, scale = G.scale;
     for (int q = q_lo; q < q_hi; ++q) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) fvp[j] = 0.0;
+        for (int j = 0; j < NW; ++j) fvp[j] = 0.0;
         for (int t = 0; t <= ny; ++t, ++kcl) {
             const int y1 = ycs == 2 ? 0 : ycs + 1, y2 = ycs == 0 ? 2 : ycs - 1;      // ycs + 1, ycs + 2 (mod 3)
             const int a1 = aas == 2 ? 0 : aas + 1, am = aas == 0 ? 2 : aas - 1;      // aas + 1, aas - 1 (mod 3)
@@ -332,12 +341,12 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
             mbar_wait(emptyA + sa, pe);
             // ---- this step: node row t between pixel rows t - 1 (below) and t (above)
             const bool has_b = t > 0, has_a = t < ny;
-            const bool was_right = ch == 1 && 16 * q + 16 >= nx;
-            const unsigned yc_b = wb + (unsigned)(ycs * kGGYC * P + lane) * E;
-            const unsigned ya_b = has_a ? wb + (unsigned)(y1 * kGGYC * P + lane) * E : zero_b;
-            const unsigned ab_b = has_b ? wb + (unsigned)((3 * kGGYC + am * kGGAC) * P + lane) * E : zero_b;
-            const unsigned aa_b = has_a ? wb + (unsigned)((3 * kGGYC + aas * kGGAC) * P + lane) * E : zero_b;
-            const unsigned a_dst = smem_u32(As) + 8u * (sa * A_STAGE + (8 * ch) * kGGLdA + sh * 32 + lane);
+            const bool was_right = ch == CG - 1 && 16 * q + 16 >= nx;
+            const unsigned yc_b = wb + (unsigned)(ycs * YC * P + lane) * E;
+            const unsigned ya_b = has_a ? wb + (unsigned)(y1 * YC * P + lane) * E : zero_b;
+            const unsigned ab_b = has_b ? wb + (unsigned)((3 * YC + am * AC) * P + lane) * E : zero_b;
+            const unsigned aa_b = has_a ? wb + (unsigned)((3 * YC + aas * AC) * P + lane) * E : zero_b;
+            const unsigned a_dst = smem_u32(As) + 8u * (sa * A_STAGE + (NW * ch) * kGGLdA + sh * 32 + lane);
             double ul = ld(yc_b, 0), uc = ld(yc_b, 1);
             double aBj = ld(ab_b, 0), aAj = ld(aa_b, 0);
             if constexpr (ALOG) {
@@ -348,7 +357,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
             }
             double fh_l = (aBj + aAj) * (uc - ul);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+            for (int j = 0; j < NW; ++j) {
                 const double ur = ld(yc_b, j + 2), aBn = ld(ab_b, j + 1), un = ld(ya_b, j + 1);
                 double aAn = ld(aa_b, j + 1);
                 if constexpr (ALOG) {
@@ -361,7 +370,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
                 const double fv = (aAj + aAn) * (un - uc);
                 double Sv = fma(rh, fh_r - fh_l, fv - fvp[j]);
                 fvp[j] = fv;
-                if (j == 7 && was_right) Sv = 0.0;
+                if (j == NW - 1 && was_right) Sv = 0.0;
                 asm volatile("st.shared.f64 [%0], %1;" ::"r"(a_dst + 8u * (j * kGGLdA)), "d"(scale * Sv) : "memory");
                 fh_l = fh_r; aBj = aBn; aAj = aAn; ul = uc; uc = ur;
             }

@@ -681,6 +681,31 @@ def test_split_contraction_matches_single_pass(splits, dev):
         assert r3.dtype == torch.float32 and rel_err(r3.double().cpu(), r1.cpu()) < 1e-5
 
 
+@pytest.mark.parametrize("nx,ny,B", [(16, 4, 5), (32, 32, 37), (64, 64, 130), (128, 16, 19), (128, 128, 64), (64, 2, 1)])
+def test_one_kernel_route_for_many_weighting_functions(nx, ny, B, dev):
+    """m > 32 on the reference's pixel meshes: vo_gridgemm.cuh (the fine residual produced inside the contraction kernel, zero
+    tiles of V skipped) against the two-kernel route (rho through HBM + vo_gemm.cuh, GPDE_VO_GRIDGEMM=0) and the version-1
+    kernels: both column-tile widths, several column tiles, sparse columns (tiles really get skipped), ragged batches,
+    shared field / Dirichlet rows, no Dirichlet data, conductivity input, FP32 I/O, bitwise repeatability."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 1000 + ny, dev, load=False)
+    two, v1 = plan.variant(GPDE_VO_GRIDGEMM="0"), plan.variant(GPDE_VO_PATH="v1")
+    T = lambda t: torch.tensor(t, device=dev)
+    for m in (33, 70, 130, 256, 300):
+        V = rng.normal(size=(fom.dim_out, m))
+        V[:, : m // 3] *= rng.uniform(size=(fom.dim_out, m // 3)) < 0.02
+        V = T(V)
+        for kw in (dict(a=T(a), y=T(y), g=T(g)), dict(a=T(a[0]), y=T(y), g=T(g[0])),
+                   dict(a=T(np.exp(a)), y=T(y), g=None, a_is_log=False)):
+            r1 = plan.residual(V=V, **kw)
+            assert rel_err(r1.cpu(), two.residual(V=V, **kw).cpu()) < 1e-12, (m, sorted(kw))
+            assert torch.equal(r1, plan.residual(V=V, **kw))
+        assert rel_err(plan.residual(T(a), T(y), T(g), V).cpu(), v1.residual(T(a), T(y), T(g), V).cpu()) < 1e-12, m
+        f = lambda t: T(t).float()
+        r32 = plan.residual(f(a), f(y), f(g), V.float())
+        assert r32.dtype == torch.float32
+        assert rel_err(r32.double().cpu(), two.residual(f(a), f(y), f(g), V.float()).double().cpu()) < 1e-5, m
+
+
 @pytest.mark.parametrize("nx,ny,B", [(32, 32, 64), (32, 32, 5), (64, 64, 37), (16, 8, 130), (128, 16, 19), (64, 4, 3), (16, 2, 9)])
 def test_small_batches_cut_the_node_rows_over_a_cluster(nx, ny, B, dev):
     """Few sample blocks: the lean grid kernel runs as thread-block clusters whose CTAs each march a range of the node
