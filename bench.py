@@ -396,17 +396,40 @@ def device_inputs(torch, dev, w, B, tdt, seed):
     return d
 
 
+def nonzero_tile_fraction(w):
+    """Fraction of the (16 consecutive nodes of a node row) x (8 columns) blocks of V with a non-zero entry: the blocks
+    vo_gridgemm.cuh does not skip."""
+    import numpy as np
+    mesh = w.physics["fom"].mesh
+    nx, ny = mesh.nx, mesh.ny
+    ncol = nx - 1
+    V = np.asarray(w.V).reshape(ny + 1, ncol, w.m)
+    cp, mp = -(-nx // 16) * 16, -(-w.m // 8) * 8
+    Z = np.zeros((ny + 1, cp, mp), dtype=bool)
+    Z[:, :ncol, :w.m] = V != 0
+    blocks = Z.reshape(ny + 1, cp // 16, 16, mp // 8, 8).any(axis=(2, 4))
+    return float(blocks.mean())
+
+
 def roofline_record(w, B, s, t_vo, path, workload, dtype, peak, peak_src):
     vo_bytes = w.vo_bytes_per_eval(s) * B
     achieved = vo_bytes / (t_vo * 1e-3) / 1e9
     # FP64 work of one VO evaluation (DESIGN.md section 4): fluxes 10 + contraction m per free node (FMA = 2 flop)
     vo_flops = 2.0 * w.d * (10 + w.m) * B
     if path in (0, 3) and w.m > 32:
-        return {"kernel": "vo_grid2_kernel<rho> + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
-                "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": vo_flops / (t_vo * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "traffic": recorded_traffic(workload, dtype),
-                "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
-                "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
+        rec = {"kernel": "vo_gridgemm_kernel (fine residual produced inside the FP64 DMMA contraction)" if path == 3
+               else "vo_matvec_kernel + vo_gemm_kernel (FP64 DMMA contraction dominates)", "bound": "tensor",
+               "achieved": vo_flops / (t_vo * 1e-3) / 1e12, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+               "frac": vo_flops / (t_vo * 1e-3) / 1e12 / FP64_PEAK_TFLOPS, "traffic": recorded_traffic(workload, dtype),
+               "peak_source": "measured FP64 mma.sync rate (profiles/r1_fp64_peak.txt); MEASURED_PEAKS.json has no FP64 entry",
+               "algorithmic_flops_per_launch": vo_flops, "hbm_frac": achieved / peak}
+        if path == 3:
+            # the kernel skips the 16-node x 8-column blocks of V that are all zero (exact); what the tensor pipe really executes
+            fill = nonzero_tile_fraction(w)
+            ex = 2.0 * w.d * (10 + fill * w.m) * B
+            rec.update({"nonzero_tile_fraction_of_V": fill, "executed_flops_per_launch": ex,
+                        "executed_frac_of_peak": ex / (t_vo * 1e-3) / 1e12 / FP64_PEAK_TFLOPS})
+        return rec
     return {"kernel": {2: "vo_grid2_kernel", 1: "vo_fused_kernel"}.get(path, "vo_matvec_kernel + vo_gemm_kernel"),
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": recorded_traffic(workload, dtype), "peak_source": peak_src, "algorithmic_bytes_per_launch": vo_bytes,

@@ -816,7 +816,9 @@ static size_t gridgemm_workspace_bytes(const gpde_vo_plan *pl, long long B, int 
     int bn, nw;
     size_t smem;
     if (!gridgemm_setup(pl, m, 0, 8, G, bn, nw, smem)) return 0;
-    return gg_packed_bytes(bn, G.ctiles, G.nstrips * (G.ny + 1)) + 16 + sizeof(double) * 8 * (size_t)B * G.ctiles * bn;
+    // packed V | partial tiles of the split contraction | conductivities of a log-field input
+    return gg_packed_bytes(bn, G.ctiles, G.nstrips * (G.ny + 1)) + 32 + sizeof(double) * 8 * (size_t)B * G.ctiles * bn +
+           sizeof(double) * (size_t)B * pl->dev.n_inputs;
 }
 template <typename T>
 static int launch_gridgemm(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *y, const T *g,
@@ -835,21 +837,26 @@ static int launch_gridgemm(const gpde_vo_plan *pl, const T *a, long long a_strid
     int splits = pl->env.gemm_splits > 0 ? pl->env.gemm_splits : gemm_splits(tiles, pl->n_sm, chunks);
     splits = std::max(1, std::min(splits, G.nstrips));
     const int ldp = G.ctiles * bn;
-    double *partial = splits > 1 ? (double *)(((uintptr_t)Vp + gg_packed_bytes(bn, G.ctiles, chunks) + 15) & ~(uintptr_t)15) : nullptr;
+    double *part0 = (double *)(((uintptr_t)Vp + gg_packed_bytes(bn, G.ctiles, chunks) + 15) & ~(uintptr_t)15);
+    double *partial = splits > 1 ? part0 : nullptr;
+    if (a_is_log) {   // conductivities by one streaming pass (behind the partial tiles in the workspace)
+        T *cond = (T *)(((uintptr_t)(part0 + (size_t)8 * B * ldp) + 15) & ~(uintptr_t)15);
+        const long long n = a_stride ? B * a_stride : (long long)pl->dev.n_inputs;
+        if (a_stride && a_stride != pl->dev.n_inputs) return 0;
+        vo_exp_rows_kernel<T><<<(unsigned)std::min<long long>((n + 255) / 256, (long long)pl->n_sm * 16), 256, 0, st>>>(a, n, cond);
+        a = cond;
+    }
     const dim3 grid((unsigned)((B + kGGBM - 1) / kGGBM), (unsigned)G.ctiles, (unsigned)splits);
     const unsigned pgrid = (unsigned)std::min<long long>(((long long)G.ctiles * chunks + 7) / 8, (long long)pl->n_sm * 8);
-#define GPDE_LAUNCH_GG3(BNV, NWV, ALOGV)                                                                          \
+#define GPDE_LAUNCH_GG(BNV, NWV)                                                                                  \
     {                                                                                                             \
         vo_gridgemm_pack_kernel<BNV, T><<<pgrid, 256, 0, st>>>(G, V, m, Vp);                                      \
-        auto kern = vo_gridgemm_kernel<BNV, NWV, ALOGV, T, T>;                                                    \
+        auto kern = vo_gridgemm_kernel<BNV, NWV, T, T>;                                                           \
         GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
         kern<<<grid, gg_threads(NWV), smem, st>>>(G, a, a_stride, y, g, g_stride, Vp, r, m, ldp, B, partial);     \
     }
-#define GPDE_LAUNCH_GG(BNV, ALOGV) GPDE_LAUNCH_GG3(BNV, 8, ALOGV)
-    if (bn == 128) { if (a_is_log) GPDE_LAUNCH_GG(128, true) else GPDE_LAUNCH_GG(128, false) }
-    else           { if (a_is_log) GPDE_LAUNCH_GG(256, true) else GPDE_LAUNCH_GG(256, false) }
+    if (bn == 128) GPDE_LAUNCH_GG(128, 8) else GPDE_LAUNCH_GG(256, 8)
 #undef GPDE_LAUNCH_GG
-#undef GPDE_LAUNCH_GG3
     GPDE_CUDA_OK(cudaGetLastError());
     if (splits > 1) {
         const long long total = B * m;

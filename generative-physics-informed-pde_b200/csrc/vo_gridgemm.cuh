@@ -46,7 +46,7 @@ struct GGDev {
 static inline size_t gg_smem_bytes(int bn, int stages_b, int elem, int nw) {
     return (size_t)stages_b * sizeof(double) * kGGKC * (bn + 4) + (size_t)kGGStagesA * sizeof(double) * kGGKC * kGGLdA +
            (size_t)elem * gg_win_pitch(elem, nw) * (2 * (16 / nw) * gg_win_cols(nw) + nw + 2) + 16 +
-           sizeof(unsigned long long) * (2 * kGGStagesA + 2 * 8) + 256 * sizeof(double);
+           sizeof(unsigned long long) * (2 * kGGStagesA + 2 * 8);
 }
 static inline size_t gg_packed_bytes(int bn, int ctiles, int chunks) {
     return (size_t)ctiles * chunks * sizeof(double) * kGGKC * (bn + 4);
@@ -107,8 +107,23 @@ template <> __device__ __forceinline__ void gg_sts_elem<float>(unsigned dst, dou
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"((float)v) : "memory");
 }
 
+// Log-field input (np.exp(self._x) of VirtualObservables.py:57): the conductivities are formed by one streaming pass before the
+// contraction kernel (inside it, 17 exp() per producer step tripled the FP64 instructions that compete with the DMMAs for the
+// pipe: 5.62 ms at config 3 against 4.26 ms + this pass).  rows = 1 for a field shared by the batch.
+template <typename T>
+__global__ void vo_exp_rows_kernel(const T *__restrict__ x, long long n, T *__restrict__ out) {
+    __shared__ double tab[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) tab[i] = kExp256Tab[i];
+    __syncthreads();
+    const unsigned tab32 = smem_u32(tab);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = (double)x[i];
+        out[i] = (T)(exp256_in_range(v) ? exp_tab256c(v, tab32) : exp(v));
+    }
+}
+
 // grid: (sample tiles of 64, column tiles of BN, parts of the contraction length = groups of whole strips)
-template <int BN, int NW, bool ALOG, typename T, typename TR>
+template <int BN, int NW, typename T, typename TR>
 __global__ void __launch_bounds__(gg_threads(NW), 1)
 vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T *__restrict__ y, const T *__restrict__ g,
                    long long g_stride, const double *__restrict__ Vp, TR *__restrict__ R, int m, int ldp, long long B,
@@ -128,7 +143,6 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     constexpr int WIN_ALL = NPROD * WIN_BYTES + YC * P * E;      // + the shared slot of zeros
     unsigned long long *bars = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(win + WIN_ALL) + 15) & ~(uintptr_t)15);
     unsigned long long *fullA = bars, *emptyA = bars + kGGStagesA, *fullB = bars + 2 * kGGStagesA, *emptyB = fullB + 8;
-    double *tab = reinterpret_cast<double *>(emptyB + 8);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long row0 = (long long)blockIdx.x * kGGBM;
@@ -147,7 +161,6 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
         for (int i = 0; i < SB; ++i) { mbar_init(fullB + i, 1); mbar_init(emptyB + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (ALOG && tid < 256) tab[tid] = kExp256Tab[tid];
     __syncthreads();
 
     if (warp < 8) {
@@ -243,7 +256,7 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
     const int ncol = G.ncol, ny = G.ny, nx = G.nx;
     const long long d = (long long)ncol * (ny + 1);
     const int nvw = (int)max(0ll, min(32ll, B - row0 - sh * 32));    // valid samples of this warp
-    const unsigned wb = smem_u32(win) + pw * WIN_BYTES, tab32 = smem_u32(tab);
+    const unsigned wb = smem_u32(win) + pw * WIN_BYTES;
     const unsigned zero_b = smem_u32(win) + NPROD * WIN_BYTES + lane * E;
     // copies: NW lanes per sample: lane group lq takes samples SPI i + lq (i < NW), lane lc of it the window column lc (< NW);
     // window columns NW (NW + 1) of sample ``lane``, and the Dirichlet values g[2 t], g[2 t + 1] of the mesh's first / last
@@ -349,23 +362,11 @@ vo_gridgemm_kernel(GGDev G, const T *__restrict__ a, long long a_stride, const T
             const unsigned a_dst = smem_u32(As) + 8u * (sa * A_STAGE + (NW * ch) * kGGLdA + sh * 32 + lane);
             double ul = ld(yc_b, 0), uc = ld(yc_b, 1);
             double aBj = ld(ab_b, 0), aAj = ld(aa_b, 0);
-            if constexpr (ALOG) {
-                if (has_a) {
-                    aAj = exp256_in_range(aAj) ? exp_tab256c(aAj, tab32) : exp(aAj);
-                    gg_sts_elem<T>(aa_b, aAj);
-                }
-            }
             double fh_l = (aBj + aAj) * (uc - ul);
 #pragma unroll
             for (int j = 0; j < NW; ++j) {
                 const double ur = ld(yc_b, j + 2), aBn = ld(ab_b, j + 1), un = ld(ya_b, j + 1);
-                double aAn = ld(aa_b, j + 1);
-                if constexpr (ALOG) {
-                    if (has_a) {
-                        aAn = exp256_in_range(aAn) ? exp_tab256c(aAn, tab32) : exp(aAn);
-                        gg_sts_elem<T>(aa_b + (unsigned)((j + 1) * P * E), aAn);
-                    }
-                }
+                const double aAn = ld(aa_b, j + 1);
                 const double fh_r = (aBn + aAn) * (ur - uc);
                 const double fv = (aAj + aAn) * (un - uc);
                 double Sv = fma(rh, fh_r - fh_l, fv - fvp[j]);
