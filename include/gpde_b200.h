@@ -152,7 +152,8 @@ int gpde_vo_plan_destroy(gpde_vo_plan *plan);
 int gpde_vo_plan_info(const gpde_vo_plan *plan, int64_t out[8]);
 
 /* Which kernels serve gpde_vo_residual_* for m weighting functions and elem_bytes (8 = f64, 4 = f32) I/O:
- * 3 = structured-grid rho kernel + V padding + FP64 tensor-core contraction (m > 32; three launches),
+ * 3 = structured pixel grid, m > 32: V packing + ONE kernel that produces the fine residual inside the FP64 tensor-core
+ *     contraction (vo_gridgemm.cuh) + the reduction of its partial tiles (three launches),
  * 2 = structured-grid kernel (V packing launch + one fused launch), 1 = generic fused kernel (one launch),
  * 0 = version-1 kernels (generic matvec + V padding + tensor-core contraction; three launches).  Informational (launch counting, tests); calls whose
  * pointers are not 16-byte aligned, that pass y = NULL or that ask for rho fall back from 2 to 1. */
