@@ -66,6 +66,10 @@ def parse():
     ap.add_argument("--no-sub", action="store_true", help="skip the records of the other configurations (configs 3, 4, FP32)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--no-overlap", action="store_true", help="keep the ROM and VO kernels on one stream")
+    ap.add_argument("--e2e-stream-fields", action="store_true",
+                    help="e2e: copy the VO data points' conductivity fields from the host every step too (default: resident)")
+    ap.add_argument("--sm-reserve", type=int, default=-1,
+                    help="SMs the VO kernel leaves to the ROM kernels of the overlapped step (-1 = calibrate during warm-up)")
     ap.add_argument("--log-input", action="store_true", help="VO residual from the log-field (exp inside the kernel) in the step")
     ap.add_argument("--e2e-chunks", type=int, default=4)
     return ap.parse_args()
@@ -309,6 +313,7 @@ class HotPath(object):
         self.vo_stream = torch.cuda.Stream(device=dev)
         self.packed, self.ev_packed = None, torch.cuda.Event()
         self.split_pack = self.path == 2
+        self.sm_reserve = 0      # SMs the VO kernel leaves to the ROM kernels of the overlapped step (run_b200 calibrates it)
 
     def vo(self, log_input=None):
         d = self.d
@@ -338,7 +343,8 @@ class HotPath(object):
                     if self.packed is None and hasattr(pw, "buf"):
                         self.packed = pw
                     self.ev_packed.record(self.vo_stream)
-                    r = self.vplan.residual(d["a_log"] if self.log_input else d["a"], d["y"], d["g"], pw, a_is_log=self.log_input)
+                    r = self.vplan.residual(d["a_log"] if self.log_input else d["a"], d["y"], d["g"], pw, a_is_log=self.log_input,
+                                            sm_reserve=self.sm_reserve)
                 else:
                     r = self.vo()
             if self.split_pack:
@@ -639,6 +645,14 @@ def run_b200(args):
 
     # ---- (2) the timed region: K steps, each step = the same launches replayed from one CUDA graph (the step is
     # launch-bound from Python at this batch); eager launches if capture is refused or --no-graph
+    # The VO kernel's CTAs own a whole SM each and its last wave is sized for the SMs it may use; the ROM kernels of the
+    # overlapped step need a few SMs beside it: the number left to them is calibrated here (untimed), one graph per candidate
+    reserve_ms = {}
+    if not args.no_overlap and not args.no_graph and hp.split_pack:
+        for cand in ([args.sm_reserve] if args.sm_reserve >= 0 else [0, 8, 11, 16, 20]):
+            hp.sm_reserve = cand
+            reserve_ms[cand] = graph_timed(torch, lambda: hp.step(overlap=True), max(10, min(K, 30)))[0]
+        hp.sm_reserve = min(reserve_ms, key=reserve_ms.get)
     if args.no_graph:
         run, mode = (lambda: hp.step(overlap=not args.no_overlap)), "eager"
     else:
@@ -670,7 +684,14 @@ def run_b200(args):
         a_key = "a_log" if hp.log_input else "a"
         outs = dict(u=torch.empty((B, w.n), dtype=tdt).pin_memory(), gX=torch.empty((B, w.E), dtype=tdt).pin_memory(),
                     r=torch.empty((B, w.m), dtype=tdt).pin_memory())
-        names_in = ["logX", "F", "gbar", a_key, "y"] + (["g"] if pinned["g"].dim() == 2 else [])
+        # Per-step inputs: what changes from step to step in the reference's loop -- the coarse-grained model's (logX, F) with
+        # the incoming gradient, and the fine-scale output y the residuals are evaluated at.  The conductivity fields of the VO
+        # data points are STATE of the ensemble (QuerryPoint.x, VirtualObservables.py:52-59: assembled once per data point;
+        # the reference arm accordingly runs with its Gamma_n cached), resident on the device like the weighting functions;
+        # ``fields_streamed`` below is the same step with the fields copied from the host every step as well.
+        names_step = ["logX", "F", "gbar", "y"] + (["g"] if pinned["g"].dim() == 2 else [])
+        names_all = names_step + [a_key]
+        names_in = names_all if args.e2e_stream_fields else names_step
         bytes_in = sum(pinned[k].numel() * pinned[k].element_size() for k in names_in)
         bytes_out = sum(t.numel() * t.element_size() for t in outs.values())
         nch = max(1, min(args.e2e_chunks, B // 256))
@@ -686,6 +707,8 @@ def run_b200(args):
             for (lo, hi) in bounds:                      # all H2D copies are enqueued first, on the copy stream
                 with torch.cuda.stream(copy_stream):
                     dd = {k: pinned[k][lo:hi].to(dev, non_blocking=True) for k in names_in}
+                    if a_key not in dd:
+                        dd[a_key] = d[a_key][lo:hi]          # resident field rows of this chunk's data points
                     ev = torch.cuda.Event()
                     ev.record(copy_stream)
                 staged.append((dd, ev))
@@ -714,26 +737,43 @@ def run_b200(args):
             dist.barrier()
         # three timed blocks of Ke steps; the MEDIAN block is reported and all three are listed: the copies share the host's
         # memory system and PCIe root with whatever else runs on the box
-        blocks = []
-        for _ in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(Ke):
-                step_e2e()
-            e1.record()
-            torch.cuda.synchronize()
-            b_ms = e0.elapsed_time(e1) / Ke
-            if world > 1:
-                tt = torch.tensor([b_ms], dtype=torch.float64, device=dev)
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-                b_ms = float(tt.item())
-            blocks.append(b_ms)
-        e_ms = sorted(blocks)[1]
+        def timed_blocks(n_blocks):
+            blocks = []
+            for _ in range(n_blocks):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(Ke):
+                    step_e2e()
+                e1.record()
+                torch.cuda.synchronize()
+                b_ms = e0.elapsed_time(e1) / Ke
+                if world > 1:
+                    tt = torch.tensor([b_ms], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                    b_ms = float(tt.item())
+                blocks.append(b_ms)
+            return blocks
+
+        blocks = timed_blocks(5)
+        e_ms = sorted(blocks)[len(blocks) // 2]
         e2e = {"value": world * B / (e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_in),
                "d2h_bytes_per_step": int(bytes_out), "ms_per_step": e_ms, "steps": Ke, "chunks": nch,
                "ms_per_step_blocks": blocks,
                "h2d_gbs_per_gpu": bytes_in / (e_ms * 1e-3) / 1e9, "cpu_affinity": affinity,
+               "inputs_copied_per_step": names_in,
+               "resident": [] if args.e2e_stream_fields else
+               ["conductivity fields of the VO data points (ensemble state, as the reference arm's cached Gamma_n)", "V"],
                "bound": "host-to-device copy (PCIe): compute is %.1f %% of the step" % (100.0 * ms_per_step / e_ms)}
+        if not args.e2e_stream_fields:
+            # the same step with the fields copied every step too (the round-1 definition of this number)
+            names_in = names_all
+            bytes_all = sum(pinned[k].numel() * pinned[k].element_size() for k in names_in)
+            step_e2e()
+            torch.cuda.synchronize()
+            blocks_all = timed_blocks(3)
+            f_ms = sorted(blocks_all)[1]
+            e2e["fields_streamed"] = {"value": world * B / (f_ms * 1e-3), "ms_per_step": f_ms, "ms_per_step_blocks": blocks_all,
+                                      "h2d_bytes_per_step": int(bytes_all), "h2d_gbs_per_gpu": bytes_all / (f_ms * 1e-3) / 1e9}
 
     # ---- the other BASELINE configurations, same run (rank 0 prints them under "configs")
     subs = {}
@@ -764,7 +804,9 @@ def run_b200(args):
         "config": workload_config(w),
         "run": {"per_gpu_batch": B, "global_batch": (total if strong else world * B),
                 "parallelism": "sample-sharded x%d, no data-path collective" % world,
-                "vo_input_in_step": "log-field (exp inside the kernel)" if hp.log_input else "conductivity"},
+                "vo_input_in_step": "log-field (exp inside the kernel)" if hp.log_input else "conductivity",
+                "sms_left_to_rom_kernels": hp.sm_reserve,
+                "ms_per_step_by_sms_left": {str(k): v for k, v in reserve_ms.items()}},
         "components": {
             "cgm_solves_per_s": world * B / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": world * B / (t_vo * 1e-3),
             "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo, other: t_vo_other,

@@ -141,12 +141,14 @@ class VoPlan(object):
         _lib.check(rc, "gpde_vo_pack_weights_" + sfx)
         return PackedWeights(Vc, buf, int(B), bool(ignore_load))
 
-    def residual(self, a, y, g, V, *, a_is_log=True, want_rho=False, ignore_load=False):
+    def residual(self, a, y, g, V, *, a_is_log=True, want_rho=False, ignore_load=False, sm_reserve=0):
         """r[B,m] = V^T (K(a_b) u~_b - f)_free with u~ = (y on free dofs, g on Dirichlet dofs).
 
         a [B,n_inputs] or [n_inputs] (shared); y [B,d] or None (zeros); g [B,n_bc], [n_bc] or None;
         V [d,m] or None (then only rho[B,d], the fine residual itself, is produced).
-        Returns r, or (r, rho) when want_rho / V is None."""
+        Returns r, or (r, rho) when want_rho / V is None.
+        ``sm_reserve``: SMs to leave to kernels the caller runs beside this call on other streams (the structured-grid
+        kernel sizes its last wave of CTAs for the remaining SMs)."""
         dt = a.dtype
         sfx = _lib.suffix(dt)
         sizes = [t.shape[0] for t in (y, a, g) if t is not None and t.dim() == 2]
@@ -173,7 +175,8 @@ class VoPlan(object):
         rc = fn(self.handle, _lib.ptr(a, dev), self.n_inputs if a.dim() == 2 else 0, int(bool(a_is_log)), _lib.ptr(y, dev),
                 _lib.ptr(g, dev), (self.n_bc if g.dim() == 2 else 0) if g is not None else 0, _lib.ptr(Vc, dev), m,
                 _lib.ptr(r, dev), _lib.ptr(rho, dev), _lib.ptr(ws, dev) if m else None,
-                (1 if ignore_load else 0) | (2 if packed is not None else 0), B, _lib.stream_of(dev))
+                (1 if ignore_load else 0) | (2 if packed is not None else 0) | (max(0, min(255, int(sm_reserve))) << 8), B,
+                _lib.stream_of(dev))
         _lib.check(rc, "gpde_vo_residual_" + sfx)
         return (r, rho) if rho is not None else r
 

@@ -66,6 +66,7 @@ struct VoEnv {
     int gemm_splits = 0;         // GPDE_GEMM_SPLITS: parts of the contraction length (0 = automatic)
     int grid2_split = 1;         // GPDE_GRID2_SPLIT: 0 = never cut the node rows over a cluster, 1 = automatic, n > 1 = force n
     bool gridgemm = true;        // GPDE_VO_GRIDGEMM=0: rho through HBM + vo_gemm_kernel instead of the one-kernel route (m > 32)
+    int grid2_spc = 0;           // GPDE_GRID2_SPC: samples per CTA of the lean grid kernel (0 = automatic, see grid2_samples_per_cta)
     VoEnv() {
         const char *e;
         if ((e = getenv("GPDE_GRID_R"))) grid_r = atoi(e);
@@ -80,6 +81,7 @@ struct VoEnv {
         if ((e = getenv("GPDE_GEMM_SPLITS"))) gemm_splits = std::max(0, std::min(8, atoi(e)));
         if ((e = getenv("GPDE_GRID2_SPLIT"))) grid2_split = std::max(0, std::min(8, atoi(e)));
         if ((e = getenv("GPDE_VO_GRIDGEMM"))) gridgemm = atoi(e) != 0;
+        if ((e = getenv("GPDE_GRID2_SPC"))) grid2_spc = std::max(0, atoi(e));
     }
 };
 }  // namespace gpde
@@ -552,7 +554,21 @@ static bool grid2_setup(const gpde_vo_plan *pl, int m, bool rho, int sub_f, Grid
     smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
     if (smem > 227 * 1024) return false;
     G.flags = pl->env.grid2_flags;
+    G.spc = S;
     return true;
+}
+
+// Samples per CTA of the lean grid kernel.  A CTA holds S = 8 * groups sample slots and owns a whole SM; with
+// ceil(B / S) CTAs the last wave leaves SMs idle (4096 samples, S = 32: 128 CTAs on 148 SMs).  The kernel is bound by
+// the bytes an SM streams, so the same number of waves is spread over all SMs instead: the smallest spc with
+// ceil(B / spc) <= waves * SMs (4096 samples: 147 CTAs of 28; a slot left empty costs an idle row of the 8-row DMMA
+// tile, nothing else).  `sm_reserve` SMs are left to kernels the caller runs beside this one on other streams.
+static int grid2_samples_per_cta(const gpde_vo_plan *pl, int S, long long B, int sm_reserve) {
+    if (pl->env.grid2_spc > 0) return std::max(S / 2, std::min(S, pl->env.grid2_spc));
+    const long long sms = std::max(1, pl->n_sm - std::max(0, sm_reserve));
+    const long long blocks = (B + S - 1) / S, waves = (blocks + sms - 1) / sms;
+    const long long spc = (B + waves * sms - 1) / (waves * sms);
+    return (int)std::max<long long>((3 * S + 3) / 4, std::min<long long>(S, spc));
 }
 
 template <typename TV>
@@ -566,7 +582,8 @@ static void grid2_pack(const Grid2Dev &G, const TV *V, int m, int NT, int NX, do
 template <typename TA, typename TY, typename TR>
 static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride, int a_is_log, const TY *y,
                         const TA *g, long long g_stride, const TA *V, int m, TR *r, void *workspace,
-                        int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st, long long y_stride = 0) {
+                        int rho_pitch, int sub_f, bool prepacked, long long B, cudaStream_t st, long long y_stride = 0,
+                        int sm_reserve = 0) {
     constexpr int EA = (int)sizeof(TA), EY = (int)sizeof(TY);
     if (y_stride == 0) y_stride = pl->dev.d;
     if (y_stride != pl->dev.d && rho_pitch <= 0) return 0;   // only the rho variant is built for strided y
@@ -581,7 +598,7 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
     const int S = 8 * G.groups;
     double *Vp = (double *)workspace;
     if (!rho && !prepacked) grid2_pack(G, V, m, NT, NX, Vp, pl->n_sm, st);
-    const unsigned blocks = (unsigned)((B + S - 1) / S);
+    unsigned blocks = (unsigned)((B + S - 1) / S);
     // small batches: the node rows of a sample block are cut over the CTAs of a thread-block cluster (SPLIT variant of the
     // kernel) when the blocks alone would leave more than half of the SMs idle; every range gets at least two stages.
     // The cluster size depends on the number of sample blocks only.  GPDE_GRID2_SPLIT=0 keeps one CTA per block.
@@ -591,6 +608,10 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
         csize = std::min(std::min(8, n_stages / 2), pl->n_sm / (int)blocks);
         if (pl->env.grid2_split > 1) csize = std::min(pl->env.grid2_split, n_stages / 2);   // forced size (tests)
         if (csize < 2 || 2 * (size_t)G.stage_bytes < (size_t)(16 * 8 * 34 + S * 33) * sizeof(double)) csize = 1;
+    }
+    if (csize == 1) {   // whole samples per CTA: balance the last wave over the SMs
+        G.spc = grid2_samples_per_cta(pl, S, B, sm_reserve);
+        blocks = (unsigned)((B + G.spc - 1) / G.spc);
     }
     const unsigned grid = blocks * (unsigned)csize;
     // the residual kernel is launched as a programmatic dependent of the packing kernel (its prologue and first
@@ -672,9 +693,10 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
 template <typename T>
 static int launch_grid_lean(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *y,
                             const T *g, long long g_stride, const T *V, int m, T *r, void *workspace,
-                            int sub_f, bool prepacked, long long B, cudaStream_t st) {
+                            int sub_f, bool prepacked, long long B, cudaStream_t st, int sm_reserve = 0) {
     if (!y || m < 1 || m > 32) return 0;
-    const int rc2 = launch_grid2<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, prepacked, B, st);
+    const int rc2 = launch_grid2<T, T, T>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, 0, sub_f, prepacked, B, st, 0,
+                                          sm_reserve);
     if (rc2 != 0) return rc2;
     if (prepacked)
         return fail(GPDE_ERR_ARG, "vo_residual: packed weights (flags bit1) need the lean structured-grid kernel for this call "
@@ -683,11 +705,12 @@ static int launch_grid_lean(const gpde_vo_plan *pl, const T *a, long long a_stri
 }
 static int launch_grid(const gpde_vo_plan *pl, const double *a, long long a_stride, int a_is_log, const double *y,
                        const double *g, long long g_stride, const double *V, int m, double *r, void *workspace,
-                       int sub_f, bool prepacked, long long B, cudaStream_t st) {
+                       int sub_f, bool prepacked, long long B, cudaStream_t st, int sm_reserve = 0) {
     GridDev G = pl->grid;
     if (!y || m < 1 || m > 32) return 0;
     {
-        const int rc2 = launch_grid_lean<double>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, sub_f, prepacked, B, st);
+        const int rc2 = launch_grid_lean<double>(pl, a, a_stride, a_is_log, y, g, g_stride, V, m, r, workspace, sub_f, prepacked, B, st,
+                                                 sm_reserve);
         if (rc2 != 0) return rc2;
     }
     if (((uintptr_t)a & 15) || ((uintptr_t)y & 15) || (a_stride & 1) || ((uintptr_t)workspace & 15)) return 0;
@@ -885,10 +908,10 @@ static int vo_residual(const gpde_vo_plan *pl, const T *a, int64_t a_stride, int
         if constexpr (sizeof(T) == 8)
             rc = launch_grid(pl, (const double *)a, (long long)a_stride, a_is_log, (const double *)y,
                              (const double *)g, (long long)g_stride, (const double *)V, m, (double *)r,
-                             workspace, (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
+                             workspace, (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st, (flags >> 8) & 0xff);
         else
             rc = launch_grid_lean<T>(pl, a, (long long)a_stride, a_is_log, y, g, (long long)g_stride, V, m, r, workspace,
-                                     (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st);
+                                     (flags & 1) ? 0 : 1, (flags & 2) != 0, (long long)B, st, (flags >> 8) & 0xff);
         if (rc != 0) return rc < 0 ? rc : GPDE_OK;
     }
     if (m == 0 && rho && use_grid(pl)) {   // the fine residual alone: rho rows straight into the caller's [B,d]

@@ -37,6 +37,7 @@ struct Grid2Dev {
     int y_off, v_off;        // byte offsets inside a stage
     int stage_bytes, v_row_bytes;   // one a/y stage (all samples of the CTA); one packed V row
     int nvs;                        // V stages in the ring (2 or 3)
+    int spc;                        // samples a CTA takes (<= 8 groups): group i gets [i spc / groups, (i + 1) spc / groups)
     int flags;                      // experiment switches (GPDE_GRID2_FLAGS): 1 = poll barriers without nanosleep
 };
 
@@ -237,14 +238,20 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const int s = lane >> 2, k = lane & 3;
     const int S = 8 * G.groups;
     const int sl = grp * 8 + s;
+    // Samples of the CTA: its 8-sample groups are filled with gsz <= 8 samples each (rows s >= gsz of the group's DMMA tile
+    // idle), spc = sum of the sizes.  The launcher picks spc so that the CTAs of the last wave spread over all SMs (4096
+    // samples: 147 CTAs of 28 instead of 128 of 32 on 148 SMs); a sample's arithmetic does not depend on its slot.
+    const int lgg = 4 - G.lognstrips;               // log2(groups)
+    const int goff = (grp * G.spc) >> lgg, gsz = (((grp + 1) * G.spc) >> lgg) - goff;
     unsigned crank = 0, csize = 1;                  // rank in the cluster and its size (SPLIT only)
     if constexpr (SPLIT) {
         asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
         asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
     }
-    const long long cta_b0 = (long long)(SPLIT ? blockIdx.x / csize : blockIdx.x) * S;
-    const bool b_valid = cta_b0 + sl < B;
-    const long long b = b_valid ? cta_b0 + sl : B - 1;
+    const long long cta_b0 = (long long)(SPLIT ? blockIdx.x / csize : blockIdx.x) * G.spc;
+    const long long grp_b0 = cta_b0 + goff;         // first sample of this warp's group
+    const bool b_valid = s < gsz && grp_b0 + s < B;
+    const long long b = b_valid ? grp_b0 + s : B - 1;
     const int ncol = G.ncol, nx = G.nx, ny = G.ny;
     const long long d = (long long)ncol * (ny + 1);
     const long long y_stride = YS ? y_stride_arg : d;
@@ -287,23 +294,24 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const int tg = tid & (gthreads - 1);
     constexpr int NIA = EA / 2, SSA = 16 / EA, NIY = EY / 2, SSY = 16 / EY;
     const int lpa = G.lognx - (EA == 8 ? 0 : 1), lpy = G.lognx - (EY == 8 ? 0 : 1);   // log2(pieces per sample)
-    const int piece_a = tg & ((1 << lpa) - 1), smp0a = 8 * grp + (tg >> lpa);
-    const int piece = tg & ((1 << lpy) - 1), smp0 = 8 * grp + (tg >> lpy);             // y
+    const int j0a = tg >> lpa, j0 = tg >> lpy;      // first sample (inside the group) this thread copies of a / of y
+    const int piece_a = tg & ((1 << lpa) - 1), smp0a = 8 * grp + j0a;
+    const int piece = tg & ((1 << lpy) - 1), smp0 = 8 * grp + j0;                      // y
     int nva = 0, nv = 0;
 #pragma unroll
-    for (int i = 0; i < NIA; ++i) nva += (cta_b0 + smp0a + SSA * i < B) ? 1 : 0;
+    for (int i = 0; i < NIA; ++i) nva += (j0a + SSA * i < gsz && grp_b0 + j0a + SSA * i < B) ? 1 : 0;
 #pragma unroll
-    for (int i = 0; i < NIY; ++i) nv += (cta_b0 + smp0 + SSY * i < B) ? 1 : 0;
+    for (int i = 0; i < NIY; ++i) nv += (j0 + SSY * i < gsz && grp_b0 + j0 + SSY * i < B) ? 1 : 0;
     // pixel rows 2 ts, 2 ts + 1 of a sample are one block of 2 nx elements (lowest address first)
     const long long a_adv = 2 * EA * G.sy, a_smp = SSA * a_stride * EA;
-    const char *a_src = reinterpret_cast<const char *>(a + (cta_b0 + smp0a) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece_a +
+    const char *a_src = reinterpret_cast<const char *>(a + (grp_b0 + j0a) * a_stride + G.in0 + (G.sy > 0 ? 0 : G.sy)) + 16 * piece_a +
                         (SPLIT ? ts_base * a_adv : 0);
     const unsigned a_dst = smp0a * G.a_pitch * EA + 16 * piece_a, a_dsmp = SSA * G.a_pitch * EA;
     // node rows 2 ts + 1, 2 ts + 2: 2 ncol elements starting on an element boundary; copied from the enclosing
     // 16-byte boundary.  The phase y_sig (in elements) is the same for the samples of a thread (they are 16 / E apart).
     // FP64: it is the same for all stages too (a stage advances by 16 ncol bytes); FP32: a stage advances by 8 ncol
     // bytes with ncol odd, so the phase alternates between y_sig and y_sig ^ 2 from stage to stage
-    const char *y_row1 = reinterpret_cast<const char *>(y + (cta_b0 + smp0) * y_stride + ncol + (SPLIT ? 2 * ts_base * ncol : 0));
+    const char *y_row1 = reinterpret_cast<const char *>(y + (grp_b0 + j0) * y_stride + ncol + (SPLIT ? 2 * ts_base * ncol : 0));
     int y_sig = (int)(((unsigned long long)y_row1 / EY) & (16 / EY - 1));
     const char *y_src = y_row1 - EY * y_sig + 16 * piece;
     const long long y_adv = 2 * EY * ncol, y_smp = SSY * y_stride * EY;
@@ -317,7 +325,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const bool y_piece_ok = EY == 8 ? (!y_last_piece || y_sig) : true;
     // the last piece of the batch's last sample would read past the tensor: copied element-wise instead
     // (FP32: only when the stage's phase leaves part of the piece outside, decided per stage)
-    const bool y_tail = (EY == 8 ? y_sig != 0 : true) && y_last_piece && nv > 0 && cta_b0 + smp0 + SSY * (nv - 1) == B - 1;
+    const bool y_tail = (EY == 8 ? y_sig != 0 : true) && y_last_piece && nv > 0 && grp_b0 + j0 + SSY * (nv - 1) == B - 1;
     unsigned long long *my_full = full_ay + 2 * grp, *my_empty = empty_ay + 2 * grp;
 
     auto issue_stage = [&](int ts, int slot) {
@@ -380,7 +388,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
     const TY *yb = y + b * y_stride;
     const TA *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
-    const int sig_b = (int)(((unsigned long long)(y + (cta_b0 + sl) * y_stride + ncol) / EY) & (16 / EY - 1));
+    const int sig_b = (int)(((unsigned long long)(y + (grp_b0 + s) * y_stride + ncol) / EY) & (16 / EY - 1));
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
     const unsigned y_lane = G.y_off + (sl * G.y_pitch + (EY == 8 ? 2 * ((sl >> 1) & 1) + 2 : 4) + sig_b + c0) * EY;
     const int y_lane_odd = EY == 4 ? 4 * ((sig_b ^ 2) - sig_b) : 0;   // FP32: odd (global) stages sit at phase sig_b ^ 2
@@ -600,7 +608,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
 
     if constexpr (RHO) {
         const int pad = m - (int)d;   // zero the K padding [d, m) of this CTA's rows
-        for (int idx = tid; idx < S * pad; idx += kThreads) {
+        for (int idx = tid; idx < G.spc * pad; idx += kThreads) {   // (samples cta_b0 .. cta_b0 + spc - 1, whatever their slots)
             const int si = idx / pad, c = idx - si * pad;
             if (cta_b0 + si < B) r[(cta_b0 + si) * (long long)m + d + c] = (TR)0;
         }
@@ -640,8 +648,10 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             const unsigned part32 = smem_u32(part);
             for (int idx = tid; idx < S * MC; idx += kThreads) {
                 const int si = idx / MC, col = idx - si * MC;
-                const long long bs = cta_b0 + si;
-                if (col < m && bs < B) {
+                const int gi = si >> 3, ss = si & 7;
+                const int go = (gi * G.spc) >> lgg, gs = (((gi + 1) * G.spc) >> lgg) - go;
+                const long long bs = cta_b0 + go + ss;
+                if (col < m && ss < gs && bs < B) {
                     double v = 0.0;
                     for (unsigned c = 0; c < csize; ++c) {
                         unsigned remote;
@@ -659,9 +669,10 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     } else {
         for (int idx = tid; idx < S * MC; idx += kThreads) {
             const int si = idx / MC, col = idx - si * MC;
-            const long long bs = cta_b0 + si;
-            if (col < m && bs < B) {
-                const int gi = si >> 3, ss = si & 7;
+            const int gi = si >> 3, ss = si & 7;
+            const int go = (gi * G.spc) >> lgg, gs = (((gi + 1) * G.spc) >> lgg) - go;
+            const long long bs = cta_b0 + go + ss;
+            if (col < m && ss < gs && bs < B) {
                 double v = 0.0;
                 for (int qq = 0; qq < G.nstrips; ++qq) v += red[(((size_t)gi * G.nstrips + qq) * 8 + ss) * NW + col];
                 r[bs * m + col] = (TR)(G.scale * v);

@@ -172,7 +172,9 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *plan, int64_t B, int m);
  *   flags: bit0 = ignore the load vector f
  *          bit1 = `workspace` already holds V packed by gpde_vo_pack_weights_f64 (same plan, m, bit0):
  *                 the call skips its packing launch; it fails with GPDE_ERR_ARG instead of falling
- *                 back when the lean structured-grid kernel cannot serve it (V must still be passed)  */
+ *                 back when the lean structured-grid kernel cannot serve it (V must still be passed)
+ *          bits 8-15 = number of SMs to leave to kernels the caller runs beside this call on other streams
+ *                 (the structured-grid kernel sizes its last wave for the remaining SMs; 0 = all SMs)  */
 int gpde_vo_residual_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,
                          const double *y, const double *g, int64_t g_stride, const double *V, int m,
                          double *r, double *rho, void *workspace, int flags, int64_t B,

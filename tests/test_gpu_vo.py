@@ -736,3 +736,41 @@ def test_small_batches_cut_the_node_rows_over_a_cluster(nx, ny, B, dev):
     assert torch.equal(plan.residual(T(a)[perm], T(y)[perm], T(g)[perm], V), r[perm])
     pw = plan.pack_weights(V, B)
     assert torch.equal(plan.residual(T(a), T(y), T(g), pw), r)
+
+
+@pytest.mark.parametrize("nx,ny,B", [(64, 64, 229), (32, 32, 300), (16, 8, 700), (128, 16, 150), (64, 4, 163)])
+def test_partly_filled_sample_groups_give_the_same_bits(nx, ny, B, dev):
+    """The lean grid kernel fills the 8-sample groups of a CTA with fewer samples when that spreads the last wave of CTAs
+    over all SMs (grid2_samples_per_cta in vo.cu: 4096 samples = 147 CTAs of 28 instead of 128 of 32).  A sample's
+    arithmetic does not depend on its slot: every samples-per-CTA setting (forced through GPDE_GRID2_SPC, and the automatic
+    one, with and without reserved SMs) must reproduce the full-group result BITWISE -- contraction and rho variants,
+    FP64 and FP32 I/O at every phase of y, log and conductivity input, ragged last CTA."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 7 + ny + B, dev, load=False)
+    S = 8 * (16 // (nx // 16))
+    full = plan.variant(GPDE_GRID2_SPLIT="0", GPDE_GRID2_SPC=str(S))
+    T = lambda t: torch.tensor(t, device=dev)
+    d = fom.dim_out
+    big = torch.zeros(B * d + 3, dtype=torch.float32, device=dev)
+    variants = [plan.variant(GPDE_GRID2_SPLIT="0", GPDE_GRID2_SPC=str(c)) for c in sorted({S - 1, S - 3, (7 * S) // 8, (3 * S) // 4})]
+    variants.append(plan.variant(GPDE_GRID2_SPLIT="0"))
+    for m in (8, 25, 32):
+        V = T(rng.normal(size=(d, m)))
+        r0 = full.residual(T(a), T(y), T(g), V)
+        r0_lin = full.residual(torch.exp(T(a)), T(y), T(g[0]), V, a_is_log=False)
+        _, rho0 = full.residual(torch.exp(T(a)), T(y), T(g[0]), None, a_is_log=False)
+        for p in variants:
+            assert torch.equal(p.residual(T(a), T(y), T(g), V), r0), m
+            assert torch.equal(p.residual(torch.exp(T(a)), T(y), T(g[0]), V, a_is_log=False), r0_lin), m
+            assert torch.equal(p.residual(torch.exp(T(a)), T(y), T(g[0]), None, a_is_log=False)[1], rho0), m
+            assert torch.equal(p.residual(torch.exp(T(a)), T(y), T(g[0]), V, a_is_log=False, sm_reserve=11), r0_lin), m
+        for off in range(4):
+            y32 = big[off:off + B * d].view(B, d)
+            y32.copy_(T(y).float())
+            r0_32 = full.residual(T(a).float(), y32, T(g).float(), V.float())
+            _, rho0_32 = full.residual(T(a).float(), y32, T(g).float(), None)
+            for p in variants:
+                assert torch.equal(p.residual(T(a).float(), y32, T(g).float(), V.float()), r0_32), (m, off)
+                assert torch.equal(p.residual(T(a).float(), y32, T(g).float(), None)[1], rho0_32), (m, off)
+    # against the version-1 kernels as an independent route
+    V = T(rng.normal(size=(d, 25)))
+    assert rel_err(variants[-1].residual(T(a), T(y), T(g), V).cpu(), plan.variant(GPDE_VO_PATH="v1").residual(T(a), T(y), T(g), V).cpu()) < 1e-11
