@@ -66,6 +66,7 @@ struct VoEnv {
     int gemm_splits = 0;         // GPDE_GEMM_SPLITS: parts of the contraction length (0 = automatic)
     int grid2_split = 1;         // GPDE_GRID2_SPLIT: 0 = never cut the node rows over a cluster, 1 = automatic, n > 1 = force n
     bool gridgemm = true;        // GPDE_VO_GRIDGEMM=0: rho through HBM + vo_gemm_kernel instead of the one-kernel route (m > 32)
+    bool fused_t = true;         // GPDE_VO_FUSED_T=0: residual_T as expansion kernel + marching kernel (w [B,d] through HBM)
     int grid2_spc = 0;           // GPDE_GRID2_SPC: samples per CTA of the lean grid kernel (0 = automatic, see grid2_samples_per_cta)
     VoEnv() {
         const char *e;
@@ -82,6 +83,7 @@ struct VoEnv {
         if ((e = getenv("GPDE_GRID2_SPLIT"))) grid2_split = std::max(0, std::min(8, atoi(e)));
         if ((e = getenv("GPDE_VO_GRIDGEMM"))) gridgemm = atoi(e) != 0;
         if ((e = getenv("GPDE_GRID2_SPC"))) grid2_spc = std::max(0, atoi(e));
+        if ((e = getenv("GPDE_VO_FUSED_T"))) fused_t = atoi(e) != 0;
     }
 };
 }  // namespace gpde
@@ -688,6 +690,52 @@ static int launch_grid2(const gpde_vo_plan *pl, const TA *a, long long a_stride,
     return 1;
 }
 
+// Transposed application q = K_ff(a) (V s) on the reference's pixel meshes in ONE kernel (WT variant of vo_grid2_kernel):
+// V^T packed in fragment order (vo_grid2_pack_t_kernel, 4 us), then the marching kernel produces the rows of w = s V^T
+// in shared memory itself.  Returns 1 if it served the call, 0 if the two-kernel route should (mesh / alignment / shared
+// memory), <0 on error.  s, V and a share the element type T; q too.
+template <typename T>
+static int launch_grid2_wt(const gpde_vo_plan *pl, const T *a, long long a_stride, int a_is_log, const T *V, int mw, const T *s,
+                           T *q, void *workspace, long long B, cudaStream_t st) {
+    constexpr int EA = (int)sizeof(T);
+    if (!pl->env.fused_t || mw < 1 || mw > 32) return 0;
+    Grid2Dev G;
+    int NT, NX;
+    size_t smem;
+    if (!grid2_setup(pl, 0, true, 0, G, NT, NX, smem, EA, 8)) return 0;
+    if (((uintptr_t)a & 15) || ((a_stride * EA) & 15) || ((G.in0 * EA) & 15) || ((G.sy * EA) & 15) || ((uintptr_t)workspace & 15)) return 0;
+    const int KS = mw <= 16 ? 4 : (mw <= 28 ? 7 : 8);
+    G.v_row_bytes = G.nstrips * 2 * KS * 256;
+    const size_t fixed = smem;                  // (rho variant: no V stages counted yet)
+    G.nvs = (fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2;
+    if (pl->env.grid2_nvs == 2 || pl->env.grid2_nvs == 3) G.nvs = pl->env.grid2_nvs;
+    smem = fixed + (size_t)G.nvs * 2 * G.v_row_bytes;
+    if (smem > 227 * 1024) return 0;
+    const int S = 8 * G.groups, d = pl->dev.d;
+    double *Vp = (double *)workspace;
+    {
+        const long long total = (long long)(G.ny + 1) * (G.v_row_bytes / 8);
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 8);
+        vo_grid2_pack_t_kernel<T><<<grid, 256, 0, st>>>(G, V, mw, KS, Vp);
+    }
+    G.spc = grid2_samples_per_cta(pl, S, B, 0);
+    const unsigned blocks = (unsigned)((B + G.spc - 1) / G.spc);
+#define GPDE_LAUNCH_GRID2_WT(KSV)                                                                                \
+    {                                                                                                            \
+        auto kern = a_is_log ? vo_grid2_kernel<1, 0, true, false, true, T, double, T, false, KSV>                \
+                             : vo_grid2_kernel<1, 0, true, false, false, T, double, T, false, KSV>;              \
+        GPDE_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+        kern<<<blocks, 512, smem, st>>>(G, a, a_stride, a_is_log, (const double *)nullptr, 0ll, s, (long long)mw, \
+                                        (const double *)Vp, d, q, B);                                            \
+    }
+    if (KS == 4) GPDE_LAUNCH_GRID2_WT(4)
+    else if (KS == 7) GPDE_LAUNCH_GRID2_WT(7)
+    else GPDE_LAUNCH_GRID2_WT(8)
+#undef GPDE_LAUNCH_GRID2_WT
+    GPDE_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
 // Structured-grid path.  Returns 1 if it served the call, 0 if the caller should use the generic kernels (alignment /
 // size conditions not met), <0 on error.  FP32 I/O: the lean kernel only.
 template <typename T>
@@ -1004,6 +1052,10 @@ static int vo_residual_T(const gpde_vo_plan *pl, const T *a, int64_t a_stride, i
     if (!a || !V || !s || !q || !workspace) return fail(GPDE_ERR_ARG, "vo_residual_T: null argument");
     DeviceGuard guard(pl->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (use_grid(pl) && m <= 32) {   // one kernel: w = s V^T never leaves the SM
+        const int rc = launch_grid2_wt<T>(pl, a, (long long)a_stride, a_is_log, V, m, s, q, workspace, (long long)B, st);
+        if (rc != 0) return rc < 0 ? rc : GPDE_OK;
+    }
     if constexpr (sizeof(T) == 4) {
         // FP32 I/O on the reference's pixel meshes, m <= 32: the same two launches as FP64 (s, V converted on load by the
         // expansion kernel; w stays FP64 workspace; the marching kernel stages a as floats and stores q as floats)
@@ -1249,8 +1301,11 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
         need = std::max(need, sizeof(double) * ((size_t)B * mp + mp * ldb + (size_t)B * pl->dev.d));
     }
     if (m > 32) need = std::max(need, gridgemm_workspace_bytes(pl, (long long)B, m));
-    if (pl->grid.ok && m > 0 && m <= 32)   // packed V (+ the per-row tile masks of the lean kernel)
+    if (pl->grid.ok && m > 0 && m <= 32) {   // packed V (+ the per-row tile masks of the lean kernel)
         need = std::max(need, grid_packed_bytes(pl->grid, 4) + (size_t)(pl->grid.ny + 1) * kGrid2MaskBytes);
+        // packed V^T rows of the one-kernel transposed application (launch_grid2_wt): <= 8 k-steps
+        need = std::max(need, (size_t)(pl->grid.ny + 1) * (size_t)((pl->grid.nx + 15) / 16) * 2 * 8 * 256);
+    }
     return need;
 }
 

@@ -175,6 +175,21 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const TV *__restrict__ V, int m
     }
 }
 
+// Transposed application (WT variant of the kernel below): V[d,mw] row-major -> per node row t the B fragments of
+// w_row = s V_row^T (mma.sync.m8n8k4.f64: 8 samples x 8 nodes, contraction over the weighting functions):
+//   [strip q][n-tile nt < 2][k-step ks < KS][lane]:  V[t*ncol + 16 q + 8 nt + lane / 4][4 ks + lane % 4]  (0 outside V)
+template <typename TV>
+__global__ void vo_grid2_pack_t_kernel(Grid2Dev G, const TV *__restrict__ V, int mw, int KS, double *__restrict__ Vp) {
+    const int per_row = G.v_row_bytes / 8;
+    const long long total = (long long)(G.ny + 1) * per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / per_row), e = (int)(i - (long long)t * per_row);
+        const int lane = e & 31, ks = (e >> 5) % KS, qn = (e >> 5) / KS;          // qn = 2 q + nt
+        const int c = 8 * qn + (lane >> 2), j = 4 * ks + (lane & 3);
+        Vp[i] = (c < G.ncol && j < mw) ? (double)V[((long long)t * G.ncol + c) * mw + j] : 0.0;
+    }
+}
+
 // the B fragments and DMMAs of the n-tiles named by the compile-time MASK (straight-line code per mask value: the tiles'
 // accumulator chains are independent and interleave)
 template <int NT, int MASK, typename LoadPair>
@@ -209,8 +224,16 @@ __device__ __forceinline__ void grid2_contract(unsigned msk, double (&acc)[NT][2
 // it with the contraction switched off (that rebuilds the marching state: previous node row, previous pixel row, vertical
 // fluxes); each CTA reduces its strips as usual, the partial results meet in rank order through distributed shared memory
 // on rank 0.  The cut depends only on the number of sample blocks of the call, never on a sample's position in the batch.
+// WT (KS > 0; rho variant only): the transposed application q = K_ff(a) (V s) = Gamma^T s (VirtualObservables.py:663) in ONE
+// kernel -- "accumulating the residual gradient directly": the node rows of w = s V^T are not staged from global memory
+// but PRODUCED by the group's warps, a stage ahead of their use, straight into the y slots of the stage: a warp forms its
+// 8 samples x 16 columns of a node row with 2 x KS DMMAs (A fragments = the samples' s, KS k-steps, in registers for the
+// whole kernel; B fragments from the packed V^T rows of the V ring) and its D fragments go to shared memory as 16-byte
+// pieces (row pitch nx inside a slot); the group's full barrier counts the warps' arrivals beside the threads' cp.async
+// arrivals of the conductivity rows.  w [B,d] (134 MB written and read back at config 2) never exists.  In this variant
+// `g` / `g_stride` carry s [B,mw] and mw (the Dirichlet data of the transposed application are zero), `y` is unused.
 template <int NT, int NX, bool RHO, bool YS, bool ALOG, typename TA = double, typename TY = double, typename TR = double,
-          bool SPLIT = false>
+          bool SPLIT = false, int KS = 0>
 __global__ void __launch_bounds__(512, 1)
 vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_is_log,
                 const TY *__restrict__ y, long long y_stride_arg, const TA *__restrict__ g, long long g_stride,
@@ -220,6 +243,8 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     // one more live value shifts the register allocation of the other variants by ~3 % (measured A/B on one box)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int kThreads = 512, kWarps = 16;
+    constexpr bool WT = KS > 0;
+    static_assert(!WT || (RHO && !YS && !SPLIT && sizeof(TY) == 8), "WT: rho variant with FP64 y slots");
     constexpr int NP = 2 * NT;                      // B-fragment pairs per strip and node row
     constexpr int EA = (int)sizeof(TA), EY = (int)sizeof(TY);   // bytes per staged element
     // shared memory: 2 a/y stages | nvs V stages | barriers | exp table
@@ -273,7 +298,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     }
     if (tid == 0) {
         for (int i = 0; i < 2 * G.groups; ++i) {
-            mbar_init(full_ay + i, gthreads);
+            mbar_init(full_ay + i, gthreads + (WT ? G.nstrips : 0));
             mbar_init(empty_ay + i, G.nstrips);
         }
         for (int i = 0; i < G.nvs; ++i) {
@@ -333,7 +358,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
 #pragma unroll
         for (int i = 0; i < NIA; ++i)
             if (i < nva) cp_async16_u32(sb + a_dst + i * a_dsmp, a_src + i * a_smp);
-        if (y_piece_ok) {
+        if (!WT && y_piece_ok) {
             const int nvy = nv - ((y_tail && ts == n_stages - 1 && (EY == 8 || y_sig < 2)) ? 1 : 0);
             if constexpr (EY == 8) {
 #pragma unroll
@@ -374,12 +399,14 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         int v_next = vst[0], v_islot = vst[1];
         mbar_arrive_expect_tx(full_v + v_islot, bytes);
         bulk_g2s(v_base + (size_t)v_islot * v_bytes,
-                 reinterpret_cast<const char *>(Vp) + (size_t)(2 * (ts_base + v_next)) * G.v_row_bytes, bytes, full_v + v_islot);
+                 reinterpret_cast<const char *>(Vp) + (size_t)(2 * (ts_base + v_next) + (WT ? 1 : 0)) * G.v_row_bytes, bytes,
+                 full_v + v_islot);          // forward: packed rows 2 ts, 2 ts + 1 (the rows whose residual the stage completes);
+                                             // WT: rows 2 ts + 1, 2 ts + 2 (the node rows the stage brings in)
         ++v_next;
         if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) vst[2] = vst[2] ^ 1; }
         vst[0] = v_next; vst[1] = v_islot;
     };
-    if (!RHO && tid == 0) {
+    if ((!RHO || WT) && tid == 0) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // the packing kernel's rows (no-op without a dependent launch)
         while (vst[0] < G.nvs && vst[0] < n_local) issue_v();
     }
@@ -387,10 +414,12 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     // ---- per-lane constants of the consumer
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
     const TY *yb = y + b * y_stride;
-    const TA *gp = (g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
-    const int sig_b = (int)(((unsigned long long)(y + (grp_b0 + s) * y_stride + ncol) / EY) & (16 / EY - 1));
+    const TA *gp = (!WT && g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
+    const int sig_b = WT ? 0 : (int)(((unsigned long long)(y + (grp_b0 + s) * y_stride + ncol) / EY) & (16 / EY - 1));
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
-    const unsigned y_lane = G.y_off + (sl * G.y_pitch + (EY == 8 ? 2 * ((sl >> 1) & 1) + 2 : 4) + sig_b + c0) * EY;
+    // (WT: the rows are produced in place, always at an even offset, and read back as 16-byte pieces: consecutive samples
+    //  2 doubles apart modulo 4 make the quarter-warps of those loads conflict-free)
+    const unsigned y_lane = G.y_off + (sl * G.y_pitch + (EY == 8 ? 2 * (WT ? (sl & 1) : ((sl >> 1) & 1)) + 2 : 4) + sig_b + c0) * EY;
     const int y_lane_odd = EY == 4 ? 4 * ((sig_b ^ 2) - sig_b) : 0;   // FP32: odd (global) stages sit at phase sig_b ^ 2
     const unsigned a_lane0 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? 0 : nx * EA);   // pixel row 2 ts
     const unsigned a_lane1 = (sl * G.a_pitch + c0) * EA + (G.sy > 0 ? nx * EA : 0);   // pixel row 2 ts + 1
@@ -398,7 +427,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const unsigned x_lane = G.nstrips * NP * 512 + (q * 4 + k) * 32;
     const int mask_dbl = (G.v_row_bytes - kGrid2MaskBytes) >> 3;          // doubles of a packed row before its masks
     const unsigned m_lane = G.v_row_bytes - kGrid2MaskBytes + 4 * q;
-    const unsigned row_bytes = ncol * EY;
+    const unsigned row_bytes = WT ? nx * 8 : ncol * EY;      // WT: the produced rows sit at pitch nx inside a slot
     const double rh = G.rh;
     const bool rho_wide = RHO && !(m & 1) && !(reinterpret_cast<unsigned long long>(r) & 15ull);
 
@@ -410,6 +439,80 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     for (int j = 0; j < 4; ++j) fvp[j] = 0.0;
 #pragma unroll
     for (int j = 0; j < 5; ++j) ap[j] = 0.0;
+    // WT: this lane's A fragments (sample s of the group, weighting functions 4 ks + k) and the producer of a stage's rows
+    double af[WT ? KS : 1];
+    const unsigned wt_dst = y_lane - 16 * k;                       // columns 16 q + 2 k, + 1 of row 0 of the slot
+    const unsigned vt_lane = (unsigned)(q * 2 * (WT ? KS : 1)) * 256 + lane * 8;   // inside a packed V^T row
+    int v_slot = 0;                  // V stage being consumed and the parity of its full barrier
+    unsigned v_par = 0;
+    // rows of one stage: 2 node rows x 2 n-tiles = 4 independent accumulator chains of KS DMMAs, interleaved; the values
+    // stay in registers (cw) until the stage's slot is free, so the contraction overlaps the wait for the group's other
+    // warps; the V stage is released as soon as its fragments have been read
+    auto wt_compute = [&](double (&cw)[8]) {
+        if constexpr (WT) {
+            mbar_wait(full_v + v_slot, v_par);
+            const unsigned vb = smem_u32(v_base) + v_slot * v_bytes + vt_lane;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cw[i] = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    dmma884(cw[4 * rr], cw[4 * rr + 1], af[ks], lds64(vb + rr * G.v_row_bytes + ks * 256));
+                    dmma884(cw[4 * rr + 2], cw[4 * rr + 3], af[ks], lds64(vb + rr * G.v_row_bytes + (KS + ks) * 256));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_v + v_slot);
+            if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
+        }
+    };
+    auto wt_store = [&](unsigned sb_dst, int slot_i, const double (&cw)[8]) {
+        if constexpr (WT) {
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr) {
+                const unsigned dst = sb_dst + wt_dst + rr * row_bytes;
+                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst), "d"(cw[4 * rr]), "d"(cw[4 * rr + 1]) : "memory");
+                asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(dst + 64), "d"(cw[4 * rr + 2]), "d"(cw[4 * rr + 3]) : "memory");
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(my_full + slot_i);
+        }
+    };
+    if constexpr (WT) {
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+            af[ks] = (b_valid && 4 * ks + k < (int)g_stride) ? (double)__ldg(g + b * g_stride + 4 * ks + k) : 0.0;
+        // node row 0: B fragments from packed row 0 in global memory, through the y slot of stage 0 (its left / right
+        // neighbours belong to other warps of the group), before the stage's own rows are produced
+        {
+            const double *vg = Vp + (vt_lane >> 3);
+            double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                dmma884(c00, c01, af[ks], __ldg(vg + ks * 32));
+                dmma884(c10, c11, af[ks], __ldg(vg + (KS + ks) * 32));
+            }
+            asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(sm0 + wt_dst), "d"(c00), "d"(c01) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(sm0 + wt_dst + 64), "d"(c10), "d"(c11) : "memory");
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) uc[j] = lds64(sm0 + y_lane + 8 * j);
+        ulc = is_left ? 0.0 : lds64(sm0 + y_lane - 8);
+        urc = lds64(sm0 + y_lane + 32);
+        if (is_right) uc[3] = 0.0;
+        __syncthreads();
+        {
+            double cw[8];
+            wt_compute(cw);
+            wt_store(sm0, 0, cw);
+            if (n_local > 1) {
+                wt_compute(cw);
+                wt_store(sm0 + G.stage_bytes, 1, cw);
+            }
+        }
+    } else
     // node row 0 straight from global memory (a range that starts higher up gets its state from the replayed stage)
     if (SPLIT && warm) {
 #pragma unroll
@@ -500,19 +603,19 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         for (int j = 0; j < 5; ++j) ap[j] = an[j];
     };
 
-    int v_slot = 0;                  // V stage being consumed and the parity of its full barrier
-    unsigned v_par = 0;
     for (int lt = 0; lt < n_local; ++lt) {
         const int ts = ts_base + lt;
         const int slot = lt & 1;
         const unsigned par = (lt >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
         const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
-        if (!RHO && tid == 0) {
+        if ((!RHO || WT) && tid == 0) {
             // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
-            while (vst[0] < n_local && vst[0] < lt + G.nvs) {
+            // (WT: the V stage used in this iteration is the one of the a / y stage produced at its end, two ahead)
+            const int vc = WT ? lt + 2 : lt;
+            while (vst[0] < n_local && vst[0] < vc + G.nvs) {
                 if (!mbar_test(empty_v + vst[1], (unsigned)vst[2])) {
-                    if (vst[0] > lt) break;
+                    if (vst[0] > vc) break;
                     mbar_wait(empty_v + vst[1], (unsigned)vst[2]);
                 }
                 issue_v();
@@ -532,8 +635,13 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             if constexpr (!RHO) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(msk_rr) : "r"(vb + m_lane + rr * G.v_row_bytes));
             double un[4], unl, unr, an[5];
             unl = lds_elem<TY>(ya - EY);
+            if constexpr (WT) {
+                const double2 u01 = lds128(ya), u23 = lds128(ya + 16);
+                un[0] = u01.x; un[1] = u01.y; un[2] = u23.x; un[3] = u23.y;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) un[j] = lds_elem<TY>(ya + EY * j);
+                for (int j = 0; j < 4; ++j) un[j] = lds_elem<TY>(ya + EY * j);
+            }
             unr = lds_elem<TY>(ya + 4 * EY);
             const double gv = rr ? gn1 : gn0;
             if (is_left) unl = gv;
@@ -590,11 +698,16 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         if (lane == 0) {
             if (!RHO) mbar_arrive(empty_v + v_slot);
         }
-        if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
+        if constexpr (!WT) {
+            if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
+        }
         if (lt + 2 < n_local) {
+            double cw[WT ? 8 : 1];
+            if constexpr (WT) wt_compute(cw);
             if (G.flags & 1) mbar_spin(my_empty + slot, par);
             else mbar_wait(my_empty + slot, par);
             issue_stage(ts + 2, slot);
+            if constexpr (WT) wt_store(sb, slot, cw);
         }
     }
     // ---- last node row (ny): no pixel row above (SPLIT: the top range only)

@@ -774,3 +774,33 @@ def test_partly_filled_sample_groups_give_the_same_bits(nx, ny, B, dev):
     # against the version-1 kernels as an independent route
     V = T(rng.normal(size=(d, 25)))
     assert rel_err(variants[-1].residual(T(a), T(y), T(g), V).cpu(), plan.variant(GPDE_VO_PATH="v1").residual(T(a), T(y), T(g), V).cpu()) < 1e-11
+
+
+@pytest.mark.parametrize("nx,ny,B", [(64, 64, 229), (32, 32, 70), (16, 8, 300), (16, 2, 9), (64, 4, 33), (128, 16, 21), (64, 2, 1)])
+def test_transposed_application_in_one_kernel(nx, ny, B, dev):
+    """q = K_ff(a) (V s) = Gamma^T s (VirtualObservables.py:663) with the rows of w = s V^T produced inside the marching
+    kernel (WT variant of vo_grid2_kernel; w [B,d] never exists) against the two-kernel route (expansion kernel + marching
+    kernel, GPDE_VO_FUSED_T=0) and the version-1 kernels: every k-step count (m <= 16, <= 28, <= 32), log and conductivity
+    input, FP64 and FP32 I/O, ragged batches, partly filled sample groups; adjointness against the forward residual."""
+    plan, fom, a, y, g, rng = _grid_case(nx, ny, "NDP", B, nx * 5 + ny + B, dev, load=False)
+    two, v1 = plan.variant(GPDE_VO_FUSED_T="0"), plan.variant(GPDE_VO_PATH="v1")
+    part = plan.variant(GPDE_GRID2_SPC=str(8 * (16 // (nx // 16)) - 3))
+    T = lambda t: torch.tensor(t, device=dev)
+    d = fom.dim_out
+    for m in (1, 8, 16, 17, 25, 28, 32):
+        V, sv = T(rng.normal(size=(d, m))), T(rng.normal(size=(B, m)))
+        q = plan.residual_T(T(a), V, sv)
+        assert rel_err(q.cpu(), two.residual_T(T(a), V, sv).cpu()) < 1e-12, m
+        assert rel_err(q.cpu(), v1.residual_T(T(a), V, sv).cpu()) < 1e-11, m
+        assert torch.equal(part.residual_T(T(a), V, sv), q), m
+        q_lin = plan.residual_T(torch.exp(T(a)), V, sv, a_is_log=False)
+        assert rel_err(q_lin.cpu(), q.cpu()) < 1e-12, m
+        q32 = plan.residual_T(torch.exp(T(a)).float(), V.float(), sv.float(), a_is_log=False)
+        assert q32.dtype == torch.float32
+        assert rel_err(q32.double().cpu(), two.residual_T(torch.exp(T(a)).float(), V.float(), sv.float(), a_is_log=False).double().cpu()) < 2e-6, m
+        assert rel_err(plan.residual_T(T(a).float(), V.float(), sv.float()).double().cpu(), q.cpu()) < 1e-5, m
+    # <s, Gamma y> = <Gamma^T s, y> with zero Dirichlet data and no load
+    V, sv = T(rng.normal(size=(d, 25))), T(rng.normal(size=(B, 25)))
+    lhs = (plan.residual(T(a), T(y), None, V, ignore_load=True) * sv).sum(dim=1)
+    rhs = (plan.residual_T(T(a), V, sv) * T(y)).sum(dim=1)
+    assert rel_err(lhs.cpu(), rhs.cpu()) < 1e-11
