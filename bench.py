@@ -641,6 +641,11 @@ def run_b200(args):
     t_adj, _, _, _ = graph_timed(torch, lambda: hp.rom_adjoint(*keep), K)
     t_vo, _, _, _ = graph_timed(torch, hp.vo, K)
     t_vo_other, _, _, _ = graph_timed(torch, lambda: hp.vo(not hp.log_input), K)
+    # the transposed application q = K_ff(a) (V s) = Gamma^T s, the residual's gradient w.r.t. y (VirtualObservables.py:663)
+    t_vo_T = None
+    if w.m <= 32:
+        s_T = torch.randn(B, w.m, dtype=tdt, device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+        t_vo_T, _, _, _ = graph_timed(torch, lambda: hp.vplan.residual_T(d["a"], d["V"], s_T, a_is_log=False), K)
     hp.rom.check()
 
     # ---- (2) the timed region: K steps, each step = the same launches replayed from one CUDA graph (the step is
@@ -814,6 +819,9 @@ def run_b200(args):
             "ms_host_enqueue_per_step": host_enqueue_ms,
             "cgm_hbm_frac": cgm_bytes / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
             "vo_hbm_frac_log_input": w.vo_bytes_per_eval(s) * B / ((t_vo if hp.log_input else t_vo_other) * 1e-3) / 1e9 / peak,
+            "ms_vo_residual_T": t_vo_T,
+            "vo_residual_T_hbm_frac": None if t_vo_T is None else
+            s * (w.P + w.d + w.m) * B / (t_vo_T * 1e-3) / 1e9 / peak,      # a read, q written, s read: w = s V^T stays on the SM
         },
         "roofline": roofline_record(w, B, s, t_vo, hp.path, args.workload, args.dtype, peak, peak_src),
         "gpu_launches": hp.launches_per_step() * K,

@@ -450,7 +450,8 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     // warps; the V stage is released as soon as its fragments have been read
     auto wt_compute = [&](double (&cw)[8]) {
         if constexpr (WT) {
-            mbar_wait(full_v + v_slot, v_par);
+            if (G.flags & 1) mbar_spin(full_v + v_slot, v_par);
+            else mbar_wait(full_v + v_slot, v_par);
             const unsigned vb = smem_u32(v_base) + v_slot * v_bytes + vt_lane;
 #pragma unroll
             for (int i = 0; i < 8; ++i) cw[i] = 0.0;
@@ -609,9 +610,11 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         const unsigned par = (lt >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
         const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
+        // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
+        // (WT: the V stage used in this iteration is the one of the a / y stage produced at its end, two ahead)
+        // (measured on the WT variant: a second refill opportunity per iteration costs 4 %, a ring of 2 stages instead of 3
+        //  6 %: the waits for V rows are the slack of the faster warps, not what limits the kernel)
         if ((!RHO || WT) && tid == 0) {
-            // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
-            // (WT: the V stage used in this iteration is the one of the a / y stage produced at its end, two ahead)
             const int vc = WT ? lt + 2 : lt;
             while (vst[0] < n_local && vst[0] < vc + G.nvs) {
                 if (!mbar_test(empty_v + vst[1], (unsigned)vst[2])) {

@@ -10,6 +10,7 @@ from gpde_b200.VirtualObservables import VoPlan
 from gpde_b200.workloads import Workload
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
+extra = [dict(kv.split("=") for kv in spec.split(",")) for spec in sys.argv[3:]]   # e.g. GPDE_GRID2_FLAGS=2 GPDE_GRID2_NVS=2
 dev = torch.device("cuda", 0)
 w = Workload(name, B=min(B, 4096), seed=0)
 base = VoPlan.cached(w.physics["fom"], dev, pixel_input=True)
@@ -19,6 +20,8 @@ a_log = T(w.log_image).repeat(rep, 1)[:B].contiguous()
 a, V = torch.exp(a_log), T(w.V)
 s = torch.randn(B, w.m, dtype=torch.float64, device=dev)
 plans = {"one kernel": base, "two kernels": base.variant(GPDE_VO_FUSED_T="0")}
+for e in extra:
+    plans["one kernel " + ",".join("%s=%s" % (k[5:], v) for k, v in e.items())] = base.variant(**e)
 ref = plans["two kernels"].residual_T(a, V, s, a_is_log=False)
 err = (plans["one kernel"].residual_T(a, V, s, a_is_log=False) - ref).abs().max() / ref.abs().max()
 print("B %d m %d: one kernel vs two kernels rel err %.2e" % (B, w.m, err.item()))
@@ -43,5 +46,5 @@ def timed(plan, log, f32=False):
 
 for rnd in range(3):
     for label, p in plans.items():
-        print("round %d %-11s: conductivity %.2f us, log input %.2f us, FP32 I/O %.2f us" %
+        print("round %d %-28s: conductivity %.2f us, log input %.2f us, FP32 I/O %.2f us" %
               (rnd, label, timed(p, False), timed(p, True), timed(p, False, True)), flush=True)
