@@ -361,6 +361,19 @@ class HotPath(object):
         return 1 + 1 + self.vplan.launches_per_residual(self.w.m, self.tdt)
 
 
+def calibrate_sm_reserve(torch, hp, K, candidates):
+    """The VO kernel's CTAs own a whole SM each and its last wave is sized for the SMs it may use; the ROM kernels of the
+    overlapped step need a few SMs beside it.  Times one graph of the step per candidate number of SMs left to them
+    (untimed warm-up work), keeps the fastest in ``hp.sm_reserve`` and returns {candidate: ms per step}."""
+    ms = {}
+    if hp.split_pack:
+        for cand in candidates:
+            hp.sm_reserve = cand
+            ms[cand] = graph_timed(torch, lambda: hp.step(overlap=True), K)[0]
+        hp.sm_reserve = min(ms, key=ms.get)
+    return ms
+
+
 def graph_timed(torch, fn, K):
     """Average device milliseconds of ``fn`` over K replays of its CUDA graph (eager launches if capture is refused)."""
     try:
@@ -457,6 +470,7 @@ def sub_record(torch, dist, dev, name, B_total, tdt, K, rank, world, peak, peak_
     t_adj, _, _, _ = graph_timed(torch, lambda: hp.rom_adjoint(*keep), K)
     t_vo, _, _, _ = graph_timed(torch, hp.vo, K)
     t_vo_log, _, _, _ = graph_timed(torch, lambda: hp.vo(True), K)
+    calibrate_sm_reserve(torch, hp, max(5, K), [0, 8, 11, 16])
     _, _, run, mode = graph_timed(torch, lambda: hp.step(overlap=True), 2)
     if world > 1:
         dist.barrier()
@@ -481,7 +495,7 @@ def sub_record(torch, dist, dev, name, B_total, tdt, K, rank, world, peak, peak_
            "ms_rom_forward": t_fwd, "ms_rom_adjoint": t_adj, "ms_vo_residual": t_vo, "ms_vo_residual_log_input": t_vo_log,
            "cgm_solves_per_s": total / ((t_fwd + t_adj) * 1e-3), "vo_evals_per_s": total / (t_vo * 1e-3),
            "cgm_hbm_frac": w.cgm_bytes_per_solve(s) * B / ((t_fwd + t_adj) * 1e-3) / 1e9 / peak,
-           "vo_kernel_path": hp.path,
+           "vo_kernel_path": hp.path, "sms_left_to_rom_kernels": hp.sm_reserve,
            "roofline": roofline_record(w, B, s, t_vo, hp.path, name, "f64" if s == 8 else "f32", peak, peak_src)}
     del hp
     torch.cuda.empty_cache()
@@ -653,11 +667,10 @@ def run_b200(args):
     # The VO kernel's CTAs own a whole SM each and its last wave is sized for the SMs it may use; the ROM kernels of the
     # overlapped step need a few SMs beside it: the number left to them is calibrated here (untimed), one graph per candidate
     reserve_ms = {}
-    if not args.no_overlap and not args.no_graph and hp.split_pack:
-        for cand in ([args.sm_reserve] if args.sm_reserve >= 0 else [0, 8, 11, 16, 20]):
-            hp.sm_reserve = cand
-            reserve_ms[cand] = graph_timed(torch, lambda: hp.step(overlap=True), max(10, min(K, 30)))[0]
-        hp.sm_reserve = min(reserve_ms, key=reserve_ms.get)
+    if args.sm_reserve >= 0:
+        hp.sm_reserve = args.sm_reserve
+    elif not args.no_overlap and not args.no_graph:
+        reserve_ms = calibrate_sm_reserve(torch, hp, max(10, min(K, 30)), [0, 8, 11, 16, 20])
     if args.no_graph:
         run, mode = (lambda: hp.step(overlap=not args.no_overlap)), "eager"
     else:
