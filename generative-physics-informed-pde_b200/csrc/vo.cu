@@ -705,7 +705,7 @@ static int launch_grid2_wt(const gpde_vo_plan *pl, const T *a, long long a_strid
     if (!grid2_setup(pl, 0, true, 0, G, NT, NX, smem, EA, 8)) return 0;
     if (((uintptr_t)a & 15) || ((a_stride * EA) & 15) || ((G.in0 * EA) & 15) || ((G.sy * EA) & 15) || ((uintptr_t)workspace & 15)) return 0;
     const int KS = mw <= 16 ? 4 : (mw <= 28 ? 7 : 8);
-    G.v_row_bytes = G.nstrips * 2 * KS * 256;
+    G.v_row_bytes = G.nstrips * 2 * KS * 256 + kGrid2MaskBytes;
     const size_t fixed = smem;                  // (rho variant: no V stages counted yet)
     G.nvs = (fixed + 3 * 2 * (size_t)G.v_row_bytes <= 227 * 1024) ? 3 : 2;
     if (pl->env.grid2_nvs == 2 || pl->env.grid2_nvs == 3) G.nvs = pl->env.grid2_nvs;
@@ -714,9 +714,9 @@ static int launch_grid2_wt(const gpde_vo_plan *pl, const T *a, long long a_strid
     const int S = 8 * G.groups, d = pl->dev.d;
     double *Vp = (double *)workspace;
     {
-        const long long total = (long long)(G.ny + 1) * (G.v_row_bytes / 8);
-        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)pl->n_sm * 8);
-        vo_grid2_pack_t_kernel<T><<<grid, 256, 0, st>>>(G, V, mw, KS, Vp);
+        const long long warps = (long long)(G.ny + 1) * 8;   // one warp per (node row, strip slot)
+        const unsigned grid = (unsigned)std::min<long long>((warps + 3) / 4, (long long)pl->n_sm * 16);
+        vo_grid2_pack_t_kernel<T><<<grid, 128, 0, st>>>(G, V, mw, KS, Vp);
     }
     G.spc = grid2_samples_per_cta(pl, S, B, 0);
     const unsigned blocks = (unsigned)((B + G.spc - 1) / G.spc);
@@ -1304,7 +1304,7 @@ size_t gpde_vo_workspace_bytes(const gpde_vo_plan *pl, int64_t B, int m) {
     if (pl->grid.ok && m > 0 && m <= 32) {   // packed V (+ the per-row tile masks of the lean kernel)
         need = std::max(need, grid_packed_bytes(pl->grid, 4) + (size_t)(pl->grid.ny + 1) * kGrid2MaskBytes);
         // packed V^T rows of the one-kernel transposed application (launch_grid2_wt): <= 8 k-steps
-        need = std::max(need, (size_t)(pl->grid.ny + 1) * (size_t)((pl->grid.nx + 15) / 16) * 2 * 8 * 256);
+        need = std::max(need, (size_t)(pl->grid.ny + 1) * ((size_t)((pl->grid.nx + 15) / 16) * 2 * 8 * 256 + kGrid2MaskBytes));
     }
     return need;
 }

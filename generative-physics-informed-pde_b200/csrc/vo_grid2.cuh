@@ -72,6 +72,16 @@ __device__ __forceinline__ void mbar_spin(unsigned long long *bar, unsigned pari
             : "memory");
     } while (!done);
 }
+// DMMA under a warp-uniform predicate (straight-line code: a skipped link of an accumulator chain costs an issue slot, no
+// pipe time and no latency; as branches around the DMMAs the same skipping made the WT variant 16 % slower)
+__device__ __forceinline__ void dmma884_if(unsigned on, double &d0, double &d1, double a, double b) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %4, 0;\n\t"
+        "@p mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n\t}"
+        : "+d"(d0), "+d"(d1)
+        : "d"(a), "d"(b), "r"(on));
+}
 __device__ __forceinline__ double2 lds128(unsigned addr) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
@@ -178,15 +188,29 @@ __global__ void vo_grid2_pack_kernel(Grid2Dev G, const TV *__restrict__ V, int m
 // Transposed application (WT variant of the kernel below): V[d,mw] row-major -> per node row t the B fragments of
 // w_row = s V_row^T (mma.sync.m8n8k4.f64: 8 samples x 8 nodes, contraction over the weighting functions):
 //   [strip q][n-tile nt < 2][k-step ks < KS][lane]:  V[t*ncol + 16 q + 8 nt + lane / 4][4 ks + lane % 4]  (0 outside V)
+// then one 32-bit mask per strip (8 words): bit nt * KS + ks set <=> that 8-node x 4-function block of V has a non-zero
+// entry.  The kernel skips the fragment load and the DMMA of an empty block (exact: it only drops products with 0): the
+// coarse-grained-residual sampler's V = W (VirtualObservables.py:297-321) has 4 non-zero functions per node, i.e. 2 - 4 of
+// the 7 k-steps of m = 25.
 template <typename TV>
 __global__ void vo_grid2_pack_t_kernel(Grid2Dev G, const TV *__restrict__ V, int mw, int KS, double *__restrict__ Vp) {
-    const int per_row = G.v_row_bytes / 8;
-    const long long total = (long long)(G.ny + 1) * per_row;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int t = (int)(i / per_row), e = (int)(i - (long long)t * per_row);
-        const int lane = e & 31, ks = (e >> 5) % KS, qn = (e >> 5) / KS;          // qn = 2 q + nt
-        const int c = 8 * qn + (lane >> 2), j = 4 * ks + (lane & 3);
-        Vp[i] = (c < G.ncol && j < mw) ? (double)V[((long long)t * G.ncol + c) * mw + j] : 0.0;
+    const int per_row = G.v_row_bytes / 8, data = per_row - kGrid2MaskBytes / 8;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long w = warp; w < (long long)(G.ny + 1) * 8; w += nwarps) {     // one warp per (node row t, strip slot q)
+        const int t = (int)(w >> 3), q = (int)(w & 7);
+        double *row = Vp + (long long)t * per_row;
+        unsigned bits = 0;
+        if (q < G.nstrips) {
+            for (int c2 = 0; c2 < 2 * KS; ++c2) {                               // c2 = nt * KS + ks
+                const int nt = c2 / KS, ks = c2 - nt * KS;
+                const int c = 16 * q + 8 * nt + (lane >> 2), j = 4 * ks + (lane & 3);
+                const double v = (c < G.ncol && j < mw) ? (double)V[((long long)t * G.ncol + c) * mw + j] : 0.0;
+                row[(q * 2 * KS + c2) * 32 + lane] = v;
+                if (__any_sync(0xffffffffu, v != 0.0)) bits |= 1u << c2;
+            }
+        }
+        if (lane == 0) reinterpret_cast<unsigned *>(row + data)[q] = bits;
     }
 }
 
@@ -453,14 +477,19 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             if (G.flags & 1) mbar_spin(full_v + v_slot, v_par);
             else mbar_wait(full_v + v_slot, v_par);
             const unsigned vb = smem_u32(v_base) + v_slot * v_bytes + vt_lane;
+            unsigned mk[2];                  // non-zero blocks of this strip in the stage's two rows (bit nt * KS + ks)
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(mk[rr]) : "r"(smem_u32(v_base) + v_slot * v_bytes + rr * G.v_row_bytes + m_lane));
 #pragma unroll
             for (int i = 0; i < 8; ++i) cw[i] = 0.0;
 #pragma unroll
             for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
                 for (int rr = 0; rr < 2; ++rr) {
-                    dmma884(cw[4 * rr], cw[4 * rr + 1], af[ks], lds64(vb + rr * G.v_row_bytes + ks * 256));
-                    dmma884(cw[4 * rr + 2], cw[4 * rr + 3], af[ks], lds64(vb + rr * G.v_row_bytes + (KS + ks) * 256));
+                    dmma884_if(mk[rr] & (1u << ks), cw[4 * rr], cw[4 * rr + 1], af[ks], lds64(vb + rr * G.v_row_bytes + ks * 256));
+                    dmma884_if(mk[rr] & (1u << (KS + ks)), cw[4 * rr + 2], cw[4 * rr + 3], af[ks],
+                               lds64(vb + rr * G.v_row_bytes + (KS + ks) * 256));
                 }
             }
             __syncwarp();
@@ -490,7 +519,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
             const double *vg = Vp + (vt_lane >> 3);
             double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
+            for (int ks = 0; ks < KS; ++ks) {      // (zero blocks contribute zeros: no need for the masks here)
                 dmma884(c00, c01, af[ks], __ldg(vg + ks * 32));
                 dmma884(c10, c11, af[ks], __ldg(vg + (KS + ks) * 32));
             }

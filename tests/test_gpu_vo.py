@@ -799,6 +799,20 @@ def test_transposed_application_in_one_kernel(nx, ny, B, dev):
         assert q32.dtype == torch.float32
         assert rel_err(q32.double().cpu(), two.residual_T(torch.exp(T(a)).float(), V.float(), sv.float(), a_is_log=False).double().cpu()) < 2e-6, m
         assert rel_err(plan.residual_T(T(a).float(), V.float(), sv.float()).double().cpu(), q.cpu()) < 1e-5, m
+    # sparse weighting functions: the kernel skips the 8-node x 4-function blocks of V that are zero (masks from the packing
+    # kernel) -- bands of nodes per function (like the coarse mesh's hat functions), scattered entries, an all-zero V
+    for m in (25, 32):
+        sv = T(rng.normal(size=(B, m)))
+        band = np.zeros((d, m))
+        for j in range(m):
+            lo = (j * d) // m
+            band[lo:lo + max(1, d // 6), j] = rng.normal(size=min(d, lo + max(1, d // 6)) - lo)
+        scattered = rng.normal(size=(d, m)) * (rng.uniform(size=(d, m)) < 0.02)
+        for Vs in (band, scattered, np.zeros((d, m))):
+            q = plan.residual_T(T(a), T(Vs), sv)
+            q2 = two.residual_T(T(a), T(Vs), sv)
+            assert torch.equal(q, q2) or rel_err(q.cpu(), q2.cpu()) < 1e-12, m
+            assert torch.equal(part.residual_T(T(a), T(Vs), sv), q), m
     # <s, Gamma y> = <Gamma^T s, y> with zero Dirichlet data and no load
     V, sv = T(rng.normal(size=(d, 25))), T(rng.normal(size=(B, 25)))
     lhs = (plan.residual(T(a), T(y), None, V, ignore_load=True) * sv).sum(dim=1)
