@@ -753,12 +753,12 @@ def run_b200(args):
             cur.wait_stream(out_stream)
 
         Ke = max(3, min(K, 10))
-        for _ in range(3):
+        for _ in range(8):                 # untimed: the allocator's pools of the per-chunk outputs settle
             step_e2e()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        # three timed blocks of Ke steps; the MEDIAN block is reported and all three are listed: the copies share the host's
+        # five timed blocks of Ke steps; the MEDIAN block is reported and all five are listed: the copies share the host's
         # memory system and PCIe root with whatever else runs on the box
         def timed_blocks(n_blocks):
             blocks = []
