@@ -38,7 +38,7 @@ struct Grid2Dev {
     int stage_bytes, v_row_bytes;   // one a/y stage (all samples of the CTA); one packed V row
     int nvs;                        // V stages in the ring (2 or 3)
     int spc;                        // samples a CTA takes (<= 8 groups): group i gets [i spc / groups, (i + 1) spc / groups)
-    int flags;                      // experiment switches (GPDE_GRID2_FLAGS): 1 = poll barriers without nanosleep
+    int flags;                      // experiment switches (GPDE_GRID2_FLAGS): none in use at present
 };
 
 __device__ __forceinline__ void cp_async8_u32(unsigned smem_dst, const void *gmem_src) {
@@ -57,20 +57,6 @@ __device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned pari
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return done != 0;
-}
-// mbar_wait without the back-off between polls
-__device__ __forceinline__ void mbar_spin(unsigned long long *bar, unsigned parity) {
-    const unsigned addr = smem_u32(bar);
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!done);
 }
 // DMMA under a warp-uniform predicate (straight-line code: a skipped link of an accumulator chain costs an issue slot, no
 // pipe time and no latency; as branches around the DMMAs the same skipping made the WT variant 16 % slower)
@@ -414,26 +400,37 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     issue_stage(ts_base, 0);
     if (n_local > 1) issue_stage(ts_base + 1, 1);
 
-    // packed V rows 2 ts, 2 ts + 1 -> V stage (thread 0 only; v_next = next stage to copy, into slot v_islot)
-    // (thread 0's bookkeeping lives in shared memory: three registers less for every thread of the kernel)
-    volatile int *vst = reinterpret_cast<volatile int *>(tab + 256);   // [0] v_next, [1] v_islot, [2] v_ipar
-    if (tid == 0) vst[0] = vst[1] = vst[2] = 0;
-    auto issue_v = [&]() {
-        const unsigned bytes = (unsigned)v_bytes;
-        int v_next = vst[0], v_islot = vst[1];
-        mbar_arrive_expect_tx(full_v + v_islot, bytes);
-        bulk_g2s(v_base + (size_t)v_islot * v_bytes,
-                 reinterpret_cast<const char *>(Vp) + (size_t)(2 * (ts_base + v_next) + (WT ? 1 : 0)) * G.v_row_bytes, bytes,
-                 full_v + v_islot);          // forward: packed rows 2 ts, 2 ts + 1 (the rows whose residual the stage completes);
-                                             // WT: rows 2 ts + 1, 2 ts + 2 (the node rows the stage brings in)
-        ++v_next;
-        if (++v_islot == G.nvs) { v_islot = 0; if (v_next > G.nvs) vst[2] = vst[2] ^ 1; }
-        vst[0] = v_next; vst[1] = v_islot;
+    // Packed V rows -> ring of nvs V stages (forward: packed rows 2 ts, 2 ts + 1, the rows whose residual the stage completes;
+    // WT: rows 2 ts + 1, 2 ts + 2, the node rows the stage brings in).  Thread 0 primes the ring; afterwards the refill is
+    // EVENT-DRIVEN: the warp whose arrival completes a slot's empty phase copies stage j + nvs into it at once -- whoever
+    // observes the completed phase first, elected in stage order through the shared counter v_next.  (Until late in round 2
+    // thread 0 refilled at the top of its own iterations: it found the slot "just about to be released" and so ran one stage
+    // ahead instead of nvs - 1; the warps slept 13 times per stage waiting for V rows.  61.8 -> 59.4 us at config 2.)
+    const unsigned v_next32 = tab32 + 256 * 8;          // shared-memory address of the counter
+    auto copy_v = [&](int j, int slot_) {
+        mbar_arrive_expect_tx(full_v + slot_, (unsigned)v_bytes);
+        bulk_g2s(v_base + (size_t)slot_ * v_bytes,
+                 reinterpret_cast<const char *>(Vp) + (size_t)(2 * (ts_base + j) + (WT ? 1 : 0)) * G.v_row_bytes, (unsigned)v_bytes,
+                 full_v + slot_);
     };
     if ((!RHO || WT) && tid == 0) {
         asm volatile("griddepcontrol.wait;" ::: "memory");   // the packing kernel's rows (no-op without a dependent launch)
-        while (vst[0] < G.nvs && vst[0] < n_local) issue_v();
+        int j = 0;
+        for (; j < G.nvs && j < n_local; ++j) copy_v(j, j);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(v_next32), "r"(j) : "memory");
     }
+    // release of V stage j_done (slot v_slot_, parity v_par_) by this warp's lane 0
+    auto release_v = [&](int j_done, int v_slot_, unsigned v_par_) {
+        mbar_arrive(empty_v + v_slot_);
+        const int j = j_done + G.nvs;
+        if (j < n_local && mbar_test(empty_v + v_slot_, v_par_)) {
+            int cur;
+            do {   // (cur < j: the copy of the stage before is still being issued)
+                asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(cur) : "r"(v_next32), "r"(j), "r"(j + 1) : "memory");
+            } while (cur < j);
+            if (cur == j) copy_v(j, v_slot_);
+        }
+    };
 
     // ---- per-lane constants of the consumer
     const bool is_left = c0 == 0, is_right = c0 == nx - 4;
@@ -472,10 +469,9 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     // rows of one stage: 2 node rows x 2 n-tiles = 4 independent accumulator chains of KS DMMAs, interleaved; the values
     // stay in registers (cw) until the stage's slot is free, so the contraction overlaps the wait for the group's other
     // warps; the V stage is released as soon as its fragments have been read
-    auto wt_compute = [&](double (&cw)[8]) {
+    auto wt_compute = [&](double (&cw)[8], int j_stage) {
         if constexpr (WT) {
-            if (G.flags & 1) mbar_spin(full_v + v_slot, v_par);
-            else mbar_wait(full_v + v_slot, v_par);
+            mbar_wait(full_v + v_slot, v_par);
             const unsigned vb = smem_u32(v_base) + v_slot * v_bytes + vt_lane;
             unsigned mk[2];                  // non-zero blocks of this strip in the stage's two rows (bit nt * KS + ks)
 #pragma unroll
@@ -493,7 +489,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(empty_v + v_slot);
+            if (lane == 0) release_v(j_stage, v_slot, v_par);
             if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
         }
     };
@@ -535,10 +531,10 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         __syncthreads();
         {
             double cw[8];
-            wt_compute(cw);
+            wt_compute(cw, 0);
             wt_store(sm0, 0, cw);
             if (n_local > 1) {
-                wt_compute(cw);
+                wt_compute(cw, 1);
                 wt_store(sm0 + G.stage_bytes, 1, cw);
             }
         }
@@ -639,27 +635,8 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         const unsigned par = (lt >> 1) & 1;
         const unsigned sb = sm0 + slot * G.stage_bytes;
         const unsigned vb = smem_u32(v_base) + v_slot * v_bytes;
-        // refill V stages whose slot every warp has released; never block unless this stage's rows are missing
-        // (WT: the V stage used in this iteration is the one of the a / y stage produced at its end, two ahead)
-        // (measured on the WT variant: a second refill opportunity per iteration costs 4 %, a ring of 2 stages instead of 3
-        //  6 %: the waits for V rows are the slack of the faster warps, not what limits the kernel)
-        if ((!RHO || WT) && tid == 0) {
-            const int vc = WT ? lt + 2 : lt;
-            while (vst[0] < n_local && vst[0] < vc + G.nvs) {
-                if (!mbar_test(empty_v + vst[1], (unsigned)vst[2])) {
-                    if (vst[0] > vc) break;
-                    mbar_wait(empty_v + vst[1], (unsigned)vst[2]);
-                }
-                issue_v();
-            }
-        }
-        if (G.flags & 1) {
-            mbar_spin(my_full + slot, par);
-            if (!RHO) mbar_spin(full_v + v_slot, v_par);
-        } else {
-            mbar_wait(my_full + slot, par);
-            if (!RHO) mbar_wait(full_v + v_slot, v_par);
-        }
+        mbar_wait(my_full + slot, par);
+        if (!RHO) mbar_wait(full_v + v_slot, v_par);
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
             const unsigned ya = sb + y_lane + rr * row_bytes + (EY == 4 && (SPLIT ? (ts & 1) : slot) ? y_lane_odd : 0);
@@ -728,16 +705,15 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         }
         __syncwarp();
         if (lane == 0) {
-            if (!RHO) mbar_arrive(empty_v + v_slot);
+            if (!RHO) release_v(lt, v_slot, v_par);
         }
         if constexpr (!WT) {
             if (++v_slot == G.nvs) { v_slot = 0; v_par ^= 1; }
         }
         if (lt + 2 < n_local) {
             double cw[WT ? 8 : 1];
-            if constexpr (WT) wt_compute(cw);
-            if (G.flags & 1) mbar_spin(my_empty + slot, par);
-            else mbar_wait(my_empty + slot, par);
+            if constexpr (WT) wt_compute(cw, lt + 2);
+            mbar_wait(my_empty + slot, par);
             issue_stage(ts + 2, slot);
             if constexpr (WT) wt_store(sb, slot, cw);
         }
