@@ -269,7 +269,9 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const unsigned tab32 = smem_u32(tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = warp & (G.nstrips - 1), grp = warp >> G.lognstrips;
+    // strip of this warp: rotated by the group index, so that every scheduler (warp % 4) hosts all strips -- the strips'
+    // work differs from node row to node row with the non-zero tiles of V (57.0 against 58.1 us at config 2, A/B)
+    const int grp = warp >> G.lognstrips, q = (warp + grp) & (G.nstrips - 1);
     const int s = lane >> 2, k = lane & 3;
     const int S = 8 * G.groups;
     const int sl = grp * 8 + s;
@@ -299,6 +301,20 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const int ts_base = warm ? s_lo - 1 : s_lo;
     const int n_local = s_hi - ts_base;
     const int gthreads = 32 * G.nstrips;            // threads of one sample group (= 2 nx)
+    const bool is_left = c0 == 0, is_right = c0 == nx - 4;
+    const TY *yb = y + b * y_stride;
+    const TA *gp = (!WT && g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
+    // node row 0 of this lane comes straight from global memory: requested here, consumed after the set-up below (one
+    // exposed DRAM round trip less per CTA: in the profile of a one-wave launch 3.5 % of the warp samples sat behind it)
+    double r0[4] = {0.0, 0.0, 0.0, 0.0}, r0l = 0.0, r0r = 0.0, r0g = 0.0;
+    if (!WT && !warm) {
+        if (gp) r0g = (double)__ldg(gp);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (c0 + j < ncol) r0[j] = (double)__ldg(yb + c0 + j);
+        if (!is_left) r0l = (double)__ldg(yb + c0 - 1);
+        if (c0 + 4 < ncol) r0r = (double)__ldg(yb + c0 + 4);
+    }
 
     // ---- zero the stages (halo reads past a sample's rows must see finite numbers), barriers, exp table
     {
@@ -317,7 +333,9 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 256) tab[tid] = kExp256Tab[tid];
+    if constexpr (ALOG) {
+        if (tid < 256) tab[tid] = kExp256Tab[tid];
+    }
     __syncthreads();
 
     // ---- staging.  Every sample group (8 samples, nstrips warps) runs its OWN two-stage ring of a / y rows with its
@@ -433,9 +451,6 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     };
 
     // ---- per-lane constants of the consumer
-    const bool is_left = c0 == 0, is_right = c0 == nx - 4;
-    const TY *yb = y + b * y_stride;
-    const TA *gp = (!WT && g && (is_left || is_right)) ? g + b * g_stride + (is_right ? 1 : 0) : nullptr;
     const int sig_b = WT ? 0 : (int)(((unsigned long long)(y + (grp_b0 + s) * y_stride + ncol) / EY) & (16 / EY - 1));
     // byte offsets inside a stage of this lane's first column: y row 2 ts + 1, pixel row 2 ts, V pairs
     // (WT: the rows are produced in place, always at an even offset, and read back as 16-byte pieces: consecutive samples
@@ -545,12 +560,11 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
         for (int j = 0; j < 4; ++j) uc[j] = 0.0;
         ulc = urc = 0.0;
     } else {
-        const double g0 = gp ? (double)__ldg(gp) : 0.0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) uc[j] = (c0 + j < ncol) ? (double)__ldg(yb + c0 + j) : 0.0;
-        ulc = is_left ? g0 : (double)__ldg(yb + c0 - 1);
-        urc = (c0 + 4 < ncol) ? (double)__ldg(yb + c0 + 4) : 0.0;
-        if (is_right) uc[3] = g0;
+        for (int j = 0; j < 4; ++j) uc[j] = r0[j];
+        ulc = is_left ? r0g : r0l;
+        urc = r0r;
+        if (is_right) uc[3] = r0g;
     }
     // Dirichlet values of the first stage's node rows 2 ts + 1, 2 ts + 2
     double gn0 = gp ? (double)__ldg(gp + 2 * (2 * ts_base + 1)) : 0.0, gn1 = gp ? (double)__ldg(gp + 2 * (2 * ts_base + 2)) : 0.0;
