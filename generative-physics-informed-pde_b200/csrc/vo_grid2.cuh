@@ -23,6 +23,11 @@
 //   * the I/O element types are template parameters (TA: conductivities and Dirichlet values, TY: y, TR: result): FP32 I/O
 //     stages the rows as floats (half the copies, half the shared memory) and converts when a lane reads its values; the
 //     arithmetic is FP64 in every variant (the reference's model dtype is float32, factories/model.py:181,224).
+//   * the packed V rows travel through a ring of 2-3 stages filled by bulk copies; the refill is event-driven (the warp whose
+//     arrival completes a slot's empty phase issues the next copy), the strips are rotated over the schedulers by the group
+//     index, a CTA may take fewer samples than it has slots (the launcher balances the last wave over the SMs);
+//   * SPLIT: small batches as thread-block clusters that cut the node rows; WT (KS > 0): the transposed application
+//     q = K_ff(a) (V s) with the rows of V s produced by DMMAs inside the kernel (see the comments at the kernel).
 #pragma once
 #include "exp256.cuh"
 
