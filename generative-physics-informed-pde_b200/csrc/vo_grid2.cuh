@@ -274,9 +274,12 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     const unsigned tab32 = smem_u32(tab);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // strip of this warp: rotated by the group index, so that every scheduler (warp % 4) hosts all strips -- the strips'
-    // work differs from node row to node row with the non-zero tiles of V (57.0 against 58.1 us at config 2, A/B)
-    const int grp = warp >> G.lognstrips, q = (warp + grp) & (G.nstrips - 1);
+    // group and strip of this warp.  The warps of a sample group sit on ONE scheduler (warp % 4 for four groups): every
+    // scheduler then hosts all strips -- their work differs from node row to node row with the non-zero tiles of V -- and a
+    // warp that waits for its group leaves its issue slots to the warps it waits for.  (Groups of consecutive warps, one
+    // strip per scheduler: 58.1 us at config 2; the same rotated by the group index: 57.0 us; this: 56.6 us and the
+    // log-input variant 79.6 instead of 82.4 us -- A/Bs on one box each.)
+    const int grp = warp & (G.groups - 1), q = warp >> (4 - G.lognstrips);
     const int s = lane >> 2, k = lane & 3;
     const int S = 8 * G.groups;
     const int sl = grp * 8 + s;
@@ -349,7 +352,7 @@ vo_grid2_kernel(Grid2Dev G, const TA *__restrict__ a, long long a_stride, int a_
     // stages, copied by thread 0).  A sample's two rows of a stage are 2 nx E / 16 pieces of 16 bytes (E = element
     // size): the 2 nx threads of a group copy piece (tg mod pieces) of samples (tg / pieces) + (16 / E) i, i < E / 2
     // (FP64: 4 pieces per thread and array, samples 2 apart; FP32: 2 pieces, samples 4 apart).
-    const int tg = tid & (gthreads - 1);
+    const int tg = q * 32 + lane;                   // thread index inside the sample group
     constexpr int NIA = EA / 2, SSA = 16 / EA, NIY = EY / 2, SSY = 16 / EY;
     const int lpa = G.lognx - (EA == 8 ? 0 : 1), lpy = G.lognx - (EY == 8 ? 0 : 1);   // log2(pieces per sample)
     const int j0a = tg >> lpa, j0 = tg >> lpy;      // first sample (inside the group) this thread copies of a / of y
