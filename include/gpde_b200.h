@@ -217,7 +217,10 @@ int gpde_vo_moments_f64(const gpde_vo_plan *plan, const double *a, int64_t a_str
                         gpde_stream_t stream);
 
 /* q[B,d] = K_ff(a_b) (V s_b) = Gamma_b^T s_b  (VirtualObservables.py:663; with s = P r it is the
- * gradient of 1/2 r^T P r w.r.t. y).  With B = m, s = I and a_stride = 0 it yields Gamma itself. */
+ * gradient of 1/2 r^T P r w.r.t. y).  With B = m, s = I and a_stride = 0 it yields Gamma itself.
+ * On the reference's pixel meshes with m <= 32 this is one kernel (after a small packing launch of V^T): the rows
+ * of V s are produced inside the marching kernel and never reach global memory; `workspace` holds the packed V^T
+ * (or, on the other routes, V s [B,d]): >= gpde_vo_workspace_bytes(plan, B, m), 16-byte aligned. */
 int gpde_vo_residual_T_f64(const gpde_vo_plan *plan, const double *a, int64_t a_stride, int a_is_log,
                            const double *V, int m, const double *s, double *q, void *workspace,
                            int64_t B, gpde_stream_t stream);
