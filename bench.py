@@ -744,13 +744,22 @@ def run_b200(args):
         g_shared = d["g"] if pinned["g"].dim() == 1 else None
         # device-side landing buffers of the copies, allocated once (the caller's staging memory: a fresh allocation per
         # copy goes through the caching allocator with cross-stream reuse rules and showed up as steps of 6 - 45 ms among
-        # steps of 2.6 ms); a step's copies wait for the kernels of the step before (same buffers)
-        landing = {k: torch.empty_like(d[k]) for k in names_all}
-        evs = [torch.cuda.Event() for _ in bounds]
+        # steps of 2.6 ms).  Two sets, used alternately: the copies of step k + 1 run while step k computes, and wait only for
+        # the kernels of step k - 1 (the last user of their set) -- the host-to-device link never idles between steps
+        landing2 = [{k: torch.empty_like(d[k]) for k in names_all} for _ in range(2)]
+        evs2 = [[torch.cuda.Event() for _ in bounds] for _ in range(2)]
+        set_free = [torch.cuda.Event() for _ in range(2)]
+        state = {"n": 0}
 
         def step_e2e():
             cur = torch.cuda.current_stream(dev)
-            copy_stream.wait_stream(cur)
+            which = state["n"] & 1
+            landing, evs = landing2[which], evs2[which]
+            if state["n"] >= 2:
+                copy_stream.wait_event(set_free[which])
+            else:
+                copy_stream.wait_stream(cur)
+            state["n"] += 1
             staged = []
             with torch.cuda.stream(copy_stream):         # all H2D copies are enqueued first, on the copy stream
                 for (lo, hi), ev in zip(bounds, evs):
@@ -774,6 +783,7 @@ def run_b200(args):
                 outs["u"][lo:hi].copy_(uu.detach(), non_blocking=True)
                 outs["gX"][lo:hi].copy_(lX.grad, non_blocking=True)
                 outs["r"][lo:hi].copy_(rr, non_blocking=True)
+            set_free[which].record(cur)
 
         Ke = max(3, min(K, 10))
         for _ in range(8):                 # untimed: the allocator's pools of the per-chunk outputs settle
